@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""bench.py - CTR train samples/sec on synthetic Criteo-shaped data (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c2|c3] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch: encode -> fused gather+FM+first-order front end ->
+MLP (cuBLAS) -> loss -> backward -> deterministic sparse scatter-add -> fresh-optimizer update.
+
+Default workload (config.workload) = C5: DeepFM, 26 sparse fields x 10 M rows x k=64 fp32 tables (the C4 tables,
+66.6 GB, row-sharded over the ranks), 13 dense, batch 65 536 per GPU (weak scaling), deep tower (32, 32) (the
+reference's DeepFM default), uniform ids.  Other workloads: c2 = DCN 6 cross + 3x400 MLP k=16 B=4096,
+c3 = xDeepFM CIN 200-200-200 k=16 B=8192.
+
+One JSON line on stdout (rank 0).  `value` = device-timed whole-job samples/s with inputs resident in HBM;
+`e2e` = the same through the public call with pinned HOST buffers (H2D + D2H loss inside the timed region).
+`--impl reference` times the CPU oracle (the only runnable "reference CPU path", see oracle/__init__.py).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+WORKLOADS = {
+    # name: model, fields, rows/table, k, n_dense, per-GPU batch, extra
+    "c5": dict(model="DeepFM", m=26, rows=10_000_000, k=64, n_dense=13, batch=65536, deep=(32, 32),
+               desc="C5 DeepFM fwd+bwd+opt, 26 x 10M x k=64 fp32 tables (C4), B=65536/GPU, deterministic scatter-add"),
+    "c2": dict(model="DCN", m=26, rows=1_000_000, k=16, n_dense=13, batch=4096, deep=(400, 400, 400), cross=6,
+               desc="C2 DCN 6 cross + 3x400 MLP, 26 x 1M x k=16, B=4096"),
+    "c3": dict(model="xDeepFM", m=26, rows=1_000_000, k=16, n_dense=13, batch=8192, deep=(400, 400),
+               cin=(200, 200, 200), desc="C3 xDeepFM CIN 200-200-200 + DNN, 26 x 1M x k=16, B=8192"),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=None, help="rows per table (override)")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (override)")
+    ap.add_argument("--k", type=int, default=None)
+    ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="do not CUDA-graph the step")
+    ap.add_argument("--cin-precision", default="3xtf32")
+    ap.add_argument("--cpu-batch", type=int, default=8192)
+    ap.add_argument("--cpu-rows", type=int, default=100_000)
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------- data
+def make_ids(rng: np.random.RandomState, B, m, rows, dist):
+    if dist == "uniform":
+        return rng.randint(0, rows, size=(B, m)).astype(np.int64)
+    z = rng.zipf(1.05, size=(B, m)).astype(np.int64) - 1
+    return z % rows
+
+
+def make_batch(seed, B, m, rows, n_dense, dist):
+    rng = np.random.RandomState(seed)
+    ids = make_ids(rng, B, m, rows, dist)
+    dense = rng.randn(B, n_dense).astype(np.float32)
+    y = (rng.rand(B) < 0.25).astype(np.float32)
+    return ids, dense, y
+
+
+# --------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------- our arm
+def build_model(w, args, world, rank):
+    from recman_b200.th import DCN, DeepFM, xDeepFM
+    from recman_b200.th.input import DenseFeat, FeatureDictionary, SparseFeat
+
+    rows = args.rows or w["rows"]
+    k = args.k or w["k"]
+    fd = FeatureDictionary()
+    for i in range(w["m"]):
+        fd[f"C{i}"] = SparseFeat(f"C{i}", rows - 1, encoder=False)
+    for j in range(w["n_dense"]):
+        fd[f"I{j}"] = DenseFeat(f"I{j}", scaler=False)
+    B = args.batch or w["batch"]
+    common = dict(embedding_size=k, embedding_l2_reg=0.0, linear_l2_reg=0.0, batch_size=B, learning_rate=1e-3,
+                  optimizer="adam")
+    if w["model"] == "DeepFM":
+        model = DeepFM(fd, deep_hidden_units=w["deep"], deep_dropout=(1.0,) * (len(w["deep"]) + 1), deep_l2_reg=0.0,
+                       **common)
+    elif w["model"] == "DCN":
+        model = DCN(fd, deep_hidden_units=w["deep"], deep_dropout=(1.0,) * (len(w["deep"]) + 1),
+                    cross_layer_num=w["cross"], **common)
+    else:
+        from recman_b200.th.layers import leaky_relu
+
+        hp = dict(embedding_size=k, embedding_l2_reg=0.0, linear_l2_reg=0.0, deep_hidden_units=w["deep"],
+                  deep_dropout=(1.0,) * (len(w["deep"]) + 1), deep_l2_reg=0.0, cin_cross_layer_units=list(w["cin"]),
+                  cin_dropout=[1] * (len(w["cin"]) + 1), cin_l2_reg=0.0, learning_rate=1e-3, optimizer="adam",
+                  cin_precision=args.cin_precision, deep_activation=leaky_relu, cin_activation=leaky_relu)
+        model = xDeepFM(fd, hp, batch_size=B)
+    return model, fd, rows, k, B
+
+
+def algorithmic_bytes(kind, B, m, k, n_dense, n_unique=None):
+    """Algorithmic HBM bytes per launch."""
+    if kind == "rm_gather_fm_fwd":
+        # ids 8 + row read 4k + row write 4k + bias 4 + lin 4 per (b,f); dense read+write; S write; 2 logits
+        return B * (m * (8 + 8 * k + 8) + 8 * n_dense + 4 * k + 8)
+    if kind == "rm_emb_fm_bwd":
+        # per id: position 4 + dx row 4k + x row 4k; S row + 2 scalars per sample; per unique row: 4k + 2*4 written
+        nu = n_unique if n_unique is not None else B * m
+        return B * m * (4 + 8 * k) + B * (4 * k + 8) + nu * (4 * k + 8)
+    if kind == "rm_sparse_opt_step":
+        nu = n_unique if n_unique is not None else B * m
+        return nu * (8 + 12 * k)
+    return None
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = WORKLOADS[args.workload]
+    from recman_b200 import ops
+    from recman_b200.th.input import DataInputs
+
+    if world > 1:
+        from recman_b200.th import dist as rdist
+
+        model, fd, rows, k, B = build_model(w, args, world, rank)
+        rdist.shard_model(model, world, rank)
+    else:
+        model, fd, rows, k, B = build_model(w, args, world, rank)
+    m, n_dense = w["m"], w["n_dense"]
+
+    # rotating pool of distinct batches (ids differ per step so nothing is served from L2 by repetition)
+    NB = 8
+    host = [make_batch(2019 + 1000 * rank + i, B, m, rows, n_dense, args.ids) for i in range(NB)]
+    pinned = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory(), torch.from_numpy(c).pin_memory())
+              for a, b, c in host]
+    resident = [DataInputs.from_tensors(fd, a.to(dev), b.to(dev), c.to(dev)) for a, b, c in pinned]
+
+    def step_resident(i):
+        return model.fit_on_batch(resident[i % NB], None)
+
+    def step_e2e(i):
+        a, b, c = pinned[i % NB]
+        inputs = DataInputs.from_tensors(fd, a.to(dev, non_blocking=True), b.to(dev, non_blocking=True),
+                                         c.to(dev, non_blocking=True))
+        loss = model.fit_on_batch(inputs, None)
+        return float(loss.item())  # D2H read of the step's result
+
+    # ---- warm-up (also creates the variables) ----
+    for i in range(args.warmup):
+        step_resident(i)
+    torch.cuda.synchronize()
+    model.check_ids()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms, wall], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.enable_profile()
+    launches0 = ops.launch_count()
+    ms_total, wall_total = timed(step_resident, args.steps)
+    launches = ops.launch_count() - launches0
+    prof = ops.disable_profile()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = B * world / (ms_step * 1e-3)
+
+    # ---- e2e: pinned host buffers -> H2D -> step -> D2H loss ----
+    for i in range(2):
+        step_e2e(i)
+    e2e_ms, e2e_wall = timed(step_e2e, args.steps)
+    e2e_ms_step = max(e2e_ms, e2e_wall) / args.steps  # includes the host wait for the D2H read
+    e2e_value = B * world / (e2e_ms_step * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in pinned[0])
+
+    out = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        n_unique = int(np.unique(host[0][0] + (np.arange(m, dtype=np.int64) * rows)[None, :]).size)
+        kernels = {}
+        for name, (total_ms, count) in prof.items():
+            avg = total_ms / max(count, 1)
+            ab = algorithmic_bytes(name, B, m, k, n_dense, n_unique)
+            kernels[name] = {"avg_ms": round(avg, 4), "launches": count, "ms_per_step": round(total_ms / args.steps, 4),
+                             "alg_bytes": ab, "gbs": (round(ab / (avg * 1e-3) / 1e9, 1) if ab and avg > 0 else None)}
+        cand = [(v["ms_per_step"], n) for n, v in kernels.items() if v["alg_bytes"]]
+        roofline = None
+        if cand:
+            _, dom = max(cand)
+            kv = kernels[dom]
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": kv["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                        "frac": round(kv["gbs"] / hbm_peak, 4), "frac_of_nominal_8000": round(kv["gbs"] / 8000.0, 4),
+                        "peak_source": peak_src, "traffic": None, "avg_launch_ms": kv["avg_ms"],
+                        "alg_bytes_per_launch": kv["alg_bytes"]}
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cpu = cpu_baseline(args, w, steps=3, warmup=1)
+        out = {
+            "metric": "CTR train samples/sec", "value": round(value, 1), "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "model": w["model"], "fields": m, "rows_per_table": rows, "k": k,
+                       "n_dense": n_dense, "batch_per_gpu": B, "global_batch": B * world, "ids": args.ids,
+                       "optimizer": "adam (fresh per batch, as the reference)", "l2_flush":
+                       "inputs larger than L2: tables %.1f GB, 8 rotating id batches" % (m * rows * k * 4 / 1e9),
+                       "parallelism": ("single GPU" if world == 1 else f"row-sharded tables x{world} + DP dense")},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "ms_per_step": round(e2e_ms_step, 4),
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "kernels": kernels,
+            "cpu_baseline": cpu,
+            "wall_ms_per_step": round(wall_total / args.steps, 4),
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+# --------------------------------------------------------------------------------------- CPU oracle arm
+def cpu_baseline(args, w, steps=3, warmup=1):
+    """The torch-CPU oracle doing the same DeepFM/DCN/xDeepFM fwd+bwd(+sparse update) on a bounded sample."""
+    import oracle
+
+    torch.manual_seed(2019)
+    m, n_dense = w["m"], w["n_dense"]
+    k = args.k or w["k"]
+    rows = min(args.cpu_rows, args.rows or w["rows"])
+    B = min(args.cpu_batch, args.batch or w["batch"])
+    cores = torch.get_num_threads()
+    g = torch.Generator().manual_seed(2020)
+    table = torch.randn(m * rows, k, generator=g) * 0.01
+    offs = np.arange(m + 1, dtype=np.int64) * rows
+    bias_t = torch.zeros(m * rows)
+    lin_t = torch.zeros(m * rows)
+    d = m * k + n_dense
+    deep = list(w["deep"])
+    dims = [d] + deep
+    Ws = [(torch.randn(dims[i], dims[i + 1], generator=g) * 0.05).requires_grad_() for i in range(len(deep))]
+    bs = [torch.zeros(dims[i + 1], requires_grad=True) for i in range(len(deep))]
+    w_out = (torch.randn(deep[-1], 1, generator=g) * 0.05).requires_grad_()
+    w0 = torch.zeros(1, requires_grad=True)
+    extra = []
+    if w["model"] == "DCN":
+        L = w["cross"]
+        cw = (torch.randn(L, d, generator=g) * 0.05).requires_grad_()
+        cb = torch.zeros(L, d, requires_grad=True)
+        co = (torch.randn(d, 1, generator=g) * 0.05).requires_grad_()
+        c0 = torch.zeros(1, requires_grad=True)
+        extra = [cw, cb, co, c0]
+    if w["model"] == "xDeepFM":
+        shapes, final = oracle.cin_layer_shapes(m, w["cin"])
+        filt = [(torch.randn(*s, generator=g) * 0.05).requires_grad_() for s in shapes]
+        fb = [torch.zeros(s[-1], requires_grad=True) for s in shapes]
+        cin_w = (torch.randn(final, 1, generator=g) * 0.05).requires_grad_()
+        cin_w0 = torch.zeros(1, requires_grad=True)
+        extra = filt + fb + [cin_w, cin_w0]
+    dense_params = Ws + bs + [w_out, w0] + extra
+    lr = 1e-3
+
+    def step(i):
+        ids, dense, y = make_batch(7 + i, B, m, rows, n_dense, args.ids)
+        keys = oracle.global_rows(ids, offs)
+        kt = torch.from_numpy(keys)
+        e = table[kt].requires_grad_()  # [B, m, k] gathered rows (A1-A3)
+        bias = bias_t[kt].unsqueeze(-1).requires_grad_()
+        linv = lin_t[kt].requires_grad_()
+        dn = torch.from_numpy(dense)
+        lin_logit = linv.sum(1, keepdim=True)
+        if w["model"] == "DeepFM":
+            logit = oracle.deepfm_logit(e, bias, lin_logit, dn, (Ws, bs, w_out, w0), oracle.relu)
+        elif w["model"] == "DCN":
+            logit = oracle.dcn_logit(e, lin_logit, dn, (Ws, bs, w_out, w0), tuple(extra), oracle.relu)
+        else:
+            nl = len(w["cin"])
+            logit = oracle.xdeepfm_logit(e, lin_logit, dn, (Ws, bs, w_out, w0), (extra[:nl], extra[nl:2 * nl], extra[-2], extra[-1]))
+        loss = oracle.create_loss(torch.from_numpy(y), oracle.prediction(logit), "classification")
+        loss.backward()
+        # A4: deterministic segment sum of the embedding gradient, then the fresh-optimizer update on touched rows
+        uniq, sums, _, _ = oracle.segment_sum_sorted(keys.reshape(-1), e.grad.reshape(-1, k).numpy())
+        ut = torch.from_numpy(uniq)
+        table[ut] = oracle.fresh_optimizer_step(table[ut], torch.from_numpy(sums), "adam", lr)
+        with torch.no_grad():
+            for p in dense_params:
+                if p.grad is not None:
+                    p.copy_(oracle.fresh_optimizer_step(p, p.grad, "adam", lr))
+                    p.grad = None
+        return float(loss)
+
+    for i in range(warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(warmup + i)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": round(B / dt, 1), "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} steps of B={B} (same model; tables {m} x {rows} x k={k} to bound host RAM), "
+                      f"torch-CPU oracle fwd+bwd + numpy segment-sum + sparse update, {dt * 1e3:.1f} ms/step",
+            "cpu_model": _cpu_model(), "ms_per_step": round(dt * 1e3, 2)}
+
+
+def _cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    steps = max(1, min(args.steps, 10))
+    cpu = cpu_baseline(args, w, steps=steps, warmup=max(1, min(args.warmup, 2)))
+    rows = args.rows or w["rows"]
+    k = args.k or w["k"]
+    B = args.batch or w["batch"]
+    out = {
+        "impl": "reference", "metric": "CTR train samples/sec", "value": cpu["value"], "unit": "samples/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": args.warmup,
+        "ms_per_step": cpu["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "model": w["model"], "fields": w["m"], "rows_per_table": rows, "k": k,
+                   "n_dense": w["n_dense"], "batch_per_gpu": B, "ids": args.ids},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,216 @@
+/*
+ * recman_b200.h - C ABI of librecman_b200.so: the B200 (sm_100a) kernels behind
+ * the recman.th CTR hot path.
+ *
+ * The reference (dev-wei/recman) has no FFI / plugin / operator registry: its
+ * only boundary is the Python layer vocabulary of recman/tf/core/layers.py,
+ * whose numerical backend is TensorFlow library ops.  Every entry point below
+ * therefore cites the reference *call site* whose TF op(s) it replaces
+ * (file:line under the reference tree).  INTEGRATION.md shows the ctypes
+ * binding a recman maintainer would add.
+ *
+ * Conventions
+ *   - plain `extern "C"`, raw pointers + explicit sizes/strides, no torch types;
+ *   - every pointer is a DEVICE pointer unless its comment says "host";
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - the caller owns every buffer including workspaces (`*_workspace_bytes`
+ *     queries); no hidden allocation, no hidden synchronisation, no global
+ *     mutable state -> thread-safe per (stream, workspace);
+ *   - return value: 0 = ok, >0 = cudaError_t, <0 = RM_E_* below;
+ *     `rm_last_error()` returns a thread-local message for the last failure;
+ *   - there is no CPU path and no other-architecture path: `rm_device_check`
+ *     refuses anything but compute capability 10.x.
+ *   - all floating point is IEEE fp32 (no fast-math), ids are int64 as in the
+ *     reference (tf/inputs.py:158).
+ */
+#ifndef RECMAN_B200_H_
+#define RECMAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RM_ABI_VERSION 1
+
+#define RM_E_INVALID (-1)     /* bad argument (null pointer, negative size, ...) */
+#define RM_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
+#define RM_E_ARCH (-3)        /* device is not sm_100 */
+#define RM_E_WORKSPACE (-4)   /* workspace too small */
+
+/* optimizer kinds: tf/core/utils.py:201-213 (create_optimizer) */
+#define RM_OPT_ADAM 0
+#define RM_OPT_ADAGRAD 1
+#define RM_OPT_GD 2
+
+/* activation kinds for rm_cin_* : hparams/xDeepFM.py:29,33 (tf.nn.leaky_relu, alpha 0.2) */
+#define RM_ACT_IDENTITY 0
+#define RM_ACT_RELU 1
+#define RM_ACT_LEAKY_RELU 2
+
+/* CIN contraction precision: tcgen05 has no fp32 MMA. */
+#define RM_CIN_FP32_SIMT 0 /* CUDA-core fp32 FMA (verification path)             */
+#define RM_CIN_3XTF32 1    /* tcgen05 kind::tf32, hi/lo split, 3 MMAs (parity)   */
+#define RM_CIN_TF32 2      /* tcgen05 kind::tf32 single pass (fast, ~1e-3)        */
+
+int rm_version(void);
+const char* rm_last_error(void);
+/* 0 when `device` is a compute-capability-10.x GPU, RM_E_ARCH otherwise. */
+int rm_device_check(int device);
+/* Kernels launched by this library in this process so far (every own <<<>>> site
+ * counts 1, every cub:: device primitive call counts 1).  bench.py's gpu_launches. */
+int64_t rm_launch_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * K1  multi-table embedding gather (forward)
+ * replaces: tf.nn.embedding_lookup per field + tf.concat(axis=1)
+ *           recman/tf/core/layers.py:117-128 and :238-261
+ * All m tables live in one [total_rows, k] array; field f owns rows
+ * [table_offsets[f], table_offsets[f+1]).  out[b*out_stride + f*k + c] =
+ * table[table_offsets[f] + ids[b*m+f]][c].  One launch for all fields; the
+ * concat is never materialised separately.  k == 1 is the bias / first-order
+ * weight lookup (layers.py:124-128, :418-439).
+ * An id outside its table writes zeros and sets *status != 0 (status may be NULL).
+ * ------------------------------------------------------------------------- */
+int rm_gather_fwd(const float* table, const int64_t* table_offsets, const int64_t* ids,
+                  int64_t B, int32_t m, int32_t k, float* out, int64_t out_stride,
+                  int32_t* status, void* stream);
+
+/* K1 pooled variant: tf.nn.embedding_lookup_sparse(combiner="sqrtn")
+ * recman/tf/core/layers.py:144-169.  CSR: sample b pools
+ * values[offsets[b]..offsets[b+1]) of the table starting at row `row_offset`
+ * with `table_rows` rows: out[b*out_stride + c] = sum_j row_j[c] / sqrt(n_b)
+ * (n_b == 0 -> zeros), accumulated in CSR order. */
+int rm_gather_pooled_fwd(const float* table, int64_t row_offset, int64_t table_rows,
+                         const int64_t* values, const int64_t* offsets, int64_t B, int32_t k,
+                         float* out, int64_t out_stride, int32_t* status, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * K3  FM layer: recman/tf/core/layers.py:457-478 (FMLayer.__call__)
+ * embeds[b*ld + f*k + c], bias[b*m + f] (NULL = no first-order term).
+ * out[b] = sum_f bias + 0.5*sum_c[(sum_f e)^2 - sum_f e^2];
+ * sum_out (nullable) [B,k] receives sum_f e for the backward.
+ * ------------------------------------------------------------------------- */
+int rm_fm_fwd(const float* embeds, int64_t ld, const float* bias, int64_t B, int32_t m, int32_t k,
+              float* out, float* sum_out, void* stream);
+/* backward: d_embeds[b,f,:] (+)= gout[b]*(S[b,:] - e[b,f,:]); d_bias[b,f] = gout[b].
+ * `sum` may be NULL (S is recomputed).  accumulate != 0 adds into d_embeds. */
+int rm_fm_bwd(const float* embeds, int64_t ld, const float* sum, const float* gout, int64_t B,
+              int32_t m, int32_t k, float* d_embeds, int64_t d_ld, float* d_bias, int32_t accumulate,
+              void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * K1+K3 fused DeepFM front end (recman/tf/core/DeepFM.py:107-140):
+ * gather all fields into the DNN input row  x[b] = [e_0 .. e_{m-1} | dense]
+ * (DNNCombiner, layers.py:494-501), and from the rows still in registers
+ * produce the FM logit (layers.py:457-478, bias term from `bias_table`
+ * [total_rows] if non-NULL) and the first-order linear logit
+ * sum_f lin_table[row] + sum_j dense[b,j]*lin_dense[j]  (layers.py:330-347).
+ * Nullable: bias_table, lin_table, dense/lin_dense (n_dense = 0), fm_out,
+ * lin_out, sum_out.  x row stride `ld` >= m*k + n_dense.
+ * ------------------------------------------------------------------------- */
+int rm_gather_fm_fwd(const float* table, const float* bias_table, const float* lin_table,
+                     const int64_t* table_offsets, const int64_t* ids, const float* dense,
+                     const float* lin_dense, int32_t n_dense, int64_t B, int32_t m, int32_t k,
+                     float* x, int64_t ld, float* fm_out, float* lin_out, float* sum_out,
+                     int32_t* status, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * K2  deterministic sparse embedding-gradient scatter-add
+ * replaces: TF autodiff of tf.nn.embedding_lookup (IndexedSlices with duplicate
+ *           rows summed) for recman/tf/core/layers.py:117-128.
+ * Step 1 (plan, depends on ids only): key[p] = table_offsets[p % m] + ids[p]
+ * (table_offsets NULL -> key = ids[p]); stable radix sort of (key, p); run-length
+ * encode.  Outputs: sorted_pos[N], seg_start[N+1] (first n_unique+1 valid),
+ * uniq_rows[N] ascending (first n_unique valid), n_unique[1].
+ * Step 2 (reduce): out_rows[u,:] = sum over j in segment u, ascending position,
+ * of grad[(p/m)*ld + (p%m)*k + :], p = sorted_pos[j] - a fixed order, no atomics.
+ * N = B*m < 2^31, total_rows < 2^32.
+ * ------------------------------------------------------------------------- */
+size_t rm_segment_plan_workspace_bytes(int64_t N);
+int rm_segment_plan(const int64_t* ids, const int64_t* table_offsets, int64_t N, int32_t m,
+                    int64_t total_rows, void* workspace, size_t workspace_bytes,
+                    int32_t* sorted_pos, int32_t* seg_start, int64_t* uniq_rows, int32_t* n_unique,
+                    void* stream);
+int rm_segment_reduce(const float* grad, int64_t ld, int32_t m, int32_t k, int64_t N,
+                      const int32_t* sorted_pos, const int32_t* seg_start, const int32_t* n_unique,
+                      float* out_rows, void* stream);
+
+/* Fused DeepFM embedding backward: the gradient row of position p=(b,f) is
+ *   dx[b*ld + f*k + :] + g_fm[b] * (S[b,:] - x[b*ld + f*k + :])      (FM bwd, A5b)
+ * and the k=1 tables (FM bias, linear weight) both receive g_fm[b] / g_lin[b].
+ * Segment sums go to out_rows [n_unique,k], out_bias[n_unique], out_lin[n_unique]
+ * (each nullable).  dx may be NULL (no DNN), g_fm NULL (no FM). */
+int rm_emb_fm_bwd(const float* dx, const float* x, int64_t ld, const float* sum, const float* g_fm,
+                  const float* g_lin, int32_t m, int32_t k, int64_t N, const int32_t* sorted_pos,
+                  const int32_t* seg_start, const int32_t* n_unique, float* out_rows, float* out_bias,
+                  float* out_lin, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * K4  DCN cross network.  Call site recman/tf/core/DCN.py:135-137 (the class
+ * itself is absent from the reference; arithmetic = arXiv 1708.05123 eq. 3):
+ *   x_{l+1} = x0*(x_l . w[l]) + b[l] + x_l,  logit = x_L . w_out + w0_out
+ * x[b*ld + :d]; w,b [L,d]; w_out [d]; w0_out [1]; logit [B];
+ * dots [B,L] receives s_l = x_l . w_l (saved for the backward).  d <= 2048.
+ * ------------------------------------------------------------------------- */
+int rm_cross_fwd(const float* x, int64_t ld, const float* w, const float* b, const float* w_out,
+                 const float* w0_out, int64_t B, int32_t d, int32_t L, float* logit, float* dots,
+                 void* stream);
+/* backward.  gout [B].  dx[b*d_ld + :d] (+)= dL/dx.  Parameter gradients are
+ * batch-reduced in a fixed order (per-block partials in `workspace`, then one
+ * ordered pass): dw, db [L,d]; dw_out [d]; dw0_out [1]. */
+size_t rm_cross_bwd_workspace_bytes(int64_t B, int32_t d, int32_t L);
+int rm_cross_bwd(const float* x, int64_t ld, const float* w, const float* b, const float* w_out,
+                 const float* dots, const float* gout, int64_t B, int32_t d, int32_t L, float* dx,
+                 int64_t d_ld, int32_t accumulate, float* dw, float* db, float* dw_out,
+                 float* dw0_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * K5  CIN layer: recman/tf/core/layers.py:711-751 (one iteration of the loop)
+ *   Z[(b,d),(p,q)] = x0[b,p,d] * xk[b,q,d]           (outer product, p-major)
+ *   F = act(Z . W + bias),  W [m*H, N]               (conv1d 1x1 == GEMM)
+ *   out[b, n, d] = F[(b,d), n]                       (transpose to [B,N,D])
+ * x0[b*x0_bstride + p*D + d], xk[b*xk_bstride + q*D + d] (both may be views into
+ * wider rows: x0 into the front-end row buffer, xk into the previous layer's
+ * [B,N,D] output).  Z is never materialised.  `pre` (nullable) receives the pre-activation
+ * [B,N,D] for the backward.  The split-half / sum-pool / cin_w head stay in
+ * torch (views and a tiny GEMV).
+ * ------------------------------------------------------------------------- */
+int rm_cin_layer_fwd(const float* x0, int64_t x0_bstride, const float* xk, int64_t xk_bstride, const float* W,
+                     const float* bias, int64_t B, int32_t m, int32_t H, int32_t D, int32_t N,
+                     int32_t act, int32_t precision, float* out, float* pre, void* workspace,
+                     size_t workspace_bytes, void* stream);
+size_t rm_cin_layer_workspace_bytes(int64_t B, int32_t m, int32_t H, int32_t D, int32_t N,
+                                    int32_t precision);
+/* backward of one CIN layer.  dout [B,N,D] is dL/d(out); pre as saved.
+ * dW [m*H,N], dbias [N] are batch-reduced deterministically;
+ * dx0 [B,m,D] is accumulated (+=) (x0 feeds every layer), dxk [B,H,D]
+ * (batch stride dxk_bstride) is written. */
+int rm_cin_layer_bwd(const float* x0, int64_t x0_bstride, const float* xk, int64_t xk_bstride, const float* W,
+                     const float* pre, const float* dout, int64_t B, int32_t m, int32_t H,
+                     int32_t D, int32_t N, int32_t act, int32_t precision, float* dW, float* dbias,
+                     float* dx0, float* dxk, int64_t dxk_bstride, void* workspace,
+                     size_t workspace_bytes, void* stream);
+size_t rm_cin_layer_bwd_workspace_bytes(int64_t B, int32_t m, int32_t H, int32_t D, int32_t N,
+                                        int32_t precision);
+
+/* ------------------------------------------------------------------------- *
+ * N1  optimizer step on K2's (rows, sums) output and on dense parameters.
+ * The reference constructs a NEW optimizer every batch
+ * (recman/tf/core/xDeepFM.py:116-126) so every step is a first step with
+ * zero slots; the kernels implement exactly that (oracle.fresh_optimizer_step).
+ * Sparse: for u < *n_unique: table[uniq_rows[u], :] <- step(., rows[u,:] + l2*table).
+ * Dense:  p[i] <- step(p[i], g[i] + l2*p[i]).
+ * ------------------------------------------------------------------------- */
+int rm_sparse_opt_step(float* table, int32_t k, const int64_t* uniq_rows, const float* rows,
+                       const int32_t* n_unique, int64_t max_rows, int32_t opt, float lr, float l2,
+                       void* stream);
+int rm_dense_opt_step(float* p, const float* g, int64_t n, int32_t opt, float lr, float l2,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECMAN_B200_H_ */

@@ -1,0 +1,297 @@
+"""torch.autograd.Function shells around the C-ABI kernels.
+
+Embedding-table gradients never become dense tensors: K2 (sort -> segment sum) produces
+``ops.SparseGrad`` objects that are attached to the table parameter (``param.rm_sparse_grads``) and the
+autograd engine receives ``None`` for the table.  The dense part of a table gradient, if any (the
+reference's whole-table L2 term, layers.py:188-193), flows through ordinary autograd into ``param.grad``.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import torch
+from torch.autograd import Function
+
+from . import _C, ops
+
+
+def attach_sparse_grad(param: torch.Tensor, sg: ops.SparseGrad) -> None:
+    lst = getattr(param, "rm_sparse_grads", None)
+    if lst is None:
+        lst = []
+        param.rm_sparse_grads = lst
+    lst.append(sg)
+
+
+def pop_sparse_grads(param: torch.Tensor) -> List[ops.SparseGrad]:
+    lst = getattr(param, "rm_sparse_grads", None) or []
+    param.rm_sparse_grads = []
+    return lst
+
+
+def dense_table_grad(param: torch.Tensor, consume: bool = False) -> torch.Tensor:
+    """Dense view of everything a table received this step (tests, small tables): param.grad + scattered rows."""
+    total = param.shape[0]
+    out = torch.zeros(total, param.numel() // total, dtype=param.dtype, device=param.device)
+    if param.grad is not None:
+        out += param.grad.reshape(total, -1)
+    for sg in (pop_sparse_grads(param) if consume else getattr(param, "rm_sparse_grads", None) or []):
+        out += sg.to_dense(total)
+    return out.reshape(param.shape)
+
+
+# --------------------------------------------------------------------------- #
+# embedding layer (A1-A4)
+# --------------------------------------------------------------------------- #
+@dataclass
+class SparseRun:
+    """A run of consecutive one-hot fields: output columns [col, col+n), id columns [id_col, id_col+n)."""
+
+    col: int
+    n: int
+    id_col: int
+    offsets: torch.Tensor  # int64 [n+1] device: global row offset of each field's table
+
+
+@dataclass
+class MultiField:
+    col: int
+    row_offset: int
+    rows: int
+    csr_index: int  # which (values, offsets) pair
+
+
+@dataclass
+class EmbeddingLayout:
+    m: int
+    k: int
+    total_rows: int
+    runs: List[SparseRun] = field(default_factory=list)
+    multi: List[MultiField] = field(default_factory=list)
+
+
+def _run_ids(sparse_ids: torch.Tensor, run: SparseRun) -> torch.Tensor:
+    if run.id_col == 0 and run.n == sparse_ids.shape[1]:
+        return sparse_ids if sparse_ids.is_contiguous() else sparse_ids.contiguous()
+    return sparse_ids[:, run.id_col : run.id_col + run.n].contiguous()
+
+
+def _expand_csr(values, offsets, B):
+    counts = offsets[1:] - offsets[:-1]
+    sample = torch.repeat_interleave(torch.arange(B, device=values.device), counts)
+    scale = torch.rsqrt(counts.clamp_min(1).to(torch.float32))
+    return sample, scale[sample]
+
+
+class EmbeddingLayerFunction(Function):
+    """FeatEmbeddingLayer: all fields -> embeds [B,m,k] (+ bias [B,m]); backward = deterministic scatter-add."""
+
+    @staticmethod
+    def forward(ctx, table, bias_table, layout: EmbeddingLayout, status, sparse_ids, *csr):
+        B = sparse_ids.shape[0] if sparse_ids is not None else csr[1].numel() - 1
+        m, k = layout.m, layout.k
+        out = torch.empty(B, m * k, dtype=torch.float32, device=table.device)
+        bias_out = torch.empty(B, m, dtype=torch.float32, device=table.device) if bias_table is not None else None
+        run_ids = []
+        for run in layout.runs:
+            ids = _run_ids(sparse_ids, run)
+            run_ids.append(ids)
+            ops.gather(table, run.offsets, ids, out=out[:, run.col * k :], status=status)
+            if bias_out is not None:
+                ops.gather(bias_table.reshape(-1, 1), run.offsets, ids, out=bias_out[:, run.col :], status=status)
+        for mf in layout.multi:
+            values, offsets = csr[2 * mf.csr_index], csr[2 * mf.csr_index + 1]
+            ops.gather_pooled(table, mf.row_offset, mf.rows, values, offsets, out=out[:, mf.col * k :], status=status)
+            if bias_out is not None:
+                ops.gather_pooled(bias_table.reshape(-1, 1), mf.row_offset, mf.rows, values, offsets,
+                                  out=bias_out[:, mf.col :], status=status)
+        ctx.layout = layout
+        ctx.table = table
+        ctx.bias_table = bias_table
+        ctx.run_ids = run_ids
+        ctx.csr = csr
+        ctx.B = B
+        embeds = out.view(B, m, k)
+        if bias_out is None:
+            return embeds
+        return embeds, bias_out.view(B, m, 1)
+
+    @staticmethod
+    def backward(ctx, g_embeds, g_bias=None):
+        layout: EmbeddingLayout = ctx.layout
+        B, m, k = ctx.B, layout.m, layout.k
+        table, bias_table = ctx.table, ctx.bias_table
+        ge = g_embeds.reshape(B, m * k)
+        if not ge.is_contiguous():
+            ge = ge.contiguous()
+        gb = None
+        if g_bias is not None and bias_table is not None:
+            gb = g_bias.reshape(B, m)
+            if not gb.is_contiguous():
+                gb = gb.contiguous()
+        for run, ids in zip(layout.runs, ctx.run_ids):
+            plan = ops.segment_plan(ids, run.offsets, layout.total_rows)
+            rows = ops.segment_reduce(ge[:, run.col * k :], plan, k, ld=m * k)
+            attach_sparse_grad(table, ops.SparseGrad(plan.uniq_rows, rows, plan.n_unique))
+            if gb is not None:
+                brow = ops.segment_reduce(gb[:, run.col :], plan, 1, ld=m)
+                attach_sparse_grad(bias_table, ops.SparseGrad(plan.uniq_rows, brow.reshape(-1), plan.n_unique))
+        for mf in layout.multi:
+            values, offsets = ctx.csr[2 * mf.csr_index], ctx.csr[2 * mf.csr_index + 1]
+            if values.numel() == 0:
+                continue
+            sample, scale = _expand_csr(values, offsets, B)
+            keys = (values + mf.row_offset).contiguous()
+            plan = ops.segment_plan(keys, None, layout.total_rows)
+            grows = (ge[:, mf.col * k : (mf.col + 1) * k][sample] * scale[:, None]).contiguous()
+            rows = ops.segment_reduce(grows, plan, k, ld=k)
+            attach_sparse_grad(table, ops.SparseGrad(plan.uniq_rows, rows, plan.n_unique))
+            if gb is not None:
+                brows = (gb[:, mf.col][sample] * scale).contiguous()
+                brow = ops.segment_reduce(brows, plan, 1, ld=1)
+                attach_sparse_grad(bias_table, ops.SparseGrad(plan.uniq_rows, brow.reshape(-1), plan.n_unique))
+        return (None,) * (5 + len(ctx.csr))
+
+
+# --------------------------------------------------------------------------- #
+# FM (A5)
+# --------------------------------------------------------------------------- #
+class FMFunction(Function):
+    @staticmethod
+    def forward(ctx, embeds, bias):
+        out, S = ops.fm_fwd(embeds, bias)
+        ctx.save_for_backward(embeds, S)
+        ctx.has_bias = bias is not None
+        ctx.bias_shape = None if bias is None else bias.shape
+        return out.reshape(-1, 1)
+
+    @staticmethod
+    def backward(ctx, gout):
+        embeds, S = ctx.saved_tensors
+        de, dbias = ops.fm_bwd(embeds, S, gout.reshape(-1).contiguous(), want_bias=ctx.has_bias)
+        return de, (dbias.reshape(ctx.bias_shape) if ctx.has_bias else None)
+
+
+# --------------------------------------------------------------------------- #
+# cross network (A6)
+# --------------------------------------------------------------------------- #
+class CrossFunction(Function):
+    """x may be a padded row buffer [B, ld] of which the first d columns are the input (d=None: all)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, w_out, w0_out, d=None):
+        xin = x if d is None else x[:, :d]
+        logit, dots = ops.cross_fwd(xin, w, b, w_out.reshape(-1), w0_out)
+        ctx.save_for_backward(x, w, b, w_out, dots)
+        ctx.d = d
+        return logit.reshape(-1, 1)
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, w, b, w_out, dots = ctx.saved_tensors
+        d = ctx.d
+        xin = x if d is None else x[:, :d]
+        dx_full = torch.empty_like(x, memory_format=torch.contiguous_format)
+        dx_view = dx_full if d is None else dx_full[:, :d]
+        if d is not None and x.shape[1] > d:
+            dx_full[:, d:].zero_()
+        _, dw, db, dwo, dw0 = ops.cross_bwd(xin, w, b, w_out.reshape(-1), dots, gout.reshape(-1).contiguous(),
+                                            dx=dx_view, accumulate=False)
+        return dx_full, dw, db, dwo.reshape(w_out.shape), dw0, None
+
+
+# --------------------------------------------------------------------------- #
+# CIN layer (A7)
+# --------------------------------------------------------------------------- #
+class CINLayerFunction(Function):
+    """One CIN layer: (x0 [B,m,D], xk [B,H,D], W [m*H,N], bias [N]) -> act(Z.W + bias) as [B,N,D]."""
+
+    @staticmethod
+    def forward(ctx, x0, xk, W, bias, act, precision):
+        out, pre = ops.cin_layer_fwd(x0, xk, W, bias, act, precision, want_pre=True)
+        ctx.save_for_backward(x0, xk, W, pre)
+        ctx.act, ctx.precision = act, precision
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x0, xk, W, pre = ctx.saved_tensors
+        dx0 = torch.zeros_like(x0, memory_format=torch.contiguous_format)
+        dxk = torch.empty(xk.shape, dtype=xk.dtype, device=xk.device)
+        dW, dbias = ops.cin_layer_bwd(x0, xk, W, pre, dout, ctx.act, ctx.precision, dx0, dxk)
+        return dx0, dxk, dW, dbias, None, None
+
+
+# --------------------------------------------------------------------------- #
+# fused DeepFM / DCN / xDeepFM front end (K1 + K3 + first-order, one launch)
+# --------------------------------------------------------------------------- #
+class FrontEndFunction(Function):
+    """ids -> (xbuf [B, ld] = [embeds | dense | 0-pad], fm [B,1], lin [B,1]).
+
+    ``xbuf`` rows are 16-byte aligned (ld % 4 == 0); consumers read ``xbuf[:, :d]``.  Backward takes
+    d(xbuf) [B, ld] (only the first m*k columns are used), d(fm), d(lin) and runs the fused K2.
+
+    ``lin_table`` / ``lin_dense`` are (detached) views of the ``linear_w`` parameter ``W_lin`` - id rows in the
+    embedding table's row numbering, then one weight per dense feature.  Their gradients go back to
+    ``W_lin`` itself: sparse rows for the id part, ``W_lin.rm_dense_tail = (first_row, grad)`` for the tail.
+    """
+
+    @staticmethod
+    def forward(ctx, table, bias_table, W_lin, lin_table, lin_dense, offsets, total_rows, status, ids, dense):
+        x, fm, lin, S = ops.gather_fm_fwd(table, bias_table, lin_table, offsets, ids, dense, lin_dense, status=status)
+        ctx.table, ctx.bias_table, ctx.W_lin = table, bias_table, W_lin
+        ctx.has_lin = lin_table is not None
+        ctx.n_lin_dense = 0 if lin_dense is None else lin_dense.numel()
+        ctx.total_rows = total_rows
+        ctx.save_for_backward(x, S, ids, offsets, dense)
+        ctx.set_materialize_grads(False)
+        return x, fm.reshape(-1, 1), lin.reshape(-1, 1)
+
+    @staticmethod
+    def backward(ctx, dx, dfm, dlin):
+        x, S, ids, offsets, dense = ctx.saved_tensors
+        k = ctx.table.shape[1]
+        ld = x.shape[1]
+        plan = ops.segment_plan(ids, offsets, ctx.total_rows)
+        if dx is not None and (dx.stride(1) != 1 or dx.stride(0) != ld):
+            dx = dx.contiguous()
+        g_fm = None if dfm is None else dfm.reshape(-1).contiguous()
+        g_lin = None if dlin is None else dlin.reshape(-1).contiguous()
+        want_bias = ctx.bias_table is not None and g_fm is not None
+        want_lin = ctx.has_lin and g_lin is not None
+        rows, ob, ol = ops.emb_fm_bwd(dx, x, ld, S, g_fm, g_lin if want_lin else None, plan, k, True, want_bias,
+                                      want_lin)
+        attach_sparse_grad(ctx.table, ops.SparseGrad(plan.uniq_rows, rows, plan.n_unique))
+        if want_bias:
+            attach_sparse_grad(ctx.bias_table, ops.SparseGrad(plan.uniq_rows, ob, plan.n_unique))
+        if want_lin and ctx.W_lin is not None:
+            attach_sparse_grad(ctx.W_lin, ops.SparseGrad(plan.uniq_rows, ol, plan.n_unique))
+            if ctx.n_lin_dense and dense is not None:
+                ctx.W_lin.rm_dense_tail = (ctx.total_rows, dense.t() @ g_lin)
+        return (None,) * 10
+
+
+class FirstLinearFunction(Function):
+    """y = xbuf[:, :d] @ W + b with the input gradient written straight into a padded [B, ld] buffer."""
+
+    @staticmethod
+    def forward(ctx, xbuf, W, b, d):
+        x = xbuf[:, :d]
+        ctx.save_for_backward(xbuf, W)
+        ctx.d = d
+        return torch.addmm(b, x, W)
+
+    @staticmethod
+    def backward(ctx, g):
+        xbuf, W = ctx.saved_tensors
+        d = ctx.d
+        g = g.contiguous()
+        dW = xbuf[:, :d].t() @ g
+        db = g.sum(0)
+        dxbuf = torch.empty_like(xbuf)
+        torch.mm(g, W.t(), out=dxbuf[:, :d])
+        if xbuf.shape[1] > d:
+            dxbuf[:, d:].zero_()
+        return dxbuf, dW, db, None

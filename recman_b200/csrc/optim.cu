@@ -1,0 +1,120 @@
+// N1: optimizer step on K2's (unique rows, summed gradient rows) output and on
+// dense parameters.  The reference builds a NEW optimizer inside every
+// fit_on_batch (recman/tf/core/xDeepFM.py:116-126 -> create_optimizer,
+// recman/tf/core/utils.py:201-213), so every step is a first step with zero
+// slot variables; these kernels implement exactly that stateless update
+// (oracle.fresh_optimizer_step) and touch only the rows that received gradient.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace rm {
+
+struct OptParams {
+  int opt;
+  float lr;    // plain learning rate (adagrad, gd)
+  float lr_t;  // adam: lr*sqrt(1-b2)/(1-b1)
+  float l2;
+};
+
+__device__ __forceinline__ float opt_update(float p, float g, const OptParams& o) {
+  g += o.l2 * p;
+  if (o.opt == RM_OPT_ADAM) {
+    const float m = 0.1f * g;             // (1 - beta1) * g, beta1 = 0.9
+    const float v = 0.001f * g * g;       // (1 - beta2) * g^2, beta2 = 0.999
+    return p - o.lr_t * m / (sqrtf(v) + 1e-7f);
+  } else if (o.opt == RM_OPT_ADAGRAD) {
+    const float acc = 0.1f + g * g;       // initial_accumulator_value = 0.1
+    return p - o.lr * g / (sqrtf(acc) + 1e-7f);
+  }
+  return p - o.lr * g;                    // gd / fresh momentum
+}
+
+__global__ void __launch_bounds__(256) sparse_opt_kernel(float* __restrict__ table, int k,
+                                                         const int64_t* __restrict__ uniq_rows,
+                                                         const float* __restrict__ rows,
+                                                         const int32_t* __restrict__ n_unique, OptParams o) {
+  const int64_t total = (int64_t)(*n_unique) * k;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t u = i / k;
+    const int c = (int)(i - u * k);
+    float* p = table + uniq_rows[u] * (int64_t)k + c;
+    *p = opt_update(*p, rows[i], o);
+  }
+}
+
+__global__ void __launch_bounds__(256) sparse_opt_vec_kernel(float* __restrict__ table, int k4,
+                                                             const int64_t* __restrict__ uniq_rows,
+                                                             const float* __restrict__ rows,
+                                                             const int32_t* __restrict__ n_unique, OptParams o) {
+  const int64_t total = (int64_t)(*n_unique) * k4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t u = i / k4;
+    const int c = (int)(i - u * k4);
+    float* p = table + (uniq_rows[u] * (int64_t)k4 + c) * 4;
+    float4 pv = ld4(p);
+    const float4 g = ld4(rows + i * 4);
+    pv.x = opt_update(pv.x, g.x, o);
+    pv.y = opt_update(pv.y, g.y, o);
+    pv.z = opt_update(pv.z, g.z, o);
+    pv.w = opt_update(pv.w, g.w, o);
+    st4(p, pv);
+  }
+}
+
+__global__ void __launch_bounds__(256) dense_opt_kernel(float* __restrict__ p, const float* __restrict__ g, int64_t n,
+                                                        OptParams o) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = opt_update(p[i], g[i], o);
+}
+
+static int make_params(int opt, float lr, float l2, OptParams* o) {
+  if (opt != RM_OPT_ADAM && opt != RM_OPT_ADAGRAD && opt != RM_OPT_GD) {
+    set_error("unknown optimizer kind %d", opt);
+    return RM_E_INVALID;
+  }
+  o->opt = opt;
+  o->lr = lr;
+  o->lr_t = (float)((double)lr * sqrt(1.0 - 0.999) / (1.0 - 0.9));
+  o->l2 = l2;
+  return 0;
+}
+
+}  // namespace rm
+
+extern "C" {
+
+int rm_sparse_opt_step(float* table, int32_t k, const int64_t* uniq_rows, const float* rows, const int32_t* n_unique,
+                       int64_t max_rows, int32_t opt, float lr, float l2, void* stream) {
+  using namespace rm;
+  RM_CHECK_ARG(table && uniq_rows && rows && n_unique, "null pointer");
+  RM_CHECK_ARG(k > 0 && max_rows >= 0, "bad shape");
+  OptParams o;
+  int rc = make_params(opt, lr, l2, &o);
+  if (rc) return rc;
+  if (max_rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (k % 4 == 0 && aligned16(table) && aligned16(rows)) {
+    sparse_opt_vec_kernel<<<grid_for(max_rows * (k / 4), 256, 8), 256, 0, st>>>(table, k / 4, uniq_rows, rows, n_unique,
+                                                                               o);
+  } else {
+    sparse_opt_kernel<<<grid_for(max_rows * k, 256, 8), 256, 0, st>>>(table, k, uniq_rows, rows, n_unique, o);
+  }
+  RM_LAUNCH_CHECK();
+  return 0;
+}
+
+int rm_dense_opt_step(float* p, const float* g, int64_t n, int32_t opt, float lr, float l2, void* stream) {
+  using namespace rm;
+  RM_CHECK_ARG(p && g, "null pointer");
+  RM_CHECK_ARG(n >= 0, "bad shape");
+  OptParams o;
+  int rc = make_params(opt, lr, l2, &o);
+  if (rc) return rc;
+  if (n == 0) return 0;
+  dense_opt_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(p, g, n, o);
+  RM_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,360 @@
+"""torch-facing wrappers over the C ABI (``recman_b200._C``).
+
+PyTorch is plumbing here: it owns device memory and streams; every hot op is a
+hand-written sm_100a kernel reached through ``librecman_b200.so``.  There is no
+fallback: tensors that are not on a CUDA device raise.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _C
+
+_checked_devices = set()
+
+
+def _dev_check(t: torch.Tensor) -> None:
+    if not t.is_cuda:
+        raise _C.RecmanB200Error("recman_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if idx not in _checked_devices:
+        _C.call("rm_device_check", idx)
+        _checked_devices.add(idx)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t
+
+
+def _rows_view(t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
+    """Accept a 2-D/3-D tensor whose rows are dense; returns (tensor, row stride in floats)."""
+    _f32c(t, name)
+    if t.dim() == 3:
+        if t.stride(2) != 1 or t.stride(1) != t.shape[2]:
+            t = t.contiguous()
+        return t, t.stride(0)
+    if t.dim() == 2:
+        if t.stride(1) != 1:
+            t = t.contiguous()
+        return t, t.stride(0)
+    raise ValueError(f"{name} must be 2-D or 3-D")
+
+
+def enable_profile():
+    _C.enable_profile()
+
+
+def disable_profile():
+    return _C.disable_profile()
+
+
+def launch_count() -> int:
+    return int(_C.lib.rm_launch_count())
+
+
+def new_status(device) -> torch.Tensor:
+    return torch.zeros(1, dtype=torch.int32, device=device)
+
+
+# --------------------------------------------------------------------------- #
+# K1 gather
+# --------------------------------------------------------------------------- #
+def gather(table, table_offsets, ids, out=None, status=None):
+    """[total_rows,k] table, int64 ids [B,m] -> [B, m, k] (or into ``out`` [B, >=m*k])."""
+    _dev_check(table)
+    _f32c(table, "table")
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and table.is_contiguous()
+    assert table_offsets.dtype == torch.int64 and table_offsets.is_cuda
+    B, m = ids.shape
+    k = table.shape[1]
+    if out is None:
+        out = torch.empty(B, m, k, dtype=torch.float32, device=table.device)
+        stride = m * k
+    else:
+        assert out.dim() == 2 and out.stride(1) == 1
+        stride = out.stride(0)
+    _C.call("rm_gather_fwd", _p(table), _p(table_offsets), _p(ids), B, m, k, _p(out), stride, _p(status), _stream())
+    return out
+
+
+def gather_pooled(table, row_offset, table_rows, values, offsets, out=None, status=None):
+    """sqrtn-pooled CSR lookup -> [B, k]."""
+    _dev_check(table)
+    assert values.dtype == torch.int64 and offsets.dtype == torch.int64
+    B = offsets.numel() - 1
+    k = table.shape[1]
+    if out is None:
+        out = torch.empty(B, k, dtype=torch.float32, device=table.device)
+    assert out.stride(-1) == 1
+    _C.call(
+        "rm_gather_pooled_fwd", _p(table), int(row_offset), int(table_rows), _p(values), _p(offsets), B, k, _p(out),
+        out.stride(0), _p(status), _stream(),
+    )
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# K3 FM
+# --------------------------------------------------------------------------- #
+def fm_fwd(embeds, bias=None, want_sum=True):
+    _dev_check(embeds)
+    e, ld = _rows_view(embeds, "embeds")
+    B, m, k = embeds.shape
+    out = torch.empty(B, dtype=torch.float32, device=e.device)
+    S = torch.empty(B, k, dtype=torch.float32, device=e.device) if want_sum else None
+    if bias is not None:
+        bias = _f32c(bias, "bias").reshape(B, m).contiguous()
+    _C.call("rm_fm_fwd", _p(e), ld, _p(bias), B, m, k, _p(out), _p(S), _stream())
+    return out, S
+
+
+def fm_bwd(embeds, S, gout, d_embeds=None, want_bias=True, accumulate=False):
+    _dev_check(embeds)
+    e, ld = _rows_view(embeds, "embeds")
+    B, m, k = embeds.shape
+    if d_embeds is None:
+        d_embeds = torch.empty(B, m, k, dtype=torch.float32, device=e.device)
+        accumulate = False
+    de, d_ld = _rows_view(d_embeds, "d_embeds")
+    assert de.data_ptr() == d_embeds.data_ptr(), "d_embeds must have dense rows"
+    d_bias = torch.empty(B, m, dtype=torch.float32, device=e.device) if want_bias else None
+    gout = gout.reshape(B).contiguous()
+    _C.call("rm_fm_bwd", _p(e), ld, _p(S), _p(gout), B, m, k, _p(de), d_ld, _p(d_bias), int(accumulate), _stream())
+    return d_embeds, d_bias
+
+
+def gather_fm_fwd(table, bias_table, lin_table, table_offsets, ids, dense, lin_dense, ld=None, status=None):
+    """Fused DeepFM front end.  Returns (x_buf [B, ld], fm [B], lin [B], S [B,k])."""
+    _dev_check(table)
+    B, m = ids.shape
+    k = table.shape[1]
+    n_dense = 0 if dense is None else dense.shape[1]
+    d = m * k + n_dense
+    if ld is None:
+        ld = (d + 3) // 4 * 4
+    dev = table.device
+    x = torch.empty(B, ld, dtype=torch.float32, device=dev)
+    if ld > d:
+        x[:, d:].zero_()
+    fm = torch.empty(B, dtype=torch.float32, device=dev)
+    lin = torch.empty(B, dtype=torch.float32, device=dev)
+    S = torch.empty(B, k, dtype=torch.float32, device=dev)
+    if dense is not None:
+        dense = _f32c(dense, "dense").contiguous()
+    _C.call(
+        "rm_gather_fm_fwd", _p(table), _p(bias_table), _p(lin_table), _p(table_offsets), _p(ids), _p(dense),
+        _p(lin_dense), n_dense, B, m, k, _p(x), ld, _p(fm), _p(lin), _p(S), _p(status), _stream(),
+    )
+    return x, fm, lin, S
+
+
+# --------------------------------------------------------------------------- #
+# K2 deterministic scatter-add
+# --------------------------------------------------------------------------- #
+@dataclass
+class SegmentPlan:
+    """sort + run-length-encode of the (table,row) keys of one batch (ids only)."""
+
+    N: int
+    m: int
+    sorted_pos: torch.Tensor  # int32 [N]
+    seg_start: torch.Tensor  # int32 [N+1]
+    uniq_rows: torch.Tensor  # int64 [N]
+    n_unique: torch.Tensor  # int32 [1] (device)
+    workspace: torch.Tensor
+
+    def num_unique(self) -> int:
+        return int(self.n_unique.item())  # host sync: tests / densify only
+
+
+def segment_plan(ids, table_offsets, total_rows) -> SegmentPlan:
+    _dev_check(ids)
+    assert ids.dtype == torch.int64 and ids.is_contiguous()
+    if ids.dim() == 2:
+        B, m = ids.shape
+    else:
+        B, m = ids.numel(), 1
+    N = B * m
+    dev = ids.device
+    ws_bytes = _C.lib.rm_segment_plan_workspace_bytes(N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    sorted_pos = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+    seg_start = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    uniq_rows = torch.empty(max(N, 1), dtype=torch.int64, device=dev)
+    n_unique = torch.empty(1, dtype=torch.int32, device=dev)
+    _C.call(
+        "rm_segment_plan", _p(ids), _p(table_offsets), N, m, int(total_rows), _p(ws), ws_bytes, _p(sorted_pos),
+        _p(seg_start), _p(uniq_rows), _p(n_unique), _stream(),
+    )
+    return SegmentPlan(N, m, sorted_pos, seg_start, uniq_rows, n_unique, ws)
+
+
+def segment_reduce(grad, plan: SegmentPlan, k: int, ld: Optional[int] = None, out_rows=None):
+    """grad rows addressed as grad[(p//m)*ld + (p%m)*k] -> summed rows [N, k] (first n_unique valid)."""
+    _dev_check(grad)
+    _f32c(grad, "grad")
+    if ld is None:
+        g2 = grad.reshape(-1, plan.m * k)
+        grad = g2 if g2.is_contiguous() else g2.contiguous()
+        ld = plan.m * k
+    if out_rows is None:
+        out_rows = torch.empty(max(plan.N, 1), k, dtype=torch.float32, device=grad.device)
+    _C.call(
+        "rm_segment_reduce", _p(grad), ld, plan.m, k, plan.N, _p(plan.sorted_pos), _p(plan.seg_start),
+        _p(plan.n_unique), _p(out_rows), _stream(),
+    )
+    return out_rows
+
+
+def emb_fm_bwd(dx, x, ld, S, g_fm, g_lin, plan: SegmentPlan, k, want_rows=True, want_bias=False, want_lin=False):
+    dev = plan.sorted_pos.device
+    n = max(plan.N, 1)
+    out_rows = torch.empty(n, k, dtype=torch.float32, device=dev) if want_rows else None
+    out_bias = torch.empty(n, dtype=torch.float32, device=dev) if want_bias else None
+    out_lin = torch.empty(n, dtype=torch.float32, device=dev) if want_lin else None
+    _C.call(
+        "rm_emb_fm_bwd", _p(dx), _p(x), ld, _p(S), _p(g_fm), _p(g_lin), plan.m, k, plan.N, _p(plan.sorted_pos),
+        _p(plan.seg_start), _p(plan.n_unique), _p(out_rows), _p(out_bias), _p(out_lin), _stream(),
+    )
+    return out_rows, out_bias, out_lin
+
+
+@dataclass
+class SparseGrad:
+    """K2's output for one table: rows ``uniq_rows[:n]`` received ``rows[:n]``."""
+
+    uniq_rows: torch.Tensor
+    rows: torch.Tensor  # [N, k] or [N] for k == 1 tables
+    n_unique: torch.Tensor
+
+    def to_dense(self, total_rows: int) -> torch.Tensor:
+        n = int(self.n_unique.item())
+        rows = self.rows[:n].reshape(n, -1)
+        out = torch.zeros(total_rows, rows.shape[1], dtype=rows.dtype, device=rows.device)
+        out.index_copy_(0, self.uniq_rows[:n], rows)
+        return out
+
+
+# --------------------------------------------------------------------------- #
+# K4 cross network
+# --------------------------------------------------------------------------- #
+def cross_fwd(x, w, b, w_out, w0_out):
+    _dev_check(x)
+    x, ld = _rows_view(x, "x")
+    B, d = x.shape
+    L = w.shape[0]
+    logit = torch.empty(B, dtype=torch.float32, device=x.device)
+    dots = torch.empty(B, max(L, 1), dtype=torch.float32, device=x.device)
+    _C.call(
+        "rm_cross_fwd", _p(x), ld, _p(w.contiguous()), _p(b.contiguous()), _p(w_out.contiguous()), _p(w0_out), B, d, L,
+        _p(logit), _p(dots), _stream(),
+    )
+    return logit, dots
+
+
+def cross_bwd(x, w, b, w_out, dots, gout, dx=None, accumulate=False):
+    _dev_check(x)
+    x, ld = _rows_view(x, "x")
+    B, d = x.shape
+    L = w.shape[0]
+    dev = x.device
+    if dx is None:
+        dx = torch.empty(B, d, dtype=torch.float32, device=dev)
+        accumulate = False
+    assert dx.stride(1) == 1
+    dw = torch.empty(L, d, dtype=torch.float32, device=dev)
+    db = torch.empty(L, d, dtype=torch.float32, device=dev)
+    dw_out = torch.empty(d, dtype=torch.float32, device=dev)
+    dw0 = torch.empty(1, dtype=torch.float32, device=dev)
+    ws_bytes = _C.lib.rm_cross_bwd_workspace_bytes(B, d, L)
+    ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+    gout = gout.reshape(B).contiguous()
+    _C.call(
+        "rm_cross_bwd", _p(x), ld, _p(w.contiguous()), _p(b.contiguous()), _p(w_out.contiguous()), _p(dots), _p(gout),
+        B, d, L, _p(dx), dx.stride(0), int(accumulate), _p(dw), _p(db), _p(dw_out), _p(dw0), _p(ws), ws_bytes,
+        _stream(),
+    )
+    return dx, dw, db, dw_out, dw0
+
+
+# --------------------------------------------------------------------------- #
+# K5 CIN layer
+# --------------------------------------------------------------------------- #
+def cin_layer_fwd(x0, xk, W, bias, act: int, precision: int, want_pre=True):
+    """x0 [B,m,D], xk [B,H,D] (rows dense, batch stride free), W [m*H, N] -> out [B,N,D], pre."""
+    _dev_check(x0)
+    _f32c(x0, "x0")
+    B, m, D = x0.shape
+    if x0.stride(2) != 1 or x0.stride(1) != D:
+        x0 = x0.contiguous()
+    H = xk.shape[1]
+    assert xk.stride(2) == 1 and xk.stride(1) == D
+    W = _f32c(W, "W").contiguous()
+    N = W.shape[1]
+    assert W.shape[0] == m * H
+    dev = x0.device
+    out = torch.empty(B, N, D, dtype=torch.float32, device=dev)
+    pre = torch.empty(B, N, D, dtype=torch.float32, device=dev) if want_pre else None
+    ws_bytes = _C.lib.rm_cin_layer_workspace_bytes(B, m, H, D, N, precision)
+    ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+    _C.call(
+        "rm_cin_layer_fwd", _p(x0), x0.stride(0), _p(xk), xk.stride(0), _p(W), _p(bias.contiguous()), B, m, H, D, N, act, precision,
+        _p(out), _p(pre), _p(ws), ws_bytes, _stream(),
+    )
+    return out, pre
+
+
+def cin_layer_bwd(x0, xk, W, pre, dout, act: int, precision: int, dx0, dxk):
+    """dx0 [B,m,D] is accumulated into; dxk [B,H,D] (batch stride free) is written."""
+    _dev_check(x0)
+    B, m, D = x0.shape
+    if x0.stride(2) != 1 or x0.stride(1) != D:
+        x0 = x0.contiguous()
+    H = xk.shape[1]
+    W = W.contiguous()
+    N = W.shape[1]
+    dev = x0.device
+    dout = dout.contiguous()
+    assert xk.stride(2) == 1 and xk.stride(1) == D and dxk.stride(2) == 1 and dxk.stride(1) == D
+    assert dx0.is_contiguous()
+    dW = torch.empty(m * H, N, dtype=torch.float32, device=dev)
+    dbias = torch.empty(N, dtype=torch.float32, device=dev)
+    ws_bytes = _C.lib.rm_cin_layer_bwd_workspace_bytes(B, m, H, D, N, precision)
+    ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+    _C.call(
+        "rm_cin_layer_bwd", _p(x0), x0.stride(0), _p(xk), xk.stride(0), _p(W), _p(pre), _p(dout), B, m, H, D, N, act, precision,
+        _p(dW), _p(dbias), _p(dx0), _p(dxk), dxk.stride(0), _p(ws), ws_bytes, _stream(),
+    )
+    return dW, dbias
+
+
+# --------------------------------------------------------------------------- #
+# N1 optimizer steps
+# --------------------------------------------------------------------------- #
+def sparse_opt_step(table, sg: SparseGrad, opt: int, lr: float, l2: float = 0.0):
+    _dev_check(table)
+    k = table.shape[1] if table.dim() == 2 else 1
+    _C.call(
+        "rm_sparse_opt_step", _p(table), k, _p(sg.uniq_rows), _p(sg.rows), _p(sg.n_unique), sg.uniq_rows.numel(), opt,
+        float(lr), float(l2), _stream(),
+    )
+
+
+def dense_opt_step(p, g, opt: int, lr: float, l2: float = 0.0):
+    _dev_check(p)
+    assert p.is_contiguous() and g.is_contiguous() and p.numel() == g.numel()
+    _C.call("rm_dense_opt_step", _p(p), _p(g), p.numel(), opt, float(lr), float(l2), _stream())

@@ -1,0 +1,103 @@
+"""recman.th.DeepFM - the class the reference stub reserves (recman/th/DeepFM.py:12-13), built to the
+composition and keyword vocabulary of the stale TF1 shell recman/tf/core/DeepFM.py:30-183:
+
+    embeddings + bias (use_bias=True) -> LinearLayer ; FMLayer(embeds, bias) ; DNN(flatten(embeds) ++ dense)
+    -> add_n([linear, fm, dnn]) -> sigmoid ;  loss = logloss + L2(embeds, linear, dnn)
+"""
+
+from __future__ import annotations
+
+import torch
+
+from .DeepModel import DeepModel, create_loss
+from .input import DataInputs, FeatureDictionary
+from .layers import DNN, DNNCombiner, FMLayer, LinearCombiner, LinearLayer, PredictionLayer, relu
+
+
+class DeepFM(DeepModel):
+    def __init__(
+        self,
+        feat_dict: FeatureDictionary,
+        embedding_size=8,
+        embedding_l2_reg=0.00001,
+        linear_l2_reg=0.00001,
+        fm_dropout=(1.0, 1.0),
+        deep_hidden_units=(32, 32),
+        deep_dropout=(0.8, 0.8, 0.8),
+        deep_l2_reg=0.00001,
+        deep_activation=relu,
+        epoch=10,
+        batch_size=64,
+        learning_rate=0.001,
+        optimizer="adam",
+        random_seed=2019,
+        use_fm=True,
+        use_deep=True,
+        loss_type="logloss",
+        eval_metric=(),
+        what_means_greater=None,
+        use_interactive_session=False,
+        log_dir="./logs",
+        embedding_l2_mode="dense",
+    ):
+        assert use_fm or use_deep
+        assert loss_type in ["logloss", "mse"], \
+            "loss_type can be either 'logloss' for classification task or 'mse' for regression task"
+        hparams = dict(
+            embedding_size=embedding_size, embedding_l2_reg=embedding_l2_reg, linear_l2_reg=linear_l2_reg,
+            fm_dropout=tuple(fm_dropout), deep_hidden_units=tuple(deep_hidden_units), deep_dropout=tuple(deep_dropout),
+            deep_l2_reg=deep_l2_reg, deep_activation=deep_activation, learning_rate=learning_rate, optimizer=optimizer,
+            embedding_l2_mode=embedding_l2_mode,
+        )
+        DeepModel.__init__(self, feat_dict, hparams, eval_metric, epoch, batch_size, random_seed,
+                           task="classification" if loss_type == "logloss" else "regression")
+        self.use_fm = use_fm
+        self.use_deep = use_deep
+        self.loss_type = loss_type
+
+    def _out(self, inputs: DataInputs, training=True):
+        hp = self.hparams
+        self.embeddings = self._embedding_layer(use_bias=True, l2_mode=hp["embedding_l2_mode"])
+        linear_feats = list(self.feat_dict.values())  # LinearCombiner(self.feat_dict), DeepFM.py:122
+        fused_feats = self.feat_dict.sparse_feats + self.feat_dict.dense_feats
+        self.linear = LinearLayer(self.variables, fused_feats if len(fused_feats) == len(linear_feats) else linear_feats,
+                                  hp["linear_l2_reg"], training=training)
+        fm_dropout = hp["fm_dropout"] if training else (1.0,) * len(hp["fm_dropout"])
+        fm_identity = all(p >= 1 for p in fm_dropout)
+
+        fused = self._fused_front_end(self.embeddings, inputs, self.linear, want_fm=self.use_fm and fm_identity)
+        if fused is not None:
+            rows, fm_logit, linear_logit = fused
+            m, k = len(self.embeddings.feats), hp["embedding_size"]
+            if self.use_fm and fm_logit is None:  # FM dropout active: unfused FM on the gathered block
+                raise NotImplementedError("fm_dropout < 1 with the fused front end")
+            dnn_input = rows
+        else:
+            feat_embeds, feat_bias = self.embeddings(inputs)
+            linear_logit = self.linear(LinearCombiner(self.linear.linear_feats)(inputs))
+            fm_logit = None
+            if self.use_fm:
+                fm = FMLayer(fm_dropout)
+                fm.training = training
+                fm_logit = fm(feat_embeds, feat_bias)
+            dnn_input = DNNCombiner()([feat_embeds] + inputs.dense_inputs(self.feat_dict)) if self.use_deep else None
+
+        final_logit = linear_logit
+        if self.use_fm:
+            final_logit = final_logit + fm_logit
+        self.dnn = None
+        if self.use_deep:
+            self.dnn = DNN(self.variables, hp["deep_hidden_units"],
+                           hp["deep_dropout"] if training else (1.0,) * len(hp["deep_dropout"]),
+                           hp["deep_activation"], hp["deep_l2_reg"])
+            self.dnn.training = training
+            final_logit = final_logit + self.dnn(dnn_input)
+        self.final_logit = final_logit
+        return PredictionLayer(self.variables, self.task, use_bias=False)(final_logit)
+
+    def _loss(self, inputs):
+        loss = create_loss(inputs.y, self._out(inputs), task=self.task)
+        loss = loss + self.embeddings.l2() + self.linear.l2()
+        if self.use_deep:
+            loss = loss + self.dnn.l2()
+        return loss

@@ -1,0 +1,303 @@
+"""recman.th.DeepModel - sklearn-style estimator base, mirror of recman/tf/core/DeepModel.py:21-228.
+
+Same public surface (``fit / predict / evaluate / get_batch / fit_on_batch / restore``, abstract
+``_out`` / ``_loss``) and the same batch loop, including the reference's quirks that affect results:
+``len // batch_size + 1`` batches with a possibly EMPTY last batch (DeepModel.py:49,188 - skipped here
+instead of being fed to the kernels), evaluation with ``training=True`` (DeepModel.py:103-111) and a NEW
+optimizer for every batch (xDeepFM.py:116-126), which makes every step a stateless first step.
+
+What differs is underneath: batches are packed once into pinned host buffers and copied in one piece per
+dtype (``DataInputs.load``), the forward/backward runs on the sm_100a kernels, embedding gradients stay
+sparse and the optimizer touches only the rows that received gradient.
+"""
+
+from __future__ import annotations
+
+import logging
+from abc import ABC, abstractmethod
+from time import time
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from .. import _C, ops
+from ..autograd import FrontEndFunction, dense_table_grad, pop_sparse_grads
+from .input import DataInputs, FeatureDictionary
+from .layers import FeatEmbeddingLayer, LinearLayer, PaddedRows
+
+log = logging.getLogger(__name__)
+
+try:
+    from sklearn.base import BaseEstimator, TransformerMixin
+except Exception:  # pragma: no cover
+
+    class BaseEstimator:  # type: ignore
+        pass
+
+    class TransformerMixin:  # type: ignore
+        pass
+
+
+KERAS_EPSILON = 1e-7
+
+
+def binary_crossentropy(y_true, y_pred):
+    """tf.losses.binary_crossentropy on probabilities (tf/core/utils.py:192-194): clip to [eps, 1-eps], log(p+eps)."""
+    eps = KERAS_EPSILON
+    p = torch.clamp(y_pred, eps, 1 - eps)
+    y = y_true.to(p.dtype)
+    return (-(y * torch.log(p + eps) + (1 - y) * torch.log(1 - p + eps))).mean(dim=-1)
+
+
+def create_loss(y_true, y_pred, task):
+    if task == "classification":
+        return binary_crossentropy(y_true, y_pred)
+    if task == "regression":
+        return ((y_pred - y_true.to(y_pred.dtype)) ** 2).mean(dim=-1)
+    raise ValueError()
+
+
+def get_linear_features(feat_dict, linear_feats):
+    """tf/core/utils.py:26-35."""
+    if linear_feats:
+        return [feat_dict[name] for name in linear_feats.split(",")]
+    return feat_dict.sparse_feats + feat_dict.sparse_val_feats + feat_dict.multi_val_csv_feats + feat_dict.dense_feats
+
+
+def _shuffle(n, seed):
+    return np.random.RandomState(seed).permutation(n)
+
+
+def _take(X, idx):
+    if hasattr(X, "iloc"):
+        return X.iloc[idx]
+    if isinstance(X, dict):
+        return {k: v[idx] for k, v in X.items()}
+    return X[idx]
+
+
+class DeepModel(BaseEstimator, TransformerMixin, ABC):
+    def __init__(self, feat_dict: FeatureDictionary, hparams: dict, metrics, epoch, batch_size=64, random_seed=2019,
+                 task="classification"):
+        assert task in ["classification", "regression"], \
+            "target can be either 'classification' for classification task or 'regression' for regression task"
+        self.task = task
+        self.feat_dict = feat_dict
+        self.hparams = hparams
+        self.epoch = epoch
+        self.batch_size = batch_size
+        self.random_seed = random_seed
+        self.metrics = metrics
+        self.variables: Dict[str, torch.nn.Parameter] = dict()
+        self.device = torch.device("cuda")
+        self._emb_status = None
+        self.samples_seen = 0
+
+    # ------------------------------------------------------------------ front end shared by the models
+    def _embedding_layer(self, use_bias, l2_mode="dense") -> FeatEmbeddingLayer:
+        layer = FeatEmbeddingLayer(
+            self.variables, self.feat_dict, self.hparams["embedding_size"], self.hparams.get("embedding_l2_reg", 0.0),
+            use_bias=use_bias, seed=self.random_seed,
+        )
+        layer.status = self._status()
+        if l2_mode == "touched":  # scale mode: regularise only rows that were looked up (SURVEY hard part 5)
+            layer._upsert_variables()
+            self.variables[layer.table_name].rm_l2_touched = float(layer.l2_reg)
+            layer.l2_reg = 0.0
+        return layer
+
+    def _status(self):
+        if self._emb_status is None:
+            self._emb_status = ops.new_status(self.device)
+        return self._emb_status
+
+    def check_ids(self):
+        """Raises if any id seen so far was outside its table (host sync; call it outside hot loops)."""
+        if self._emb_status is not None and int(self._emb_status.item()) != 0:
+            raise _C.RecmanB200Error("an embedding id was outside its table (rows were zero-filled)")
+
+    def _fused_front_end(self, layer: FeatEmbeddingLayer, inputs: DataInputs, linear: Optional[LinearLayer],
+                         want_fm: bool):
+        """One launch: gather -> [embeds | dense] row buffer (+ FM logit, + first-order logit).
+
+        Eligible when every embedding feature is a one-hot SparseFeat and k % 4 == 0, k <= 128.
+        Returns (PaddedRows, fm_logit | None, lin_logit | None) or None when not eligible.
+        """
+        k = layer.embedding_size
+        if not (layer.all_one_hot and k % 4 == 0 and k <= 128 and inputs.sparse_ids is not None):
+            return None
+        layer._upsert_variables()
+        table = self.variables[layer.table_name]
+        bias_table = self.variables[layer.bias_name] if (layer.use_bias and want_fm) else None
+        lin_table = lin_dense = None
+        dense = inputs.dense
+        n_dense = 0 if dense is None else dense.shape[1]
+        if linear is not None:
+            # the fused kernel indexes linear_w with the embedding table's row numbers: needs the same layout,
+            # i.e. linear features == [all sparse feats in order] + [all dense feats in order]
+            feats = linear.linear_feats
+            want = self.feat_dict.sparse_feats + self.feat_dict.dense_feats
+            if [f.name for f in feats] != [f.name for f in want]:
+                return None
+            linear._upsert_variables()
+            W = linear.effective_weight()
+            flat = W.reshape(-1)
+            lin_table = flat[: layer.total_rows]
+            lin_dense = flat[layer.total_rows :] if n_dense else None
+        lay = layer.layout()
+        ids = inputs.sparse_ids
+        W_lin = None
+        if linear is not None:
+            W_lin = self.variables[f"{linear.prefix}linear_w"]
+            lin_table = lin_table.detach()
+            lin_dense = None if lin_dense is None else lin_dense.detach().contiguous()
+        x, fm, lin = FrontEndFunction.apply(table, bias_table, W_lin, lin_table, lin_dense, lay.runs[0].offsets,
+                                            layer.total_rows, self._status(), ids, dense)
+        d = lay.m * k + n_dense
+        if linear is not None:
+            lin = lin + self.variables[f"{linear.prefix}linear_w0"]
+        return PaddedRows(x, d), (fm if want_fm else None), (lin if linear is not None else None)
+
+    # ------------------------------------------------------------------ reference API
+    def predict(self, X, training=False, batch_number_to_show_progress=50):
+        n = len(X) if not isinstance(X, dict) else len(next(iter(X.values())))
+        dummy_y = np.ones(n, dtype=np.float32)
+        outs = []
+        total_batch = n // self.batch_size + 1
+        with torch.no_grad():
+            for batch_index in range(total_batch):
+                x_batch, y_batch = self.get_batch(X, dummy_y, self.batch_size, batch_index)
+                if len(y_batch) == 0:  # the reference feeds this empty batch to TF; nothing to compute
+                    continue
+                inputs = DataInputs(self.device).load(self.feat_dict, x_batch, y_batch)
+                outs.append(self._out(inputs, training=training).reshape(-1))
+                if batch_index % batch_number_to_show_progress == 0:
+                    log.info(f"Predict: {(batch_index + 1)}/{total_batch} has been completed")
+        log.info(f"Predict: {total_batch}/{total_batch} has been completed")
+        if not outs:
+            return np.zeros((0,), dtype=np.float32)
+        return torch.cat(outs).cpu().numpy()
+
+    def evaluate(self, X, y, training=False, batch_number_to_show_progress=50):
+        pred = self.predict(X, training, batch_number_to_show_progress)
+        return [metric(y, pred) for metric in self.metrics]
+
+    @staticmethod
+    def get_batch(X, y, batch_size, index):
+        start = index * batch_size
+        end = start + batch_size
+        end = end if end < len(y) else len(y)
+        if isinstance(X, dict):
+            return {k: v[start:end] for k, v in X.items()}, y[start:end]
+        return X[start:end], y[start:end]
+
+    # ------------------------------------------------------------------ state
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """Reference-named tensors: per-feature ``*_feat_embed`` / ``*_feat_bias`` views instead of the fused tables."""
+        out = {}
+        for name, p in self.variables.items():
+            out[name] = p.data
+        return out
+
+    def load_state_dict(self, state: Dict[str, torch.Tensor], strict=True):
+        for name, t in state.items():
+            if name in self.variables:
+                self.variables[name].data.copy_(t.to(self.device))
+            elif strict:
+                raise KeyError(name)
+
+    def save(self, path="ckpt_model.pt"):
+        torch.save({k: v.cpu() for k, v in self.state_dict().items()}, path)
+
+    def restore(self, path="ckpt_model.pt"):
+        """DeepModel.restore (DeepModel.py:83-86) with torch.save files instead of tf.train.Checkpoint."""
+        self.load_state_dict(torch.load(path), strict=False)
+
+    # ------------------------------------------------------------------ training
+    @abstractmethod
+    def _out(self, inputs, training=True):
+        pass
+
+    @abstractmethod
+    def _loss(self, inputs):
+        pass
+
+    def fit_on_batch(self, X, y):
+        """One optimisation step (xDeepFM.py:116-126): encode, forward, backward, fresh-optimizer update."""
+        inputs = X if isinstance(X, DataInputs) else DataInputs(self.device).load(self.feat_dict, X, y)
+        loss = self._loss(inputs)
+        loss.backward()
+        self.optimizer_step()
+        self.samples_seen += inputs.batch_size
+        return loss.detach()
+
+    def optimizer_step(self):
+        opt = self.hparams.get("optimizer", "adam")
+        if not isinstance(opt, str) or opt not in _C.OPT_KINDS:
+            raise ValueError(f"optimizer {opt!r}: the kernels implement adam / adagrad / gd / momentum")
+        kind = _C.OPT_KINDS[opt]
+        lr = float(self.hparams.get("learning_rate", 0.001))
+        for name, p in self.variables.items():
+            sparse = pop_sparse_grads(p)
+            tail = getattr(p, "rm_dense_tail", None)
+            p.rm_dense_tail = None
+            if sparse and p.grad is None:
+                l2 = float(getattr(p, "rm_l2_touched", 0.0))
+                for sg in sparse:
+                    ops.sparse_opt_step(p.data, sg, kind, lr, l2)
+                if tail is not None:
+                    first, g = tail
+                    ops.dense_opt_step(p.data.reshape(-1)[first:], g.contiguous(), kind, lr, 0.0)
+            elif sparse:
+                # a dense part exists (the reference's whole-table L2, layers.py:188-193): densify and update all rows
+                p.rm_sparse_grads = sparse
+                g = dense_table_grad(p, consume=True)
+                if tail is not None:
+                    first, gt = tail
+                    g.reshape(-1)[first:] += gt
+                ops.dense_opt_step(p.data, g.contiguous(), kind, lr, 0.0)
+            elif p.grad is not None:
+                ops.dense_opt_step(p.data, p.grad.contiguous(), kind, lr, 0.0)
+            p.grad = None
+
+    def _eval_at_epoch(self, X_train, y_train, X_valid=None, y_valid=None, start_time=None, epoch=0,
+                       batch_number_to_show_progress=50):
+        start_time = time() if start_time is None else start_time
+        has_valid = X_valid is not None and y_valid is not None
+        train_res = self.evaluate(X_train, y_train, training=True,
+                                  batch_number_to_show_progress=batch_number_to_show_progress)
+        valid_res = self.evaluate(X_valid, y_valid, training=True) if has_valid else None
+        log.info("[%d] train-result=%s%s [%.1f s]" % (
+            epoch, str([(str(f), round(float(r), 4)) for f, r in zip(self.metrics, train_res)]),
+            (", valid-result=%s" % str([(str(f), round(float(r), 4)) for f, r in zip(self.metrics, valid_res)]))
+            if has_valid else "", time() - start_time))
+        return train_res, valid_res
+
+    def fit(self, X_train, y_train, X_valid=None, y_valid=None, random_seed_for_mini_batch=True, tb_logger=None,
+            epoch_callback=None, show_progress=False, batch_number_to_show_progress=50):
+        assert X_train is not None or y_train is not None
+        y_train = np.asarray(y_train)
+        eval_results = self._eval_at_epoch(X_train, y_train, X_valid, y_valid, time())
+        self.history = [eval_results]
+        for epoch in range(1, self.epoch + 1):
+            t0 = time()
+            seed = np.random.randint(1, 2019) if random_seed_for_mini_batch else self.random_seed
+            perm = _shuffle(len(y_train), seed)
+            X_train, y_train = _take(X_train, perm), y_train[perm]
+            total_batch = len(y_train) // self.batch_size + 1
+            for i in range(total_batch):
+                Xi_batch, y_batch = self.get_batch(X_train, y_train, self.batch_size, i)
+                if len(y_batch) == 0:
+                    continue
+                self.fit_on_batch(Xi_batch, y_batch)
+                if i % batch_number_to_show_progress == 0:
+                    log.info(f"Fit: {(i + 1)}/{total_batch} has been completed")
+            log.info(f"Fit: {total_batch}/{total_batch} has been completed [{time() - t0:.1f} s]")
+            eval_results = self._eval_at_epoch(X_train, y_train, X_valid, y_valid, time(), epoch,
+                                               batch_number_to_show_progress)
+            self.history.append(eval_results)
+            if epoch_callback:
+                epoch_callback(model=self, eval_results=eval_results, df_all=X_train[:1])
+        self.check_ids()
+        return self

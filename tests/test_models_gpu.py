@@ -1,0 +1,122 @@
+"""Model-level parity on the GPU: recman.th DeepFM / DCN (/ xDeepFM in test_cin_gpu.py) vs the fp64 CPU oracle -
+logits, loss and every gradient, with injected weights; fused and unfused front ends; optimizer step."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests import parity_util as pu
+
+pytestmark = pytest.mark.gpu
+
+CRITEO_SMALL = [50, 7, 1000, 3, 200, 31, 2, 90]
+
+
+@pytest.mark.parametrize("k", [8, 16, 64])
+@pytest.mark.parametrize("B", [256, 1000])
+def test_deepfm_fused_parity(k, B):
+    from recman_b200.th import DeepFM
+
+    fd = pu.make_feat_dict(CRITEO_SMALL, n_dense=13)
+    X, y = pu.synth_batch(fd, B, seed=k + B)
+    model = DeepFM(fd, embedding_size=k, deep_hidden_units=(32, 32), deep_dropout=(1, 1, 1), batch_size=B)
+    rep = pu.compare(model, X, y)
+    assert "grad:feat_embed_table" in rep and "grad:feat_bias_table" in rep and "grad:linear_w" in rep
+
+
+def test_deepfm_unfused_with_multival_ml100k_shape():
+    """C1 shape: 5 sparse + 2 dense + 1 multi-valued field, k=8, B=256 -> unfused kernels (K1 pooled, K3, K2)."""
+    from recman_b200.th import DeepFM
+
+    fd = pu.make_feat_dict([944, 1683, 3, 22, 796], n_dense=2, multi_tags=[f"g{i}" for i in range(19)])
+    X, y = pu.synth_batch(fd, 256, seed=3)
+    model = DeepFM(fd, embedding_size=8, deep_dropout=(1, 1, 1), batch_size=256)
+    pu.compare(model, X, y)
+
+
+def test_deepfm_k_not_multiple_of_4_uses_scalar_kernels():
+    from recman_b200.th import DeepFM
+
+    fd = pu.make_feat_dict([20, 30, 5], n_dense=1)
+    X, y = pu.synth_batch(fd, 100, seed=4)
+    model = DeepFM(fd, embedding_size=6, deep_dropout=(1, 1, 1), batch_size=100)
+    pu.compare(model, X, y)
+
+
+@pytest.mark.parametrize("use_fm,use_deep", [(True, False), (False, True)])
+def test_deepfm_towers(use_fm, use_deep):
+    from recman_b200.th import DeepFM
+
+    fd = pu.make_feat_dict(CRITEO_SMALL, n_dense=3)
+    X, y = pu.synth_batch(fd, 300, seed=5)
+    model = DeepFM(fd, embedding_size=16, deep_dropout=(1, 1, 1), use_fm=use_fm, use_deep=use_deep, batch_size=300)
+    pu.compare(model, X, y)
+
+
+@pytest.mark.parametrize("k,L", [(16, 6), (8, 3)])
+def test_dcn_parity(k, L):
+    from recman_b200.th import DCN
+
+    fd = pu.make_feat_dict(CRITEO_SMALL * 2, n_dense=13)
+    X, y = pu.synth_batch(fd, 512, seed=6)
+    model = DCN(fd, embedding_size=k, deep_hidden_units=(64, 64, 64), deep_dropout=(1, 1, 1, 1), cross_layer_num=L,
+                cross_layer_l2_reg=1e-5, deep_l2_reg=1e-5, batch_size=512)
+    pu.compare(model, X, y)
+
+
+@pytest.mark.parametrize("opt", ["adam", "adagrad", "gd"])
+@pytest.mark.parametrize("l2_mode,emb_l2", [("dense", 1e-5), ("touched", 1e-5), ("dense", 0.0)])
+def test_fit_on_batch_matches_oracle_update(opt, l2_mode, emb_l2):
+    """One full step (forward, backward, fresh optimizer) against the oracle's update rule on dense gradients."""
+    from recman_b200.th import DeepFM
+    from recman_b200.th.input import DataInputs
+
+    fd = pu.make_feat_dict([40, 9, 300], n_dense=2)
+    X, y = pu.synth_batch(fd, 128, seed=7)
+    lr = 0.01
+    lin_l2 = 1e-5 if l2_mode == "dense" else 0.0
+    model = DeepFM(fd, embedding_size=8, deep_dropout=(1, 1, 1), batch_size=128, optimizer=opt, learning_rate=lr,
+                   embedding_l2_reg=emb_l2, embedding_l2_mode=l2_mode, linear_l2_reg=lin_l2)
+    with torch.no_grad():
+        model._out(DataInputs("cuda").load(fd, X, y))
+    pu.randomize_variables(model)
+    st, _, o_loss = pu.oracle_loss(model, X, y, torch.float64)
+    if l2_mode == "touched":  # oracle_loss sees l2_reg == 0 on the layer; the touched-rows term is added below
+        assert model.embeddings.l2_reg == 0.0
+    o_loss.backward()
+    before = {k: v.detach().clone() for k, v in st.items()}
+    model.fit_on_batch(X, y)
+    for name, p in model.variables.items():
+        g = st[name].grad if st[name].grad is not None else torch.zeros_like(st[name])
+        if l2_mode == "touched" and name == "feat_embed_table" and emb_l2:
+            touched = g.abs().sum(1) != 0
+            g = g + emb_l2 * before[name] * touched[:, None]
+        exp = oracle.fresh_optimizer_step(before[name], g, opt, lr)
+        got = p.detach().cpu().double()
+        if opt == "adam":
+            # fresh Adam is sign-like (lr*g/(|g|+3e-6)): where |g| is at rounding-noise level the step is
+            # ill-conditioned, so those entries are only required to stay within one step of the old value
+            solid = g.abs() > 1e-4 * g.abs().max()
+            assert torch.all((got - before[name]).abs() <= lr * 1.0001 + 1e-12), name
+            torch.testing.assert_close(got[solid], exp[solid], rtol=1e-5, atol=lr * 2e-3, msg=lambda m: f"{name}: {m}")
+        else:
+            torch.testing.assert_close(got, exp, rtol=1e-5, atol=1e-7, msg=lambda m: f"{name}: {m}")
+
+
+def test_predict_and_evaluate_batches():
+    from recman_b200.th import DeepFM
+    from recman_b200.th.metric import LogLoss, RocAucScore
+
+    fd = pu.make_feat_dict([30, 12], n_dense=1)
+    X, y = pu.synth_batch(fd, 130, seed=8)
+    model = DeepFM(fd, embedding_size=8, batch_size=64, epoch=1, eval_metric=(LogLoss(), RocAucScore()),
+                   learning_rate=0.01)
+    p = model.predict(X)
+    assert p.shape == (130,) and np.all((p > 0) & (p < 1))
+    p2 = model.predict({k: v[:128] for k, v in X.items()})  # 128 % 64 == 0: the reference's empty trailing batch
+    assert p2.shape == (128,)
+    np.testing.assert_array_equal(p[:128], p2)
+    model.fit(X, y, random_seed_for_mini_batch=False)
+    res = model.evaluate(X, y)
+    assert len(res) == 2 and all(np.isfinite(r) for r in res)
+    assert len(model.history) == 2
