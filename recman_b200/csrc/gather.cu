@@ -243,12 +243,12 @@ extern "C" {
 int rm_gather_fwd(const float* table, const int64_t* table_offsets, const int64_t* ids, int64_t B, int32_t m,
                   int32_t k, float* out, int64_t out_stride, int32_t* status, void* stream) {
   using namespace rm;
-  RM_CHECK_ARG(table && table_offsets && ids && out, "null pointer");
   RM_CHECK_ARG(B >= 0 && m > 0 && k > 0, "bad shape");
   RM_CHECK_ARG(out_stride >= (int64_t)m * k, "out_stride smaller than m*k");
   const int64_t N = B * m;
   RM_UNSUPPORTED(N < (int64_t)1 << 31, "B*m must be < 2^31");
-  if (N == 0) return 0;
+  if (N == 0) return 0;  // empty batch: nothing to do, pointers may be null
+  RM_CHECK_ARG(table && table_offsets && ids && out, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = (k % 4 == 0) && (out_stride % 4 == 0) && aligned16(table) && aligned16(out);
   if (vec) {

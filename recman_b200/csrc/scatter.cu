@@ -236,8 +236,9 @@ int rm_segment_plan(const int64_t* ids, const int64_t* table_offsets, int64_t N,
                     void* workspace, size_t workspace_bytes, int32_t* sorted_pos, int32_t* seg_start,
                     int64_t* uniq_rows, int32_t* n_unique, void* stream) {
   using namespace rm;
-  RM_CHECK_ARG(ids && sorted_pos && seg_start && uniq_rows && n_unique, "null pointer");
+  RM_CHECK_ARG(seg_start && n_unique, "null pointer");
   RM_CHECK_ARG(N >= 0 && m > 0 && total_rows > 0, "bad shape");
+  RM_CHECK_ARG(N == 0 || (ids && sorted_pos && uniq_rows), "null pointer");
   RM_UNSUPPORTED(N < ((int64_t)1 << 31) - 1, "N must be < 2^31 - 1");
   RM_UNSUPPORTED(total_rows <= ((int64_t)1 << 32), "total_rows must be <= 2^32 (32-bit sort keys)");
   cudaStream_t st = (cudaStream_t)stream;

@@ -133,7 +133,8 @@ def oracle_loss(model, X, y, dtype=torch.float64):
     if isinstance(model, DeepFM):
         lin = _oracle_linear(fd, model.linear, st, X, dtype)
         nl = len(hp["deep_hidden_units"])
-        logit = oracle.deepfm_logit(embeds, bias, lin, dense, _dnn_params(st, nl), _act(hp["deep_activation"]),
+        dnn_p = _dnn_params(st, nl) if model.use_deep else None
+        logit = oracle.deepfm_logit(embeds, bias, lin, dense, dnn_p, _act(hp["deep_activation"]),
                                     model.use_fm, model.use_deep)
         l2 = emb_l2 + hp["linear_l2_reg"] * oracle.l2_loss(st["linear_w"])
         if model.use_deep:

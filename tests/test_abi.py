@@ -50,6 +50,7 @@ def test_argument_validation_without_a_gpu(built_lib):
 
     rc = _C.lib.rm_gather_fwd(None, None, None, 4, 2, 8, None, 16, None, None)
     assert rc == -1 and "null pointer" in _C.last_error()
+    assert _C.lib.rm_gather_fwd(None, None, None, 0, 2, 8, None, 16, None, None) == 0  # empty batch is a no-op
     rc = _C.lib.rm_cross_fwd(1, 4096, 1, 1, 1, None, 4, 4096, 2, 1, None, None)
     assert rc == -2 and "2048" in _C.last_error()
     with pytest.raises(_C.RecmanB200Error):

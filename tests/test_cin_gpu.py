@@ -1,0 +1,113 @@
+"""K5 parity: CIN layer forward/backward (CUDA-core fp32 path and tcgen05 paths) and the xDeepFM model vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests import parity_util as pu
+
+pytestmark = pytest.mark.gpu
+
+ACTS = {0: (lambda t: t), 1: oracle.relu, 2: oracle.leaky_relu_tf}
+
+
+def _layer_oracle(x0, xk, W, bias, act):
+    """One CIN layer in the oracle's op order: returns act(Z.W + b) as [B,N,D] (layers.py:711-739)."""
+    B, m, D = x0.shape
+    H = xk.shape[1]
+    z = torch.einsum("bpd,bqd->bdpq", x0, xk).reshape(B, D, m * H)
+    f = z @ W + bias
+    return ACTS[act](f).permute(0, 2, 1), f.permute(0, 2, 1)
+
+
+CASES = [  # B, m, H, D, N
+    (3, 2, 2, 4, 16),
+    (37, 6, 6, 8, 20),
+    (64, 26, 26, 16, 200),
+    (40, 26, 100, 16, 200),
+    (9, 5, 7, 12, 10),
+    (5, 3, 4, 64, 6),
+    (130, 4, 3, 1, 8),
+]
+
+
+def _make(B, m, H, D, N, seed):
+    g = torch.Generator().manual_seed(seed)
+    x0 = (torch.randn(B, m, D, generator=g) * 0.5).double().requires_grad_()
+    xk_full = (torch.randn(B, 2 * H, D, generator=g) * 0.5).double()  # xk is the first half of a wider tensor
+    xk = xk_full[:, :H].clone().requires_grad_()
+    W = (torch.randn(m * H, N, generator=g) / np.sqrt(m * H)).double().requires_grad_()
+    bias = (torch.randn(N, generator=g) * 0.1).double().requires_grad_()
+    dout = torch.randn(B, N, D, generator=g).double()
+    return x0, xk_full, xk, W, bias, dout
+
+
+@pytest.mark.parametrize("B,m,H,D,N", CASES)
+@pytest.mark.parametrize("act", [0, 2])
+def test_cin_layer_simt_fwd_bwd(B, m, H, D, N, act):
+    from recman_b200 import ops
+
+    x0, xk_full, xk, W, bias, dout = _make(B, m, H, D, N, B * 7 + H)
+    out64, pre64 = _layer_oracle(x0, xk, W, bias, act)
+    out64.backward(dout)
+    xk_dev = xk_full.float().cuda()[:, :H]  # batch stride 2*H*D
+    x0d, Wd, bd = x0.detach().float().cuda(), W.detach().float().cuda(), bias.detach().float().cuda()
+    out, pre = ops.cin_layer_fwd(x0d, xk_dev, Wd, bd, act, 0)
+    scale = max(1.0, float(pre64.abs().max()))
+    torch.testing.assert_close(pre.cpu().double(), pre64.detach(), rtol=1e-5, atol=2e-6 * scale)
+    torch.testing.assert_close(out.cpu().double(), out64.detach(), rtol=1e-5, atol=2e-6 * scale)
+    dx0 = torch.ones(B, m, D, device="cuda")  # accumulated into
+    dxk_full = torch.zeros(B, 2 * H, D, device="cuda")
+    dW, dbias = ops.cin_layer_bwd(x0d, xk_dev, Wd, pre, dout.float().cuda(), act, 0, dx0, dxk_full[:, :H])
+    for name, got, exp in [("dW", dW, W.grad), ("dbias", dbias, bias.grad), ("dx0", dx0 - 1, x0.grad),
+                           ("dxk", dxk_full[:, :H], xk.grad)]:
+        e = exp.double()
+        torch.testing.assert_close(got.cpu().double(), e, rtol=1e-5, atol=1e-5 * float(e.abs().max()),
+                                   msg=lambda m_: f"{name}: {m_}")
+    assert torch.all(dxk_full[:, H:] == 0)
+    # determinism
+    dx0b = torch.ones(B, m, D, device="cuda")
+    dxkb = torch.zeros(B, 2 * H, D, device="cuda")
+    dW2, dbias2 = ops.cin_layer_bwd(x0d, xk_dev, Wd, pre, dout.float().cuda(), act, 0, dx0b, dxkb[:, :H])
+    assert torch.equal(dW, dW2) and torch.equal(dbias, dbias2) and torch.equal(dx0, dx0b) and torch.equal(dxk_full, dxkb)
+
+
+def test_cin_notebook_kat_on_gpu():
+    """notes/xDeepFM.ipynb cell 6 through the CUDA kernels (all-ones filters, identity activation)."""
+    from recman_b200 import ops
+
+    x = torch.tensor([[[1, 2, 3, 4], [5, 6, 7, 8]]], dtype=torch.float32, device="cuda")
+    z16 = torch.zeros(16, device="cuda")
+    f0, _ = ops.cin_layer_fwd(x, x, torch.ones(4, 16, device="cuda"), z16, 0, 0)
+    nxt, direct0 = f0[:, :8], f0[:, 8:]
+    f1, _ = ops.cin_layer_fwd(x, nxt, torch.ones(16, 16, device="cuda"), z16, 0, 0)
+    pooled = torch.cat([direct0.sum(-1), f1.sum(-1)], dim=1).cpu().reshape(-1).tolist()
+    assert pooled == [344.0] * 8 + [27648.0] * 16
+
+
+@pytest.mark.parametrize("precision", ["fp32"])
+def test_xdeepfm_parity(precision):
+    from recman_b200.th import xDeepFM
+    from recman_b200.th.layers import leaky_relu
+
+    fd = pu.make_feat_dict([50, 7, 1000, 3, 200, 31, 2, 90], n_dense=13)
+    X, y = pu.synth_batch(fd, 256, seed=11)
+    hp = dict(embedding_size=16, deep_hidden_units=(32, 32), deep_dropout=(1, 1, 1), cin_cross_layer_units=[20, 20, 12],
+              cin_dropout=[1, 1, 1, 1], cin_precision=precision, deep_activation=leaky_relu, cin_activation=leaky_relu,
+              learning_rate=0.01)
+    model = xDeepFM(fd, hp, batch_size=256)
+    rep = pu.compare(model, X, y)
+    assert any(k.startswith("grad:cin_filter_") for k in rep)
+
+
+def test_xdeepfm_toy_frame_with_multival():
+    """The 16-row toy frame shape of examples/xDeepFM_test.py:24-45: 3 SparseFeat + 1 MultiValCsvFeat (a-d)."""
+    from recman_b200.th import xDeepFM
+    from recman_b200.th.layers import leaky_relu
+
+    fd = pu.make_feat_dict([7, 7, 4], n_dense=0, multi_tags=["a", "b", "c", "d"])
+    X, y = pu.synth_batch(fd, 16, seed=12)
+    hp = dict(embedding_size=8, deep_hidden_units=(32, 32), deep_dropout=(1, 1, 1), cin_cross_layer_units=[10, 10, 10],
+              cin_dropout=[1, 1, 1, 1], cin_precision="fp32", deep_activation=leaky_relu, cin_activation=leaky_relu)
+    model = xDeepFM(fd, hp, batch_size=128)
+    pu.compare(model, X, y)

@@ -245,7 +245,8 @@ def test_fused_embedding_backward(k):
     assert_close(ops.SparseGrad(plan.uniq_rows, ob, plan.n_unique).to_dense(total), torch.from_numpy(exp_bias), atol_scale=5e-6)
     assert_close(ops.SparseGrad(plan.uniq_rows, ol, plan.n_unique).to_dense(total), torch.from_numpy(exp_lin), atol_scale=5e-6)
     rows2, _, _ = ops.emb_fm_bwd(dx.cuda(), x, ld, S, g_fm.cuda(), g_lin.cuda(), plan, k, True, False, False)
-    assert torch.equal(rows, rows2)  # deterministic
+    n = plan.num_unique()
+    assert torch.equal(rows[:n], rows2[:n])  # deterministic
     # no FM, no DNN variants
     r3, _, _ = ops.emb_fm_bwd(dx.cuda(), None, ld, None, None, None, plan, k)
     exp3 = oracle.dense_table_grad(keys, dx[:, : m * k].reshape(-1, k).double().numpy(), total)
