@@ -311,11 +311,23 @@ def cin_layer_fwd(x0, xk, W, bias, act: int, precision: int, want_pre=True):
     pre = torch.empty(B, N, D, dtype=torch.float32, device=dev) if want_pre else None
     ws_bytes = _C.lib.rm_cin_layer_workspace_bytes(B, m, H, D, N, precision)
     ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+    global _last_cin_ws
+    _last_cin_ws = ws if ws_bytes else None
     _C.call(
         "rm_cin_layer_fwd", _p(x0), x0.stride(0), _p(xk), xk.stride(0), _p(W), _p(bias.contiguous()), B, m, H, D, N, act, precision,
         _p(out), _p(pre), _p(ws), ws_bytes, _stream(),
     )
     return out, pre
+
+
+_last_cin_ws = None
+
+
+def cin_tc_status() -> int:
+    """Status word of the last tensor-core CIN launch (0 = ok, 2 = a bounded pipeline wait expired). Host sync."""
+    if _last_cin_ws is None:
+        return 0
+    return int(_last_cin_ws[:4].view(torch.int32).item())
 
 
 def cin_layer_bwd(x0, xk, W, pre, dout, act: int, precision: int, dx0, dxk):

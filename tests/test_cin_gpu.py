@@ -111,3 +111,68 @@ def test_xdeepfm_toy_frame_with_multival():
               cin_dropout=[1, 1, 1, 1], cin_precision="fp32", deep_activation=leaky_relu, cin_activation=leaky_relu)
     model = xDeepFM(fd, hp, batch_size=128)
     pu.compare(model, X, y)
+
+
+# ----------------------------------------------------------------------------------------------- tcgen05 path
+TC_CASES = [  # B, m, H, D, N
+    (16, 26, 26, 16, 200),   # one 256-row tile, layer 0 of C3
+    (40, 26, 100, 16, 200),  # 640 rows: 3 tiles, last one partial
+    (3, 2, 2, 4, 16),        # the notebook shape: 12 rows, tiny K (one partial stage)
+    (37, 6, 6, 8, 20),       # C1-like: m=6 -> MPAD 8, N=20 -> NPAD 32
+    (9, 5, 7, 12, 10),       # D does not divide the tile
+    (200, 8, 50, 16, 256),   # widest N
+    (64, 32, 3, 16, 100),    # m = 32 (largest supported)
+]
+
+
+@pytest.mark.parametrize("B,m,H,D,N", TC_CASES)
+# 3xTF32 tolerance: the tensor core accumulates in fp32 with round-toward-zero, a bias that grows linearly with the
+# number of accumulate steps (3*K/8): measured 3.3e-5 of max|F| at K = 2600, < 4e-6 at K <= 700.  The CUDA-core fp32
+# path (precision 0) is the strict 1e-5 parity path at any K (test_cin_layer_simt_fwd_bwd).
+@pytest.mark.parametrize("precision,rtol,atol", [(1, 1e-5, 5e-5), (2, 5e-3, 3e-3)])
+@pytest.mark.parametrize("act", [2])
+def test_cin_layer_tcgen05_fwd(B, m, H, D, N, precision, rtol, atol, act):
+    """tensor-core forward vs the fp64 oracle: 3xTF32 within 1e-5, single-pass TF32 within ~1e-3."""
+    from recman_b200 import ops
+
+    x0, xk_full, xk, W, bias, dout = _make(B, m, H, D, N, B * 3 + N)
+    out64, pre64 = _layer_oracle(x0, xk, W, bias, act)
+    xk_dev = xk_full.float().cuda()[:, :H]
+    x0d, Wd, bd = x0.detach().float().cuda(), W.detach().float().cuda(), bias.detach().float().cuda()
+    out, pre = ops.cin_layer_fwd(x0d, xk_dev, Wd, bd, act, precision)
+    torch.cuda.synchronize()
+    assert ops.cin_tc_status() == 0, "a pipeline wait timed out inside the tcgen05 kernel"
+    scale = max(1.0, float(pre64.abs().max()))
+    torch.testing.assert_close(pre.cpu().double(), pre64.detach(), rtol=rtol, atol=atol * scale)
+    torch.testing.assert_close(out.cpu().double(), out64.detach(), rtol=rtol, atol=atol * scale)
+    # against the CUDA-core fp32 path of the same library
+    out_s, pre_s = ops.cin_layer_fwd(x0d, xk_dev, Wd, bd, act, 0)
+    torch.testing.assert_close(pre, pre_s, rtol=rtol, atol=atol * scale)
+    # deterministic
+    out2, _ = ops.cin_layer_fwd(x0d, xk_dev, Wd, bd, act, precision)
+    assert torch.equal(out, out2)
+
+
+def test_cin_tcgen05_notebook_kat():
+    from recman_b200 import ops
+
+    x = torch.tensor([[[1, 2, 3, 4], [5, 6, 7, 8]]], dtype=torch.float32, device="cuda")
+    z16 = torch.zeros(16, device="cuda")
+    f0, _ = ops.cin_layer_fwd(x, x, torch.ones(4, 16, device="cuda"), z16, 0, 1)
+    nxt, direct0 = f0[:, :8], f0[:, 8:]
+    f1, _ = ops.cin_layer_fwd(x, nxt, torch.ones(16, 16, device="cuda"), z16, 0, 1)
+    pooled = torch.cat([direct0.sum(-1), f1.sum(-1)], dim=1).cpu().reshape(-1).tolist()
+    assert pooled == [344.0] * 8 + [27648.0] * 16  # small integers are exact in tf32 hi/lo arithmetic
+
+
+def test_xdeepfm_parity_3xtf32():
+    from recman_b200.th import xDeepFM
+    from recman_b200.th.layers import leaky_relu
+
+    fd = pu.make_feat_dict([50, 7, 1000, 3, 200, 31, 2, 90], n_dense=13)
+    X, y = pu.synth_batch(fd, 256, seed=11)
+    hp = dict(embedding_size=16, deep_hidden_units=(32, 32), deep_dropout=(1, 1, 1), cin_cross_layer_units=[20, 20, 12],
+              cin_dropout=[1, 1, 1, 1], cin_precision="3xtf32", deep_activation=leaky_relu, cin_activation=leaky_relu,
+              learning_rate=0.01)
+    model = xDeepFM(fd, hp, batch_size=256)
+    pu.compare(model, X, y)
