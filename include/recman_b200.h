@@ -210,6 +210,25 @@ int rm_sparse_opt_step(float* table, int32_t k, const int64_t* uniq_rows, const 
 int rm_dense_opt_step(float* p, const float* g, int64_t n, int32_t opt, float lr, float l2,
                       void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * (e) multi-GPU: row-sharded tables (row r of a table lives on rank r mod W at
+ * local row r div W).  Nothing in the single-process reference corresponds to
+ * this; these are the staging kernels either side of the NCCL all-to-all of
+ * ids / vectors / gradient rows.  A routed row is KP = k+4 floats:
+ * [e_0..e_{k-1} | bias | lin | 0 | 0].  pos[j] = b*m + f of routed row j.
+ * rm_unpack_rows: x[b*ld + f*k + :k] = recv[j,:k]; bias_out[pos] = recv[j,k];
+ *                 lin_out[pos] = recv[j,k+1] (both nullable).
+ * rm_pack_grad_rows: send[j,:k] = dx[b*ld+f*k+:] + g_fm[b]*(S[b,:]-x[b*ld+f*k+:]);
+ *                 send[j,k] = g_fm[b]; send[j,k+1] = g_lin[b]  (dx, g_fm, g_lin nullable).
+ * The owner side uses rm_gather_fwd (out_stride = KP) and rm_segment_plan/reduce
+ * (m = 1, k = KP) directly on the exchange buffers.
+ * ------------------------------------------------------------------------- */
+int rm_unpack_rows(const float* recv, int64_t n, int32_t KP, const int32_t* pos, int32_t m, int32_t k,
+                   float* x, int64_t ld, float* bias_out, float* lin_out, void* stream);
+int rm_pack_grad_rows(const float* dx, const float* x, int64_t ld, const float* sum, const float* g_fm,
+                      const float* g_lin, int64_t n, int32_t KP, const int32_t* pos, int32_t m, int32_t k,
+                      float* send, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

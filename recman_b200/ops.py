@@ -370,3 +370,21 @@ def dense_opt_step(p, g, opt: int, lr: float, l2: float = 0.0):
     _dev_check(p)
     assert p.is_contiguous() and g.is_contiguous() and p.numel() == g.numel()
     _C.call("rm_dense_opt_step", _p(p), _p(g), p.numel(), opt, float(lr), float(l2), _stream())
+
+
+# --------------------------------------------------------------------------- #
+# (e) a2a staging for row-sharded tables
+# --------------------------------------------------------------------------- #
+def unpack_rows(recv, pos, m, k, x, bias_out=None, lin_out=None):
+    _dev_check(recv)
+    n, KP = recv.shape
+    assert recv.is_contiguous() and pos.dtype == torch.int32 and x.stride(1) == 1
+    _C.call("rm_unpack_rows", _p(recv), n, KP, _p(pos), m, k, _p(x), x.stride(0), _p(bias_out), _p(lin_out), _stream())
+
+
+def pack_grad_rows(dx, x, ld, S, g_fm, g_lin, pos, m, k, KP):
+    n = pos.numel()
+    send = torch.empty(n, KP, dtype=torch.float32, device=pos.device)
+    _C.call("rm_pack_grad_rows", _p(dx), _p(x), ld, _p(S), _p(g_fm), _p(g_lin), n, KP, _p(pos), m, k, _p(send),
+            _stream())
+    return send

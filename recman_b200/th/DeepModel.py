@@ -93,6 +93,7 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
         self.device = torch.device("cuda")
         self._emb_status = None
         self.samples_seen = 0
+        self.shard = None  # th.dist.ShardPlan when the tables are row-sharded over ranks (th.dist.shard_model)
 
     # ------------------------------------------------------------------ front end shared by the models
     def _embedding_layer(self, use_bias, l2_mode="dense") -> FeatEmbeddingLayer:
@@ -101,6 +102,10 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
             use_bias=use_bias, seed=self.random_seed,
         )
         layer.status = self._status()
+        if self.shard is not None:
+            if layer.l2_reg and l2_mode != "touched":
+                raise NotImplementedError("row-sharded tables: use embedding_l2_reg=0 or embedding_l2_mode='touched'")
+            layer.set_shard(self.shard)
         if l2_mode == "touched":  # scale mode: regularise only rows that were looked up (SURVEY hard part 5)
             layer._upsert_variables()
             self.variables[layer.table_name].rm_l2_touched = float(layer.l2_reg)
@@ -140,6 +145,8 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
             want = self.feat_dict.sparse_feats + self.feat_dict.dense_feats
             if [f.name for f in feats] != [f.name for f in want]:
                 return None
+            if self.shard is not None:
+                linear.total = self.shard.total_local + n_dense  # id rows are sharded like the tables, tail replicated
             linear._upsert_variables()
             W = linear.effective_weight()
             flat = W.reshape(-1)
@@ -152,8 +159,14 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
             W_lin = self.variables[f"{linear.prefix}linear_w"]
             lin_table = lin_table.detach()
             lin_dense = None if lin_dense is None else lin_dense.detach().contiguous()
-        x, fm, lin = FrontEndFunction.apply(table, bias_table, W_lin, lin_table, lin_dense, lay.runs[0].offsets,
-                                            layer.total_rows, self._status(), ids, dense)
+        if self.shard is not None:
+            from .dist import ShardedFrontEndFunction
+
+            x, fm, lin = ShardedFrontEndFunction.apply(table, bias_table, W_lin, lin_table, lin_dense, self.shard,
+                                                       self._status(), ids, dense)
+        else:
+            x, fm, lin = FrontEndFunction.apply(table, bias_table, W_lin, lin_table, lin_dense, lay.runs[0].offsets,
+                                                layer.total_rows, self._status(), ids, dense)
         d = lay.m * k + n_dense
         if linear is not None:
             lin = lin + self.variables[f"{linear.prefix}linear_w0"]
@@ -227,7 +240,12 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
         """One optimisation step (xDeepFM.py:116-126): encode, forward, backward, fresh-optimizer update."""
         inputs = X if isinstance(X, DataInputs) else DataInputs(self.device).load(self.feat_dict, X, y)
         loss = self._loss(inputs)
-        loss.backward()
+        if self.shard is not None:
+            # every rank's loss is a mean over its local batch: 1/W makes the summed gradients those of the
+            # global-batch mean (and counts the replicated L2 terms once)
+            (loss / self.shard.world).backward()
+        else:
+            loss.backward()
         self.optimizer_step()
         self.samples_seen += inputs.batch_size
         return loss.detach()
@@ -238,6 +256,17 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
             raise ValueError(f"optimizer {opt!r}: the kernels implement adam / adagrad / gd / momentum")
         kind = _C.OPT_KINDS[opt]
         lr = float(self.hparams.get("learning_rate", 0.001))
+        if self.shard is not None:
+            from .dist import allreduce_dense
+
+            dense = []
+            for p in self.variables.values():
+                if not getattr(p, "rm_sparse_grads", None) and p.grad is not None:
+                    dense.append(p.grad)
+                tail = getattr(p, "rm_dense_tail", None)
+                if tail is not None:
+                    dense.append(tail[1])
+            allreduce_dense(dense, self.shard.group)
         for name, p in self.variables.items():
             sparse = pop_sparse_grads(p)
             tail = getattr(p, "rm_dense_tail", None)

@@ -177,6 +177,13 @@ class FeatEmbeddingLayer:
         self.total_rows = int(self.row_offsets[-1])
         self.status = None
         self._layout = None
+        self.shard = None  # th.dist.ShardPlan: this rank keeps ceil(V_f / W) rows per table
+
+    def set_shard(self, plan):
+        """Row-sharded mode: the parameters hold only this rank's rows (row r -> rank r % W, local r // W)."""
+        self.shard = plan
+        self.row_offsets = list(plan.local_offsets)
+        self.total_rows = int(plan.total_local)
 
     # names -------------------------------------------------------------------------------------------
     @property
@@ -191,8 +198,14 @@ class FeatEmbeddingLayer:
         k = self.embedding_size
         if self.table_name not in self.variables:
             table = torch.empty(self.total_rows, k, dtype=torch.float32, device=DEVICE)
-            for f, lo in zip(self.feats, self.row_offsets):
-                glorot_normal([f.feat_size, k], seed=self.seed, out=table[lo : lo + f.feat_size])
+            for i, (f, lo) in enumerate(zip(self.feats, self.row_offsets)):
+                rows = f.feat_size if self.shard is None else self.shard.local_sizes[i]
+                # fans come from the full table shape so that the init scale does not depend on the world size
+                std_shape = [f.feat_size, k]
+                fan_in, fan_out = calc_fan(std_shape)
+                std = math.sqrt(2.0 / (fan_in + fan_out))
+                g = torch.Generator(device=table.device).manual_seed(int(self.seed) + (0 if self.shard is None else self.shard.rank))
+                torch.nn.init.trunc_normal_(table[lo : lo + rows], mean=0.0, std=std, a=-2 * std, b=2 * std, generator=g)
             self.variables[self.table_name] = _param(table)
         if self.use_bias and self.bias_name not in self.variables:
             self.variables[self.bias_name] = _param(torch.zeros(self.total_rows, dtype=torch.float32, device=DEVICE))
