@@ -76,6 +76,9 @@ def main():
     torch.testing.assert_close(logit.double(), ref_logit.reshape(-1)[rank * b : (rank + 1) * b].double(), rtol=1e-5, atol=2e-6)
 
     def close(name, got, exp):
+        if exp.numel() == 0:  # a table with fewer rows than ranks leaves some shards empty
+            assert got.numel() == 0
+            return
         got, exp = got.double().cpu(), exp.double().cpu()
         atol = 1e-5 * max(float(exp.abs().max()), 1e-30)
         torch.testing.assert_close(got, exp, rtol=1e-5, atol=atol, msg=lambda m: f"{name}: {m}")
