@@ -1,5 +1,6 @@
 // Error plumbing, version and device check for librecman_b200.so.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <string.h>
@@ -11,6 +12,11 @@ static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int tune_variant(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;

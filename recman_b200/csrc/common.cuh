@@ -13,6 +13,8 @@ namespace rm {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// kernel-variant override for tuning runs: integer value of environment variable `name`, else `dflt`
+int tune_variant(const char* name, int dflt);
 
 #define RM_CHECK_ARG(cond, msg)                                       \
   do {                                                                \

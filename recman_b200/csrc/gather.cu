@@ -119,8 +119,8 @@ __global__ void __launch_bounds__(256) gather_pooled_kernel(const float* __restr
 // ---------------------------------------------------------------------------
 // fused gather + FM + first-order: one row group (LPR lanes) per sample
 // ---------------------------------------------------------------------------
-template <int LPR, int U>
-__global__ void __launch_bounds__(256) gather_fm_kernel(
+template <int LPR, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB) gather_fm_kernel(
     const float* __restrict__ table, const float* __restrict__ bias_table, const float* __restrict__ lin_table,
     const int64_t* __restrict__ offs, const int64_t* __restrict__ ids, const float* __restrict__ dense,
     const float* __restrict__ lin_dense, int n_dense, int64_t B, int m, int k, float* __restrict__ x, int64_t ld,
@@ -221,11 +221,17 @@ static int launch_gather_fm(const float* table, const float* bias_table, const f
                             const int64_t* ids, const float* dense, const float* lin_dense, int n_dense, int64_t B,
                             int m, int k, float* x, int64_t ld, float* fm_out, float* lin_out, float* sum_out,
                             int32_t* status, cudaStream_t st) {
-  constexpr int U = (LPR >= 16) ? 8 : 4;
   const int groups_per_cta = 256 / LPR;
   const int grid = grid_for(B, groups_per_cta, 8);
-  gather_fm_kernel<LPR, U><<<grid, 256, 0, st>>>(table, bias_table, lin_table, offs, ids, dense, lin_dense, n_dense, B,
-                                                 m, k, x, ld, fm_out, lin_out, sum_out, status);
+  const int variant = tune_variant("RM_TUNE_GATHER_FM", 1);
+#define RM_GFM(UU, MB)                                                                                              \
+  gather_fm_kernel<LPR, UU, MB><<<grid, 256, 0, st>>>(table, bias_table, lin_table, offs, ids, dense, lin_dense,     \
+                                                      n_dense, B, m, k, x, ld, fm_out, lin_out, sum_out, status)
+  if (variant == 0) RM_GFM(8, 2);
+  else if (variant == 2) RM_GFM(4, 3);
+  else if (variant == 3) RM_GFM(2, 6);
+  else RM_GFM(4, 4);
+#undef RM_GFM
   RM_LAUNCH_CHECK();
   return 0;
 }

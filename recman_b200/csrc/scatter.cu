@@ -88,7 +88,43 @@ static PlanWorkspace plan_layout(int64_t N, void* base) {
 // ---------------------------------------------------------------------------
 // FUSED == false : row(p) = grad[(p/m)*ld + (p%m)*k + :]
 // FUSED == true  : row(p) = dx[..] + g_fm[b]*(S[b,:] - x[..]); also k=1 sums of g_fm / g_lin
-template <int LPR, int U, bool FUSED>
+//
+// A row group owns SEG segments at a time and first issues the loads of all their FIRST elements (with uniform ids
+// almost every segment is a singleton, so this is where the memory-level parallelism comes from: the dependent chain
+// seg_start -> sorted_pos -> rows is walked for SEG segments concurrently); the remaining elements of longer
+// segments follow, U at a time.  Every segment is still summed in ascending position order.
+template <bool FUSED>
+struct RowSrc {
+  const float* grad;
+  const float* x;
+  const float* sum;
+  const float* g_fm;
+  const float* g_lin;
+  int64_t ld;
+  uint32_t m;
+  int k;
+  __device__ __forceinline__ void load(uint32_t p, int c, float4& v, float& gf, float& gl) const {
+    const uint32_t b = p / m, f = p - b * m;
+    const int64_t o = (int64_t)b * ld + (int64_t)f * k + 4 * c;
+    v = grad ? ld4(grad + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+    gf = 0.f;
+    gl = 0.f;
+    if (FUSED) {
+      if (g_fm) {
+        gf = g_fm[b];
+        const float4 xv = ld4(x + o);
+        const float4 sv = ld4(sum + (int64_t)b * k + 4 * c);
+        v.x += gf * (sv.x - xv.x);
+        v.y += gf * (sv.y - xv.y);
+        v.z += gf * (sv.z - xv.z);
+        v.w += gf * (sv.w - xv.w);
+      }
+      if (g_lin) gl = g_lin[b];
+    }
+  }
+};
+
+template <int LPR, int SEG, int U, bool FUSED>
 __global__ void __launch_bounds__(256) segment_reduce_kernel(
     const float* __restrict__ grad, const float* __restrict__ x, int64_t ld, const float* __restrict__ sum,
     const float* __restrict__ g_fm, const float* __restrict__ g_lin, uint32_t m, int k,
@@ -100,62 +136,60 @@ __global__ void __launch_bounds__(256) segment_reduce_kernel(
   const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
   const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / LPR;
   const int32_t NU = *n_unique;
-  for (int64_t u = group; u < NU; u += n_groups) {
-    const int32_t s = seg_start[u], e = seg_start[u + 1];
-    float bias_acc = 0.f, lin_acc = 0.f;
+  const RowSrc<FUSED> src{grad, x, sum, g_fm, g_lin, ld, m, k};
+  for (int64_t u0 = group * SEG; u0 < NU; u0 += n_groups * SEG) {
+    int32_t s[SEG], e[SEG];
+#pragma unroll
+    for (int t = 0; t < SEG; ++t) {
+      const bool live = u0 + t < NU;
+      s[t] = live ? seg_start[u0 + t] : 0;
+      e[t] = live ? seg_start[u0 + t + 1] : 0;
+    }
     for (int c = lir; c < k4; c += LPR) {  // lane 0 always owns column chunk 0, so it also carries the k=1 sums
-      const bool col_ok = true;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int32_t j0 = s; j0 < e; j0 += U) {
-        float4 v[U], xv[U], sv[U];
-        float gf[U], gl[U];
+      uint32_t p0[SEG];
 #pragma unroll
-        for (int t = 0; t < U; ++t) {
-          v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-          xv[t] = v[t];
-          sv[t] = v[t];
-          gf[t] = 0.f;
-          gl[t] = 0.f;
-          if (j0 + t < e) {
-            const uint32_t p = (uint32_t)sorted_pos[j0 + t];
-            const uint32_t b = p / m, f = p - b * m;
-            const int64_t o = (int64_t)b * ld + (int64_t)f * k + 4 * c;
-            if (col_ok && grad) v[t] = ld4(grad + o);
-            if (FUSED) {
-              if (g_fm) {
-                gf[t] = g_fm[b];
-                if (col_ok) {
-                  xv[t] = ld4(x + o);
-                  sv[t] = ld4(sum + (int64_t)b * k + 4 * c);
-                }
-              }
-              if (g_lin) gl[t] = g_lin[b];
-            }
+      for (int t = 0; t < SEG; ++t) p0[t] = s[t] < e[t] ? (uint32_t)sorted_pos[s[t]] : 0u;
+      float4 acc[SEG];
+      float ba[SEG], la[SEG];
+#pragma unroll
+      for (int t = 0; t < SEG; ++t) {
+        acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ba[t] = 0.f;
+        la[t] = 0.f;
+        if (s[t] < e[t]) src.load(p0[t], c, acc[t], ba[t], la[t]);
+      }
+#pragma unroll
+      for (int t = 0; t < SEG; ++t) {
+        for (int32_t j0 = s[t] + 1; j0 < e[t]; j0 += U) {  // longer segments: U rows in flight, added in order
+          float4 v[U];
+          float gf[U], gl[U];
+#pragma unroll
+          for (int i = 0; i < U; ++i) {
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            gf[i] = 0.f;
+            gl[i] = 0.f;
+            if (j0 + i < e[t]) src.load((uint32_t)sorted_pos[j0 + i], c, v[i], gf[i], gl[i]);
           }
-        }
 #pragma unroll
-        for (int t = 0; t < U; ++t) {
-          if (j0 + t < e) {  // strictly ascending position order: the sum is reproducible
-            if (FUSED) {
-              acc.x += v[t].x + gf[t] * (sv[t].x - xv[t].x);
-              acc.y += v[t].y + gf[t] * (sv[t].y - xv[t].y);
-              acc.z += v[t].z + gf[t] * (sv[t].z - xv[t].z);
-              acc.w += v[t].w + gf[t] * (sv[t].w - xv[t].w);
-              if (c == lir) {
-                bias_acc += gf[t];
-                lin_acc += gl[t];
-              }
-            } else {
-              acc.x += v[t].x; acc.y += v[t].y; acc.z += v[t].z; acc.w += v[t].w;
+          for (int i = 0; i < U; ++i) {
+            if (j0 + i < e[t]) {
+              acc[t].x += v[i].x; acc[t].y += v[i].y; acc[t].z += v[i].z; acc[t].w += v[i].w;
+              ba[t] += gf[i];
+              la[t] += gl[i];
             }
           }
         }
       }
-      if (out_rows) st4(out_rows + u * k + 4 * c, acc);
-    }
-    if (FUSED && lir == 0) {
-      if (out_bias) out_bias[u] = bias_acc;
-      if (out_lin) out_lin[u] = lin_acc;
+#pragma unroll
+      for (int t = 0; t < SEG; ++t) {
+        if (u0 + t < NU) {
+          if (out_rows) st4(out_rows + (u0 + t) * k + 4 * c, acc[t]);
+          if (FUSED && c == 0) {
+            if (out_bias) out_bias[u0 + t] = ba[t];
+            if (out_lin) out_lin[u0 + t] = la[t];
+          }
+        }
+      }
     }
   }
 }
@@ -192,9 +226,15 @@ static int launch_segment_reduce(const float* grad, const float* x, int64_t ld, 
                                  const float* g_lin, int m, int k, int64_t N, const int32_t* sorted_pos,
                                  const int32_t* seg_start, const int32_t* n_unique, float* out_rows, float* out_bias,
                                  float* out_lin, cudaStream_t st) {
-  const int grid = grid_for(N, 256 / LPR, 8);  // n_unique <= N lives on the device: size for the worst case
-  segment_reduce_kernel<LPR, 4, FUSED><<<grid, 256, 0, st>>>(grad, x, ld, sum, g_fm, g_lin, (uint32_t)m, k, sorted_pos,
-                                                             seg_start, n_unique, out_rows, out_bias, out_lin);
+  const int variant = tune_variant("RM_TUNE_SEGRED", FUSED ? 2 : 4);  // measured best on B200 (profiles/r1_kbench.json)
+#define RM_SRK(SEG)                                                                                                  \
+  segment_reduce_kernel<LPR, SEG, 4, FUSED><<<grid_for(N, (256 / LPR) * SEG, 8), 256, 0, st>>>(                       \
+      grad, x, ld, sum, g_fm, g_lin, (uint32_t)m, k, sorted_pos, seg_start, n_unique, out_rows, out_bias, out_lin)
+  // n_unique <= N lives on the device: the grid is sized for the worst case
+  if (variant == 1) RM_SRK(1);
+  else if (variant == 2) RM_SRK(2);
+  else RM_SRK(4);
+#undef RM_SRK
   RM_LAUNCH_CHECK();
   return 0;
 }

@@ -80,7 +80,7 @@ class DCN(DeepModel):
         final_logit = dnn_logit + cn_logit + dnn_logit
         if self.use_linear:
             final_logit = final_logit + linear_logit
-        self.final_logit = final_logit
+        self.final_logit = final_logit.detach()  # detached: keeping the graph alive would pin its grad accumulators
         return PredictionLayer(self.variables, self.task, use_bias=False)(final_logit)
 
     def _loss(self, inputs):

@@ -92,7 +92,7 @@ class DeepFM(DeepModel):
                            hp["deep_activation"], hp["deep_l2_reg"])
             self.dnn.training = training
             final_logit = final_logit + self.dnn(dnn_input)
-        self.final_logit = final_logit
+        self.final_logit = final_logit.detach()  # detached: keeping the graph alive would pin its grad accumulators
         return PredictionLayer(self.variables, self.task, use_bias=False)(final_logit)
 
     def _loss(self, inputs):

@@ -102,6 +102,12 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
             use_bias=use_bias, seed=self.random_seed,
         )
         layer.status = self._status()
+        # the layout holds small device tensors built from host lists: build once per model (also keeps the
+        # step free of host->device copies, a requirement for CUDA-graph capture)
+        key = ("layout", use_bias, id(self.shard))
+        cache = self.__dict__.setdefault("_cache", {})
+        if key in cache:
+            layer._layout = cache[key]
         if self.shard is not None:
             if layer.l2_reg and l2_mode != "touched":
                 raise NotImplementedError("row-sharded tables: use embedding_l2_reg=0 or embedding_l2_mode='touched'")
@@ -110,6 +116,8 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
             layer._upsert_variables()
             self.variables[layer.table_name].rm_l2_touched = float(layer.l2_reg)
             layer.l2_reg = 0.0
+        if key not in cache:
+            cache[key] = layer.layout()
         return layer
 
     def _status(self):
@@ -239,16 +247,68 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
     def fit_on_batch(self, X, y):
         """One optimisation step (xDeepFM.py:116-126): encode, forward, backward, fresh-optimizer update."""
         inputs = X if isinstance(X, DataInputs) else DataInputs(self.device).load(self.feat_dict, X, y)
+        self.samples_seen += inputs.batch_size
+        if getattr(self, "_graph", None) is not None:
+            loss = self._graph_step(inputs)
+            if loss is not None:
+                return loss
+        # eager: with sharded tables every rank's loss is a mean over its local batch; 1/W makes the summed
+        # gradients those of the global-batch mean (and counts the replicated L2 terms once)
+        return self._eager_step(inputs)
+
+    # ------------------------------------------------------------------ CUDA-graphed step (N1)
+    def compile_step(self, example: DataInputs, warmup: int = 3):
+        """Capture one whole training step (forward, backward, K2, optimizer) into a CUDA graph.
+
+        The step contains no host synchronisation (K2's unique-row count stays on the device) and every buffer it
+        touches is allocated from the graph's private pool, so the launch-bound eager sequence (~150 launches for
+        DeepFM) becomes one ``cudaGraphLaunch``.  ``fit_on_batch`` then copies the batch into the static input
+        buffers and replays.  Not available with row-sharded tables yet (the exchange has a host-side split-size
+        sync).  The ``warmup`` eager steps are real optimisation steps on ``example``.
+        """
+        if self.shard is not None:
+            raise NotImplementedError("compile_step with row-sharded tables")
+        from .. import ops as _ops
+
+        st = DataInputs.from_tensors(
+            self.feat_dict, example.sparse_ids.clone(), None if example.dense is None else example.dense.clone(),
+            example["y"].clone())
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                self._eager_step(st)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        before = _ops.launch_count()
+        with torch.cuda.graph(graph):
+            loss = self._eager_step(st)
+        self._graph_launches = _ops.launch_count() - before
+        self._graph, self._graph_inputs, self._graph_loss = graph, st, loss
+        return self
+
+    def _eager_step(self, inputs: DataInputs):
         loss = self._loss(inputs)
         if self.shard is not None:
-            # every rank's loss is a mean over its local batch: 1/W makes the summed gradients those of the
-            # global-batch mean (and counts the replicated L2 terms once)
             (loss / self.shard.world).backward()
         else:
             loss.backward()
         self.optimizer_step()
-        self.samples_seen += inputs.batch_size
         return loss.detach()
+
+    def _graph_step(self, inputs: DataInputs):
+        st = self._graph_inputs
+        if inputs is not st:
+            if inputs.sparse_ids.shape != st.sparse_ids.shape:
+                return None  # ragged last batch: run it eagerly
+            st.sparse_ids.copy_(inputs.sparse_ids, non_blocking=True)
+            if st.dense is not None:
+                st.dense.copy_(inputs.dense, non_blocking=True)
+            st["y"].copy_(inputs["y"], non_blocking=True)
+        self._graph.replay()
+        return self._graph_loss
 
     def optimizer_step(self):
         opt = self.hparams.get("optimizer", "adam")

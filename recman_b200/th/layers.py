@@ -408,6 +408,8 @@ class LinearLayer:
 
     def l2(self):
         self._upsert_variables()
+        if not self.l2_reg:  # no graph through linear_w: its gradient stays sparse
+            return torch.zeros((), device=DEVICE)
         return self.l2_reg * _l2(self.variables[f"{self.prefix}linear_w"])
 
 
@@ -529,6 +531,8 @@ class DNN:
 
     def l2(self):
         v, p = self.variables, self.prefix
+        if not self.l2_reg:
+            return torch.zeros((), device=DEVICE)
         terms = [self.l2_reg * _l2(v[f"{p}dnn_layer_{i}_weights"]) for i in range(len(self.hidden_units))]
         terms.append(self.l2_reg * _l2(v[f"{p}dnn_w"]))
         return torch.stack(terms).sum()
@@ -602,6 +606,8 @@ class CIN:
 
     def l2(self):
         v, p = self.variables, self.prefix
+        if not self.l2_reg:
+            return torch.zeros((), device=DEVICE)
         terms = [self.l2_reg * _l2(v[f"{p}cin_filter_{i}"]) for i in range(len(self.cross_layer_units))]
         terms.append(self.l2_reg * _l2(v[f"{p}cin_w"]))
         return torch.stack(terms).sum()

@@ -64,7 +64,7 @@ class xDeepFM(DeepModel):
         )
         dnn_logit = self.dnn(dnn_input)
         final_logit = linear_logit + cin_logit + dnn_logit
-        self.final_logit = final_logit
+        self.final_logit = final_logit.detach()  # detached: keeping the graph alive would pin its grad accumulators
         return PredictionLayer(self.variables, self.task)(final_logit)
 
     def _loss(self, inputs):

@@ -120,3 +120,33 @@ def test_predict_and_evaluate_batches():
     res = model.evaluate(X, y)
     assert len(res) == 2 and all(np.isfinite(r) for r in res)
     assert len(model.history) == 2
+
+
+@pytest.mark.parametrize("model_name", ["DeepFM", "DCN"])
+def test_cuda_graph_step_equals_eager(model_name):
+    """compile_step: the captured fwd+bwd+K2+optimizer step replays to the same parameters as eager steps."""
+    from recman_b200 import th
+    from recman_b200.th.input import DataInputs
+
+    fd = pu.make_feat_dict(CRITEO_SMALL, n_dense=13)
+    batches = [pu.synth_batch(fd, 256, seed=40 + i) for i in range(4)]
+    kw = dict(embedding_size=16, deep_hidden_units=(32, 32), deep_dropout=(1, 1, 1), batch_size=256, learning_rate=0.01,
+              embedding_l2_reg=0.0, linear_l2_reg=0.0, optimizer="adagrad")
+    first = DataInputs("cuda").load(fd, *batches[0])
+    # compile_step runs `warmup` real steps on `first` (capture itself only records): mirror that eagerly
+    eager2 = getattr(th, model_name)(fd, **kw)
+    graph2 = getattr(th, model_name)(fd, **kw)
+    for mdl in (eager2, graph2):
+        with torch.no_grad():
+            mdl._out(DataInputs("cuda").load(fd, *batches[0]))
+        pu.randomize_variables(mdl, seed=5)
+    eager2.fit_on_batch(first, None)      # the warm-up step
+    graph2.compile_step(first, warmup=1)
+    for X, y in batches[1:]:
+        le = eager2.fit_on_batch(X, y)
+        lg = graph2.fit_on_batch(X, y)
+        torch.testing.assert_close(lg, le, rtol=1e-6, atol=1e-7)
+    for name in eager2.variables:
+        torch.testing.assert_close(graph2.variables[name].data, eager2.variables[name].data, rtol=1e-6, atol=1e-7,
+                                   msg=lambda m_: f"{name}: {m_}")
+    graph2.check_ids()
