@@ -30,8 +30,9 @@ int rm_cin_layer_fwd(const float* x0, int64_t x0_bstride, const float* xk, int64
 }
 
 size_t rm_cin_layer_bwd_workspace_bytes(int64_t B, int32_t m, int32_t H, int32_t D, int32_t N, int32_t precision) {
-  (void)precision;
   if (B < 0 || m <= 0 || H <= 0 || D <= 0 || N <= 0) return 0;
+  if (precision != RM_CIN_FP32_SIMT && rm::cin_tc_bwd_supported(B, m, H, D, N))
+    return rm::cin_tc_bwd_workspace(B, m, H, D, N, precision);
   return rm::cin_bwd_layout(B, m, H, D, N, nullptr).total;
 }
 
@@ -52,7 +53,10 @@ int rm_cin_layer_bwd(const float* x0, int64_t x0_bstride, const float* xk, int64
   RM_CHECK_ARG(x0 && xk && W && pre && dout && dx0 && dxk && workspace, "null pointer");
   RM_CHECK_ARG(x0_bstride >= (int64_t)m * D && xk_bstride >= (int64_t)H * D && dxk_bstride >= (int64_t)H * D,
                "batch stride too small");
-  // The backward GEMMs run on the CUDA-core fp32 path for every `precision` (tensor-core backward: next round).
+  if (precision != RM_CIN_FP32_SIMT && cin_tc_bwd_supported(B, m, H, D, N) && x0_bstride % 4 == 0 &&
+      xk_bstride % 4 == 0 && aligned16(x0) && aligned16(xk))
+    return cin_bwd_tc(x0, x0_bstride, xk, xk_bstride, W, pre, dout, B, m, H, D, N, act, precision, dW, dbias, dx0, dxk,
+                      dxk_bstride, workspace, workspace_bytes, st);
   return cin_bwd_simt(x0, x0_bstride, xk, xk_bstride, W, pre, dout, B, m, H, D, N, act, dW, dbias, dx0, dxk,
                       dxk_bstride, workspace, workspace_bytes, st);
 }

@@ -20,6 +20,18 @@ int cin_bwd_simt(const float* x0, int64_t bs0, const float* xk, int64_t bsk, con
                  const float* dout, int64_t B, int m, int H, int D, int N, int act, float* dW, float* dbias,
                  float* dx0, float* dxk, int64_t dbsk, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
+// dF = dout * act'(pre) and dbias[n] = sum_{b,d} dF (deterministic); shared by the SIMT and tensor-core backward
+int cin_dF_dbias(const float* dout, const float* pre, int64_t B, int N, int D, int act, float* dF, float* dbias,
+                 cudaStream_t st);
+
+// cin_tc_bwd.cu
+bool cin_tc_bwd_supported(int64_t B, int m, int H, int D, int N);
+size_t cin_tc_bwd_workspace(int64_t B, int m, int H, int D, int N, int precision);
+int cin_bwd_tc(const float* x0, int64_t bs0, const float* xk, int64_t bsk, const float* W, const float* pre,
+               const float* dout, int64_t B, int m, int H, int D, int N, int act, int precision, float* dW,
+               float* dbias, float* dx0, float* dxk, int64_t dbsk, void* workspace, size_t workspace_bytes,
+               cudaStream_t st);
+
 // cin_tc.cu
 bool cin_tc_supported(int64_t B, int m, int H, int D, int N);
 size_t cin_tc_fwd_workspace(int64_t B, int m, int H, int D, int N, int precision);

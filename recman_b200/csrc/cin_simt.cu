@@ -360,6 +360,16 @@ __global__ void __launch_bounds__(256) cin_dw_final_kernel(const float* __restri
 // ---------------------------------------------------------------------------------------------
 static int simt_tb(int D) { return D <= CIN_BM ? CIN_BM / D : 0; }
 
+int cin_dF_dbias(const float* dout, const float* pre, int64_t B, int N, int D, int act, float* dF, float* dbias,
+                 cudaStream_t st) {
+  const int64_t total = B * (int64_t)N * D;
+  cin_dF_kernel<<<grid_for(total, 256, 8), 256, 0, st>>>(dout, pre, total, act, dF);
+  RM_LAUNCH_CHECK();
+  cin_dbias_kernel<<<N, 256, 0, st>>>(dF, (int)B, N, D, dbias);
+  RM_LAUNCH_CHECK();
+  return 0;
+}
+
 int cin_fwd_simt(const float* x0, int64_t bs0, const float* xk, int64_t bsk, const float* W, const float* bias,
                  int64_t B, int m, int H, int D, int N, int act, float* out, float* pre, cudaStream_t st) {
   const int TB = simt_tb(D);
@@ -404,11 +414,10 @@ int cin_bwd_simt(const float* x0, int64_t bs0, const float* xk, int64_t bsk, con
   }
   const size_t smem = ((size_t)2 * TB * (m + H) * D + CIN_BK * CIN_AS + CIN_BK * CIN_BN) * sizeof(float);
   RM_UNSUPPORTED(smem <= 227 * 1024, "m + H too large for the backward's shared-memory accumulators");
-  const int64_t total = B * (int64_t)N * D;
-  cin_dF_kernel<<<grid_for(total, 256, 8), 256, 0, st>>>(dout, pre, total, act, ws.dF);
-  RM_LAUNCH_CHECK();
-  cin_dbias_kernel<<<N, 256, 0, st>>>(ws.dF, (int)B, N, D, dbias);
-  RM_LAUNCH_CHECK();
+  {
+    const int rc = cin_dF_dbias(dout, pre, B, N, D, act, ws.dF, dbias, st);
+    if (rc) return rc;
+  }
   RM_CUDA(cudaFuncSetAttribute(cin_bwd_dx_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cin_bwd_dx_simt_kernel<<<(unsigned)ceil_div(B, TB), 256, smem, st>>>(x0, bs0, xk, bsk, W, ws.dF, (int)B, m, H, D, N,
                                                                       TB, dx0, dxk, dbsk);

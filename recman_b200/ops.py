@@ -347,6 +347,9 @@ def cin_layer_bwd(x0, xk, W, pre, dout, act: int, precision: int, dx0, dxk):
     dbias = torch.empty(N, dtype=torch.float32, device=dev)
     ws_bytes = _C.lib.rm_cin_layer_bwd_workspace_bytes(B, m, H, D, N, precision)
     ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+    if precision != 0 and D % 4 == 0 and m <= 32 and N <= 256:  # the tensor-core backward ran (cin.cu)
+        global _last_cin_ws
+        _last_cin_ws = ws
     _C.call(
         "rm_cin_layer_bwd", _p(x0), x0.stride(0), _p(xk), xk.stride(0), _p(W), _p(pre), _p(dout), B, m, H, D, N, act, precision,
         _p(dW), _p(dbias), _p(dx0), _p(dxk), dxk.stride(0), _p(ws), ws_bytes, _stream(),

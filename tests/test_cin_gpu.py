@@ -153,6 +153,44 @@ def test_cin_layer_tcgen05_fwd(B, m, H, D, N, precision, rtol, atol, act):
     assert torch.equal(out, out2)
 
 
+@pytest.mark.parametrize("B,m,H,D,N", [c for c in TC_CASES if c[3] % 4 == 0] + [(2048, 26, 100, 16, 200)])
+@pytest.mark.parametrize("precision,tol", [(1, 5e-5), (2, 4e-3)])
+@pytest.mark.parametrize("act", [2])
+def test_cin_layer_tcgen05_bwd(B, m, H, D, N, precision, tol, act):
+    """tensor-core backward (dZ GEMM with in-TMEM contraction into dx0/dxk; slabbed dW GEMM) vs the fp64 oracle."""
+    from recman_b200 import ops
+
+    x0, xk_full, xk, W, bias, dout = _make(B, m, H, D, N, B * 5 + N)
+    out64, pre64 = _layer_oracle(x0, xk, W, bias, act)
+    xk_dev = xk_full.float().cuda()[:, :H]
+    x0d, Wd, bd = x0.detach().float().cuda(), W.detach().float().cuda(), bias.detach().float().cuda()
+    _, pre = ops.cin_layer_fwd(x0d, xk_dev, Wd, bd, act, 0)
+    # The activation derivative is discontinuous at 0: an element whose fp32 pre-activation rounds to the other side
+    # of the kink than the fp64 one (expected ~B*N*D*1e-7 of them) flips a whole dF entry.  The backward is handed
+    # `pre`, so the reference uses the mask of that same `pre` on the fp64 linear part.
+    slope = torch.where(pre.cpu().double() > 0, 1.0, 0.2) if act == 2 else torch.ones_like(pre64)
+    pre64.backward(dout * slope)
+    doutd = dout.float().cuda()
+
+    def run():
+        dx0 = torch.ones(B, m, D, device="cuda")
+        dxk_full = torch.zeros(B, 2 * H, D, device="cuda")
+        dW, dbias = ops.cin_layer_bwd(x0d, xk_dev, Wd, pre, doutd, act, precision, dx0, dxk_full[:, :H])
+        torch.cuda.synchronize()
+        assert ops.cin_tc_status() == 0, "a pipeline wait timed out inside the tcgen05 backward"
+        return dW, dbias, dx0, dxk_full
+
+    dW, dbias, dx0, dxk_full = run()
+    for name, got, exp in [("dW", dW, W.grad), ("dbias", dbias, bias.grad), ("dx0", dx0 - 1, x0.grad),
+                           ("dxk", dxk_full[:, :H], xk.grad)]:
+        e = exp.double()
+        torch.testing.assert_close(got.cpu().double(), e, rtol=tol, atol=tol * float(e.abs().max()),
+                                   msg=lambda m_: f"{name}: {m_}")
+    assert torch.all(dxk_full[:, H:] == 0)
+    dW2, dbias2, dx0b, dxkb = run()  # deterministic
+    assert torch.equal(dW, dW2) and torch.equal(dbias, dbias2) and torch.equal(dx0, dx0b) and torch.equal(dxk_full, dxkb)
+
+
 def test_cin_tcgen05_notebook_kat():
     from recman_b200 import ops
 
