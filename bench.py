@@ -166,16 +166,36 @@ def build_model(w, args, world, rank):
 
 def algorithmic_bytes(kind, B, m, k, n_dense, n_unique=None):
     """Algorithmic HBM bytes per launch."""
-    if kind == "rm_gather_fm_fwd":
+    if kind in ("rm_gather_fm_fwd", "rm_gather_fm_fwd_p2p"):
         # ids 8 + row read 4k + row write 4k + bias 4 + lin 4 per (b,f); dense read+write; S write; 2 logits
         return B * (m * (8 + 8 * k + 8) + 8 * n_dense + 4 * k + 8)
     if kind == "rm_emb_fm_bwd":
         # per id: position 4 + dx row 4k + x row 4k; S row + 2 scalars per sample; per unique row: 4k + 2*4 written
         nu = n_unique if n_unique is not None else B * m
         return B * m * (4 + 8 * k) + B * (4 * k + 8) + nu * (4 * k + 8)
+    if kind == "rm_segment_reduce_p2p":
+        # per owned id: global position 4 + gradient row (k+4)*4 (local or NVLink); per unique row: 4k + 2*4 written
+        nu = n_unique if n_unique is not None else B * m
+        return B * m * (4 + 4 * (k + 4)) + nu * (4 * k + 8)
+    if kind == "rm_pack_grad_rows":
+        # per (b,f): dx row + x row read, G row (k+4) written; S row + 2 scalars per sample
+        return B * m * (8 * k + 4 * (k + 4)) + B * (4 * k + 8)
     # rm_sparse_opt_step is launched once per table kind (k = 64, 1, 1): its averaged time is not a single-kernel
     # figure, so it is listed without bytes
     return None
+
+
+def cin_flops_per_step(w, B, k):
+    """Algorithmic flops of the CIN contraction per step: fwd 2*B*D*m*H_i*N_i per layer; bwd = 2x fwd."""
+    if w.get("cin") is None:
+        return None
+    m, D = w["m"], k
+    H, total = m, 0
+    units = list(w["cin"])
+    for i, N in enumerate(units):
+        total += 2 * B * D * m * H * N
+        H = N // 2 if i < len(units) - 1 else N  # split-half: first half feeds the next layer
+    return total
 
 
 def run_ours(args):
@@ -234,8 +254,8 @@ def run_ours(args):
     launches_per_step = (ops.launch_count() - launches0) // prof_steps
     prof = ops.disable_profile()
     graphed = False
-    if world == 1 and not args.no_graph:
-        model.compile_step(resident[0], warmup=1)
+    if not args.no_graph and (world == 1 or model.shard.peer is not None):
+        model.compile_step(resident[0], warmup=1)  # peer-memory sharding has no host sync: capturable with NCCL inside
         graphed = True
         for i in range(args.warmup):
             step_resident(i)
@@ -300,14 +320,40 @@ def run_ours(args):
             ab = algorithmic_bytes(name, B, m, k, n_dense, n_unique)
             kernels[name] = {"avg_ms": round(avg, 4), "launches": count, "ms_per_step": round(total_ms / prof_steps, 4),
                              "alg_bytes": ab, "gbs": (round(ab / (avg * 1e-3) / 1e9, 1) if ab and avg > 0 else None)}
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {})
+        except Exception:
+            pass
         cand = [(v["ms_per_step"], n) for n, v in kernels.items() if v["alg_bytes"]]
         roofline = None
-        if cand:
+        cin_f = cin_flops_per_step(w, B, k)
+        if cin_f and "rm_cin_layer_bwd" in kernels:
+            # the CIN contraction dominates xDeepFM: tensor-pipe roofline.  Peak = measured dense bf16 (the number
+            # MEASURED_PEAKS.json holds); kind::tf32 runs at half the bf16 rate and the 3xTF32 parity mode issues 3 MMAs
+            # per algorithmic product, so frac understates pipe occupancy (ncu: profiles/*c3*_ncu_full.json).
+            tpeak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1376.3)))  # timed inside a step
+            fwd_ms, bwd_ms = kernels["rm_cin_layer_fwd"]["ms_per_step"], kernels["rm_cin_layer_bwd"]["ms_per_step"]
+            for nm, fl, ms in (("rm_cin_layer_fwd", cin_f, fwd_ms), ("rm_cin_layer_bwd", 2 * cin_f, bwd_ms)):
+                kernels[nm]["alg_flops_per_step"] = fl
+                kernels[nm]["tflops"] = round(fl / (ms * 1e-3) / 1e12, 1) if ms > 0 else None
+            passes = 3 if args.cin_precision == "3xtf32" else 1
+            dom = "rm_cin_layer_bwd" if bwd_ms >= fwd_ms else "rm_cin_layer_fwd"
+            ach = kernels[dom]["tflops"]
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s",
+                        "frac": round(ach / tpeak, 4), "peak_source": "measured dense bf16, sustained (MEASURED_PEAKS.json)"
+                        if peaks else "fallback 1376 TFLOP/s", "traffic": (traffic.get(dom) or {}).get("bytes"),
+                        "traffic_source": (traffic.get(dom) or {}).get("source"),
+                        "mma_passes": passes, "issued_tflops": round(ach * passes, 1),
+                        "frac_of_tf32_peak_issued": round(ach * passes / (tpeak / 2), 4),
+                        "avg_launch_ms": kernels[dom]["avg_ms"], "alg_flops_per_step": kernels[dom]["alg_flops_per_step"]}
+        elif cand:
             _, dom = max(cand)
             kv = kernels[dom]
             roofline = {"kernel": dom, "bound": "hbm", "achieved": kv["gbs"], "peak": hbm_peak, "unit": "GB/s",
                         "frac": round(kv["gbs"] / hbm_peak, 4), "frac_of_nominal_8000": round(kv["gbs"] / 8000.0, 4),
-                        "peak_source": peak_src, "traffic": None, "avg_launch_ms": kv["avg_ms"],
+                        "peak_source": peak_src, "traffic": (traffic.get(dom) or {}).get("bytes"),
+                        "traffic_source": (traffic.get(dom) or {}).get("source"), "avg_launch_ms": kv["avg_ms"],
                         "alg_bytes_per_launch": kv["alg_bytes"]}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -320,7 +366,9 @@ def run_ours(args):
                        "n_dense": n_dense, "batch_per_gpu": B, "global_batch": B * world, "ids": args.ids,
                        "optimizer": "adam (fresh per batch, as the reference)", "l2_flush":
                        "inputs larger than L2: tables %.1f GB, 8 rotating id batches" % (m * rows * k * 4 / 1e9),
-                       "parallelism": ("single GPU" if world == 1 else f"row-sharded tables x{world} + DP dense"),
+                       "parallelism": ("single GPU" if world == 1 else f"row-sharded tables x{world} "
+                                       f"({'NVLink peer-memory gather/reduce' if model.shard.peer is not None else 'NCCL all-to-all'})"
+                                       " + DP dense all-reduce"),
                        "step_launch": ("CUDA graph replay" if graphed else "eager")},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "ms_per_step": round(e2e_ms_step, 4),
@@ -334,7 +382,12 @@ def run_ours(args):
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        # a captured graph that holds NCCL kernels plus cudaIpc peer mappings makes the orderly teardown
+        # (destroy_process_group / graph destruction) wait on the peers: leave without it
+        os._exit(0)
     return out
 
 

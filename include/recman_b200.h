@@ -148,6 +148,17 @@ int rm_emb_fm_bwd(const float* dx, const float* x, int64_t ld, const float* sum,
                   const int32_t* seg_start, const int32_t* n_unique, float* out_rows, float* out_bias,
                   float* out_lin, void* stream);
 
+/* rm_emb_fm_bwd fused with the optimizer (N1): instead of emitting the summed rows,
+ * table[uniq_rows[u],:] (and bias_table / lin_table[uniq_rows[u]] when g_fm / g_lin
+ * are given) receive the stateless first-step update of rm_sparse_opt_step in the
+ * same pass; bit-identical to rm_emb_fm_bwd followed by rm_sparse_opt_step. */
+int rm_emb_fm_bwd_update(const float* dx, const float* x, int64_t ld, const float* sum,
+                         const float* g_fm, const float* g_lin, int32_t m, int32_t k, int64_t N,
+                         const int32_t* sorted_pos, const int32_t* seg_start,
+                         const int64_t* uniq_rows, const int32_t* n_unique, float* table,
+                         float* bias_table, float* lin_table, int32_t opt, float lr, float l2,
+                         void* stream);
+
 /* ------------------------------------------------------------------------- *
  * K4  DCN cross network.  Call site recman/tf/core/DCN.py:135-137 (the class
  * itself is absent from the reference; arithmetic = arXiv 1708.05123 eq. 3):
@@ -218,7 +229,7 @@ int rm_dense_opt_step(float* p, const float* g, int64_t n, int32_t opt, float lr
  * [e_0..e_{k-1} | bias | lin | 0 | 0].  pos[j] = b*m + f of routed row j.
  * rm_unpack_rows: x[b*ld + f*k + :k] = recv[j,:k]; bias_out[pos] = recv[j,k];
  *                 lin_out[pos] = recv[j,k+1] (both nullable).
- * rm_pack_grad_rows: send[j,:k] = dx[b*ld+f*k+:] + g_fm[b]*(S[b,:]-x[b*ld+f*k+:]);
+ * rm_pack_grad_rows (pos NULL = identity): send[j,:k] = dx[b*ld+f*k+:] + g_fm[b]*(S[b,:]-x[b*ld+f*k+:]);
  *                 send[j,k] = g_fm[b]; send[j,k+1] = g_lin[b]  (dx, g_fm, g_lin nullable).
  * The owner side uses rm_gather_fwd (out_stride = KP) and rm_segment_plan/reduce
  * (m = 1, k = KP) directly on the exchange buffers.
@@ -228,6 +239,60 @@ int rm_unpack_rows(const float* recv, int64_t n, int32_t KP, const int32_t* pos,
 int rm_pack_grad_rows(const float* dx, const float* x, int64_t ld, const float* sum, const float* g_fm,
                       const float* g_lin, int64_t n, int32_t KP, const int32_t* pos, int32_t m, int32_t k,
                       float* send, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (e') row-sharded tables over NVLink PEER MEMORY (W a power of two <= 8, one
+ * NVSwitch box): the lookup and the gradient reduction read their rows straight
+ * from the owning rank - no all-to-all, no pack/unpack pass, no host sync.
+ *
+ * rm_p2p_alloc: cudaMalloc + cudaIpcGetMemHandle (handle64: 64 host bytes to be
+ *   exchanged between the ranks); rm_p2p_open maps a peer's allocation
+ *   (cudaIpcOpenMemHandle, lazy peer access); rm_p2p_close / rm_p2p_free undo.
+ * rm_gather_fm_fwd_p2p: rm_gather_fm_fwd where row `id` of field f is read from
+ *   tables[id % W] + (local_offsets[f] + id / W) * k  (same for bias / lin).
+ *   tables / bias_tables / lin_tables are HOST arrays of W device pointers
+ *   (bias_tables, lin_tables nullable); feat_sizes [m] are the GLOBAL table
+ *   sizes (range check), local_offsets [m] the owner-local first rows.
+ * rm_shard_plan: the owner-side K2 plan.  gids [W*b*m] are the ids of ALL ranks
+ *   (rank-major, e.g. an all-gather); entries with id % W == rank are selected
+ *   in ascending global position gp = src_rank*(b*m) + p, keyed by owner-local
+ *   row, stably sorted and run-length encoded.  The owned count stays on the
+ *   device: the sort runs over the fixed capacity N_cap (sentinel keys behind
+ *   the live entries); more than N_cap owned entries set *status |= 4.
+ *   Outputs as rm_segment_plan (sorted_gpos holds global positions) + n_own[1].
+ * rm_segment_reduce_p2p: rm_segment_reduce whose row gp is read from rank
+ *   gp / rows_per_rank's gradient buffer G[r] + (gp % rows_per_rank)*KP,
+ *   a KP = k+4 float row [g_0..g_{k-1} | g_bias | g_lin | 0 | 0] as written by
+ *   rm_pack_grad_rows(pos = NULL).  G is a HOST array of W device pointers.
+ *   Summation order = ascending global position, i.e. the single-GPU order of
+ *   the concatenated batch, independent of W.
+ * ------------------------------------------------------------------------- */
+int rm_p2p_alloc(size_t bytes, void** ptr, uint8_t* handle64);
+int rm_p2p_open(const uint8_t* handle64, void** ptr);
+int rm_p2p_close(void* ptr);
+int rm_p2p_free(void* ptr);
+int rm_gather_fm_fwd_p2p(const float* const* tables, const float* const* bias_tables,
+                         const float* const* lin_tables, int32_t W, const int64_t* feat_sizes,
+                         const int64_t* local_offsets, const int64_t* ids, const float* dense,
+                         const float* lin_dense, int32_t n_dense, int64_t B, int32_t m, int32_t k,
+                         float* x, int64_t ld, float* fm_out, float* lin_out, float* sum_out,
+                         int32_t* status, void* stream);
+size_t rm_shard_plan_workspace_bytes(int64_t Ntot, int64_t N_cap);
+int rm_shard_plan(const int64_t* gids, int64_t Ntot, int32_t m, int32_t W, int32_t rank,
+                  const int64_t* feat_sizes, const int64_t* local_offsets, int64_t total_local,
+                  int64_t N_cap, void* workspace, size_t workspace_bytes, int32_t* sorted_gpos,
+                  int32_t* seg_start, int64_t* uniq_rows, int32_t* n_unique, int32_t* n_own,
+                  int32_t* status, void* stream);
+int rm_segment_reduce_p2p(const float* const* G, int32_t W, int64_t rows_per_rank, int32_t KP,
+                          int32_t k, int64_t N_cap, const int32_t* sorted_gpos,
+                          const int32_t* seg_start, const int32_t* n_unique, float* out_rows,
+                          float* out_bias, float* out_lin, void* stream);
+/* ... fused with the optimizer update of the owner's local tables (bias_table / lin_table nullable). */
+int rm_segment_reduce_p2p_update(const float* const* G, int32_t W, int64_t rows_per_rank, int32_t KP,
+                                 int32_t k, int64_t N_cap, const int32_t* sorted_gpos,
+                                 const int32_t* seg_start, const int64_t* uniq_rows,
+                                 const int32_t* n_unique, float* table, float* bias_table,
+                                 float* lin_table, int32_t opt, float lr, float l2, void* stream);
 
 #ifdef __cplusplus
 }

@@ -51,6 +51,10 @@ _SIGS = {
         ctypes.c_int,
         [P, P, c_int64, P, P, P, c_int32, c_int32, c_int64, P, P, P, P, P, P, P],
     ),
+    "rm_emb_fm_bwd_update": (
+        ctypes.c_int,
+        [P, P, c_int64, P, P, P, c_int32, c_int32, c_int64, P, P, P, P, P, P, P, c_int32, c_float, c_float, P],
+    ),
     "rm_cross_fwd": (ctypes.c_int, [P, c_int64, P, P, P, P, c_int64, c_int32, c_int32, P, P, P]),
     "rm_cross_bwd_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "rm_cross_bwd": (
@@ -71,6 +75,24 @@ _SIGS = {
     "rm_cin_layer_bwd_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32, c_int32, c_int32]),
     "rm_unpack_rows": (ctypes.c_int, [P, c_int64, c_int32, P, c_int32, c_int32, P, c_int64, P, P, P]),
     "rm_pack_grad_rows": (ctypes.c_int, [P, P, c_int64, P, P, P, c_int64, c_int32, P, c_int32, c_int32, P, P]),
+    "rm_p2p_alloc": (ctypes.c_int, [c_size_t, P, P]),
+    "rm_p2p_open": (ctypes.c_int, [P, P]),
+    "rm_p2p_close": (ctypes.c_int, [P]),
+    "rm_p2p_free": (ctypes.c_int, [P]),
+    "rm_gather_fm_fwd_p2p": (
+        ctypes.c_int,
+        [P, P, P, c_int32, P, P, P, P, P, c_int32, c_int64, c_int32, c_int32, P, c_int64, P, P, P, P, P],
+    ),
+    "rm_shard_plan_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "rm_shard_plan": (
+        ctypes.c_int,
+        [P, c_int64, c_int32, c_int32, c_int32, P, P, c_int64, c_int64, P, c_size_t, P, P, P, P, P, P, P],
+    ),
+    "rm_segment_reduce_p2p": (ctypes.c_int, [P, c_int32, c_int64, c_int32, c_int32, c_int64, P, P, P, P, P, P, P]),
+    "rm_segment_reduce_p2p_update": (
+        ctypes.c_int,
+        [P, c_int32, c_int64, c_int32, c_int32, c_int64, P, P, P, P, P, P, P, c_int32, c_float, c_float, P],
+    ),
     "rm_sparse_opt_step": (ctypes.c_int, [P, c_int32, P, P, P, c_int64, c_int32, c_float, c_float, P]),
     "rm_dense_opt_step": (ctypes.c_int, [P, P, c_int64, c_int32, c_float, c_float, P]),
 }

@@ -239,12 +239,15 @@ class FrontEndFunction(Function):
     """
 
     @staticmethod
-    def forward(ctx, table, bias_table, W_lin, lin_table, lin_dense, offsets, total_rows, status, ids, dense):
+    def forward(ctx, table, bias_table, W_lin, lin_table, lin_dense, offsets, total_rows, status, ids, dense,
+                fused_opt=None):
         x, fm, lin, S = ops.gather_fm_fwd(table, bias_table, lin_table, offsets, ids, dense, lin_dense, status=status)
         ctx.table, ctx.bias_table, ctx.W_lin = table, bias_table, W_lin
         ctx.has_lin = lin_table is not None
         ctx.n_lin_dense = 0 if lin_dense is None else lin_dense.numel()
         ctx.total_rows = total_rows
+        ctx.fused_opt = fused_opt  # (opt kind, lr): apply the sparse update inside the backward kernel (N1)
+        ctx.lin_table = lin_table
         ctx.save_for_backward(x, S, ids, offsets, dense)
         ctx.set_materialize_grads(False)
         return x, fm.reshape(-1, 1), lin.reshape(-1, 1)
@@ -261,6 +264,14 @@ class FrontEndFunction(Function):
         g_lin = None if dlin is None else dlin.reshape(-1).contiguous()
         want_bias = ctx.bias_table is not None and g_fm is not None
         want_lin = ctx.has_lin and g_lin is not None
+        if ctx.fused_opt is not None:
+            kind, lr = ctx.fused_opt
+            ops.emb_fm_bwd_update(dx, x, ld, S, g_fm, g_lin if want_lin else None, plan, k, ctx.table.data,
+                                  ctx.bias_table.data if want_bias else None,
+                                  ctx.lin_table if want_lin else None, kind, lr)
+            if want_lin and ctx.W_lin is not None and ctx.n_lin_dense and dense is not None:
+                ctx.W_lin.rm_dense_tail = (ctx.total_rows, dense.t() @ g_lin)
+            return (None,) * 11
         rows, ob, ol = ops.emb_fm_bwd(dx, x, ld, S, g_fm, g_lin if want_lin else None, plan, k, True, want_bias,
                                       want_lin)
         attach_sparse_grad(ctx.table, ops.SparseGrad(plan.uniq_rows, rows, plan.n_unique))
@@ -270,7 +281,7 @@ class FrontEndFunction(Function):
             attach_sparse_grad(ctx.W_lin, ops.SparseGrad(plan.uniq_rows, ol, plan.n_unique))
             if ctx.n_lin_dense and dense is not None:
                 ctx.W_lin.rm_dense_tail = (ctx.total_rows, dense.t() @ g_lin)
-        return (None,) * 10
+        return (None,) * 11
 
 
 class FirstLinearFunction(Function):

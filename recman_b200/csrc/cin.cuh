@@ -21,8 +21,9 @@ int cin_bwd_simt(const float* x0, int64_t bs0, const float* xk, int64_t bsk, con
                  float* dx0, float* dxk, int64_t dbsk, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 // dF = dout * act'(pre) and dbias[n] = sum_{b,d} dF (deterministic); shared by the SIMT and tensor-core backward
+// (scratch: >= N floats of workspace that nothing else uses until this returns, e.g. the dW partial buffer)
 int cin_dF_dbias(const float* dout, const float* pre, int64_t B, int N, int D, int act, float* dF, float* dbias,
-                 cudaStream_t st);
+                 float* scratch, size_t scratch_floats, cudaStream_t st);
 
 // cin_tc_bwd.cu
 bool cin_tc_bwd_supported(int64_t B, int m, int H, int D, int N);

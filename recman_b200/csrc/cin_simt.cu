@@ -360,8 +360,57 @@ __global__ void __launch_bounds__(256) cin_dw_final_kernel(const float* __restri
 // ---------------------------------------------------------------------------------------------
 static int simt_tb(int D) { return D <= CIN_BM ? CIN_BM / D : 0; }
 
+// dF = dout * act'(pre) and dbias in one pass over [B, N*D]: CTA g owns a contiguous range of samples, thread t owns
+// the positions idx = t (mod 256) of the N*D plane and accumulates them in shared memory (no conflicts, fixed order),
+// then sums each n over d -> part[g, n]; cin_dbias_final_kernel adds the parts in CTA order.  Deterministic.
+__global__ void __launch_bounds__(256) cin_dF_dbias_kernel(const float* __restrict__ dout, const float* __restrict__ pre,
+                                                           int64_t B, int N, int D, int act, float* __restrict__ dF,
+                                                           float* __restrict__ part) {
+  extern __shared__ float sm_plane[];
+  const int plane = N * D;
+  for (int i = threadIdx.x; i < plane; i += 256) sm_plane[i] = 0.f;
+  const int64_t chunk = (B + gridDim.x - 1) / gridDim.x;
+  const int64_t b0 = (int64_t)blockIdx.x * chunk;
+  const int64_t b1 = b0 + chunk < B ? b0 + chunk : B;
+  for (int64_t b = b0; b < b1; ++b) {
+    const int64_t base = b * plane;
+    for (int i = threadIdx.x; i < plane; i += 256) {
+      const float v = dout[base + i] * act_grad(pre[base + i], act);
+      dF[base + i] = v;
+      sm_plane[i] += v;
+    }
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < N; n += 256) {
+    float acc = 0.f;
+    for (int d = 0; d < D; ++d) acc += sm_plane[n * D + d];
+    part[(int64_t)blockIdx.x * N + n] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) cin_dbias_final_kernel(const float* __restrict__ part, int G, int N,
+                                                              float* __restrict__ dbias) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int g = 0; g < G; ++g) acc += part[(int64_t)g * N + n];
+  dbias[n] = acc;
+}
+
 int cin_dF_dbias(const float* dout, const float* pre, int64_t B, int N, int D, int act, float* dF, float* dbias,
-                 cudaStream_t st) {
+                 float* scratch, size_t scratch_floats, cudaStream_t st) {
+  const size_t smem = (size_t)N * D * sizeof(float);
+  int64_t G = (int64_t)(scratch_floats / (size_t)N);
+  if (G > 4 * RM_NUM_SMS) G = 4 * RM_NUM_SMS;
+  if (G > B) G = B;
+  if (G >= 1 && smem <= 200 * 1024) {
+    RM_CUDA(cudaFuncSetAttribute(cin_dF_dbias_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cin_dF_dbias_kernel<<<(unsigned)G, 256, smem, st>>>(dout, pre, B, N, D, act, dF, scratch);
+    RM_LAUNCH_CHECK();
+    cin_dbias_final_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(scratch, (int)G, N, dbias);
+    RM_LAUNCH_CHECK();
+    return 0;
+  }
   const int64_t total = B * (int64_t)N * D;
   cin_dF_kernel<<<grid_for(total, 256, 8), 256, 0, st>>>(dout, pre, total, act, dF);
   RM_LAUNCH_CHECK();
@@ -415,7 +464,7 @@ int cin_bwd_simt(const float* x0, int64_t bs0, const float* xk, int64_t bsk, con
   const size_t smem = ((size_t)2 * TB * (m + H) * D + CIN_BK * CIN_AS + CIN_BK * CIN_BN) * sizeof(float);
   RM_UNSUPPORTED(smem <= 227 * 1024, "m + H too large for the backward's shared-memory accumulators");
   {
-    const int rc = cin_dF_dbias(dout, pre, B, N, D, act, ws.dF, dbias, st);
+    const int rc = cin_dF_dbias(dout, pre, B, N, D, act, ws.dF, dbias, ws.partial, (size_t)ws.slabs * m * H * N, st);
     if (rc) return rc;
   }
   RM_CUDA(cudaFuncSetAttribute(cin_bwd_dx_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -11,7 +11,7 @@
 // TMEM accumulators, bounded waits.
 //
 // The tensor core accumulates fp32 with round-toward-zero (bias linear in the number of accumulate steps, see
-// cin_tc.cu), so kernel B - whose reduction runs over all B*D rows - accumulates at most SLAB = 512 rows in TMEM and
+// cin_tc.cu), so kernel B - whose reduction runs over all B*D rows - accumulates at most slab_rows = 512 rows in TMEM and
 // the slabs are then summed in fp32 round-to-nearest, in slab order (deterministic) by cin_dw_unpermute_kernel.
 #include "tc_common.cuh"
 
@@ -20,7 +20,7 @@ namespace rm {
 constexpr int TB_STAGES = 3;
 constexpr int TB_THREADS = 320;   // kernel A: 8 producer/epilogue warps + MMA warp + W loader warp
 constexpr int TB_THREADS_B = 288;  // kernel B: 8 producer/epilogue warps + MMA warp
-constexpr int TB_SLAB = 512;       // rows of (b,d) accumulated in TMEM per CTA in kernel B
+constexpr int TB_SLAB_DEFAULT = 512;  // rows of (b,d) accumulated in TMEM per CTA in kernel B (RM_TUNE_CIN_SLAB)
 
 // ------------------------------------------------------------------------------------------------ pack W'' (kernel A)
 // image (qg, st): NMMA rows (j -> k'' = qg*NMMA + j) x 128 B; chunk c of row j at (c ^ (j&7)).
@@ -67,7 +67,7 @@ struct TbParams {
   float* partial;         // kernel B: [slabs, KPADT, NPAD]
   int32_t* status;
   int64_t Mrows;
-  int m, H, D, N, NPAD, MPAD, QG, NMMA, spq, n_qg, KPADT;
+  int m, H, D, N, NPAD, MPAD, QG, NMMA, spq, n_qg, KPADT, slab_rows;
 };
 
 // ------------------------------------------------------------------------------------------------ kernel A
@@ -129,16 +129,25 @@ __global__ void __launch_bounds__(TB_THREADS, 1) cin_bwd_dx_tc_kernel(const TbPa
     const int h = warp >> 2, quad = warp & 3;
     const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * 256);
     int it = 0;
+    // software pipeline: the dF values of the next stage are in flight while this stage is split and stored (the tile
+    // is the same for every q group, so "next" wraps around at the end of a group)
+    float vn[KS];
+    auto fetch = [&](int st) {
+#pragma unroll
+      for (int e = 0; e < KS; ++e) {
+        const int n = st * KS + e;
+        vn[e] = (valid && n < P.N) ? __ldg(dFp + (int64_t)n * P.D) : 0.f;
+      }
+    };
+    fetch(0);
     for (int qg = 0; qg < P.n_qg; ++qg) {
       // ---- produce the dF tile stage by stage (identical for every q group; re-read from L2) ----
       for (int st = 0; st < P.spq; ++st, ++it) {
         const int s = it % TB_STAGES;
         float v[KS];
 #pragma unroll
-        for (int e = 0; e < KS; ++e) {
-          const int n = st * KS + e;
-          v[e] = (valid && n < P.N) ? __ldg(dFp + (int64_t)n * P.D) : 0.f;
-        }
+        for (int e = 0; e < KS; ++e) v[e] = vn[e];
+        fetch(st + 1 < P.spq ? st + 1 : 0);
         ok = mbar_wait(empty(s), (((uint32_t)(it / TB_STAGES)) & 1u) ^ 1u) && ok;
         uint8_t* arow = gen_base + (size_t)s * stage_bytes + row_off;
 #pragma unroll
@@ -153,37 +162,31 @@ __global__ void __launch_bounds__(TB_THREADS, 1) cin_bwd_dx_tc_kernel(const TbPa
         fence_proxy_async_smem();
         mbar_arrive(full_a(s));
       }
-      // ---- epilogue of this q group: contract dZ (TMEM) with x0 (registers) and xk ----
+      // ---- epilogue of this q group: contract dZ (TMEM) with x0 (registers) and xk, two q per TMEM round trip ----
       ok = mbar_wait(accum_full, (uint32_t)qg & 1u) && ok;
       tc_fence_after();
-      for (int qi0 = 0; qi0 < P.QG; qi0 += 8) {
-        float xkv[8];
+      constexpr int MPADc = MP4 * 4;
+      for (int qi0 = 0; qi0 < P.QG; qi0 += 2) {  // QG is a multiple of 4
+        const int q0 = qg * P.QG + qi0;
+        if (q0 >= P.H) break;  // warp-uniform
+        const bool two = q0 + 1 < P.H;
+        const float xk0 = valid ? __ldg(xkp + (int64_t)q0 * P.D) : 0.f;
+        const float xk1 = (valid && two) ? __ldg(xkp + (int64_t)(q0 + 1) * P.D) : 0.f;
+        uint32_t a[2 * MPADc];
+        tmem_ld_cols<2 * MPADc>(taddr0 + (uint32_t)(qi0 * MPADc), a);
+        tmem_ld_wait();
+        float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int q = qg * P.QG + qi0 + u;
-          xkv[u] = (valid && qi0 + u < P.QG && q < P.H) ? __ldg(xkp + (int64_t)q * P.D) : 0.f;
+        for (int j = 0; j < MPADc; ++j) {
+          const float z0 = __uint_as_float(a[j]), z1 = __uint_as_float(a[MPADc + j]);
+          acc0 = fmaf(z0, x0r[j], acc0);
+          acc1 = fmaf(z1, x0r[j], acc1);
+          dx0r[j] = fmaf(z0, xk0, dx0r[j]);
+          dx0r[j] = fmaf(z1, xk1, dx0r[j]);
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int qi = qi0 + u;
-          const int q = qg * P.QG + qi;
-          if (qi < P.QG && q < P.H) {  // warp-uniform
-            uint32_t a[MP4][4];
-#pragma unroll
-            for (int c = 0; c < MP4; ++c)
-              tmem_ld4(taddr0 + (uint32_t)(qi * (MP4 * 4) + 4 * c), a[c][0], a[c][1], a[c][2], a[c][3]);
-            tmem_ld_wait();
-            float acc = 0.f;
-#pragma unroll
-            for (int c = 0; c < MP4; ++c)
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float z = __uint_as_float(a[c][e]);
-                acc = fmaf(z, x0r[4 * c + e], acc);
-                dx0r[4 * c + e] = fmaf(z, xkv[u], dx0r[4 * c + e]);
-              }
-            if (valid) dxkp[(int64_t)q * P.D] = acc;
-          }
+        if (valid) {
+          dxkp[(int64_t)q0 * P.D] = acc0;
+          if (two) dxkp[(int64_t)(q0 + 1) * P.D] = acc1;
         }
       }
       tc_fence_before();
@@ -295,8 +298,8 @@ __global__ void __launch_bounds__(TB_THREADS_B, 1) cin_bwd_dw_tc_kernel(const Tb
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   bool ok = true;
-  const int64_t r_begin = (int64_t)slab * TB_SLAB;
-  const int64_t r_end = min(P.Mrows, r_begin + TB_SLAB);
+  const int64_t r_begin = (int64_t)slab * P.slab_rows;
+  const int64_t r_end = min(P.Mrows, r_begin + P.slab_rows);
   const int n_stages = (int)((r_end - r_begin + KS - 1) / KS);
 
   if (warp < 8) {
@@ -309,29 +312,30 @@ __global__ void __launch_bounds__(TB_THREADS_B, 1) cin_bwd_dw_tc_kernel(const Tb
     const bool b_row = tid < P.NPAD;
     const uint32_t row_off = (uint32_t)tid * 128u;
     const uint32_t rx = (uint32_t)(tid & 7);
-    const int n_chunks = xrows * (KS / 4);  // float4 chunks of the staged slices per stage
-    for (int st = 0; st < n_stages; ++st) {
-      const int s = st % TB_STAGES;
+    const int n_chunks = xrows * (KS / 4);  // float4 chunks of the staged slices per stage (<= 3 per thread)
+    // Software pipeline: the global loads of stage st+1 (x0 / xk slices and this thread's dF row) are issued before
+    // the products of stage st are formed, so their latency hides behind the smem work instead of stalling it.
+    float4 stg[3], df[KS / 4];
+    auto issue_loads = [&](int st) {
       const int64_t r0 = r_begin + (int64_t)st * KS;
-      float* buf = xs + (size_t)(st & 1) * xrows * XS;
-      // ---- stage x0[b, 0..MPAD), xk[b, q_lo..q_hi] for the KS rows of this stage (coalesced float4 loads) ----
-      for (int i = tid; i < n_chunks; i += 256) {
-        const int row = i / (KS / 4), c4 = i - row * (KS / 4);
-        const int64_t r = r0 + 4 * c4;
-        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < r_end) {
-          const int64_t b = r / P.D;
-          const int d = (int)(r - b * P.D);
-          if (row < P.MPAD) {
-            if (row < P.m) val = ld4(P.x0 + b * P.bs0 + (int64_t)row * P.D + d);
-          } else {
-            val = ld4(P.xk + b * P.bsk + (int64_t)(q_lo + row - P.MPAD) * P.D + d);
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int i = tid + u * 256;
+        stg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n_chunks) {
+          const int row = i / (KS / 4), c4 = i - row * (KS / 4);
+          const int64_t r = r0 + 4 * c4;
+          if (r < r_end) {
+            const int64_t b = r / P.D;
+            const int d = (int)(r - b * P.D);
+            if (row < P.MPAD) {
+              if (row < P.m) stg[u] = ld4(P.x0 + b * P.bs0 + (int64_t)row * P.D + d);
+            } else {
+              stg[u] = ld4(P.xk + b * P.bsk + (int64_t)(q_lo + row - P.MPAD) * P.D + d);
+            }
           }
         }
-        *reinterpret_cast<float4*>(buf + row * XS + 4 * c4) = val;
       }
-      // dF row n = tid for the same (b,d) rows
-      float4 df[KS / 4];
 #pragma unroll
       for (int c4 = 0; c4 < KS / 4; ++c4) {
         const int64_t r = r0 + 4 * c4;
@@ -342,7 +346,25 @@ __global__ void __launch_bounds__(TB_THREADS_B, 1) cin_bwd_dw_tc_kernel(const Tb
           df[c4] = ld4(P.dF + (b * P.N + tid) * (int64_t)P.D + d);
         }
       }
+    };
+    if (n_stages > 0) issue_loads(0);
+    for (int st = 0; st < n_stages; ++st) {
+      const int s = st % TB_STAGES;
+      float* buf = xs + (size_t)(st & 1) * xrows * XS;
+      // ---- stage x0[b, 0..MPAD), xk[b, q_lo..q_hi] for the KS rows of this stage ----
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int i = tid + u * 256;
+        if (i < n_chunks) {
+          const int row = i / (KS / 4), c4 = i - row * (KS / 4);
+          *reinterpret_cast<float4*>(buf + row * XS + 4 * c4) = stg[u];
+        }
+      }
+      float4 dfc[KS / 4];
+#pragma unroll
+      for (int c4 = 0; c4 < KS / 4; ++c4) dfc[c4] = df[c4];
       named_bar_sync(1, 256);  // staged slices visible to all producer threads
+      if (st + 1 < n_stages) issue_loads(st + 1);
       ok = mbar_wait(empty(s), (((uint32_t)(st / TB_STAGES)) & 1u) ^ 1u) && ok;
       uint8_t* arow = gen_base + (size_t)s * stage_bytes + row_off;
       uint8_t* brow = arow + a_bytes;
@@ -363,10 +385,10 @@ __global__ void __launch_bounds__(TB_THREADS_B, 1) cin_bwd_dw_tc_kernel(const Tb
         if (SPLIT3)
           *reinterpret_cast<uint4*>(arow + ((((uint32_t)(c4 + 4)) ^ rx) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         if (b_row) {
-          split_tf32(df[c4].x, hi[0], lo[0]);
-          split_tf32(df[c4].y, hi[1], lo[1]);
-          split_tf32(df[c4].z, hi[2], lo[2]);
-          split_tf32(df[c4].w, hi[3], lo[3]);
+          split_tf32(dfc[c4].x, hi[0], lo[0]);
+          split_tf32(dfc[c4].y, hi[1], lo[1]);
+          split_tf32(dfc[c4].z, hi[2], lo[2]);
+          split_tf32(dfc[c4].w, hi[3], lo[3]);
           *reinterpret_cast<uint4*>(brow + ((((uint32_t)c4) ^ rx) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           if (SPLIT3)
             *reinterpret_cast<uint4*>(brow + ((((uint32_t)(c4 + 4)) ^ rx) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -446,7 +468,7 @@ __global__ void __launch_bounds__(256) cin_dw_unpermute_kernel(const float* __re
 
 // ------------------------------------------------------------------------------------------------ host side
 struct TbLayout {
-  int MPAD, MP4, QG, NMMA, spq, n_qg, NPAD, KPADT, n_ktiles, slabs;
+  int MPAD, MP4, QG, NMMA, spq, n_qg, NPAD, KPADT, n_ktiles, slabs, slab_rows;
   size_t off_status, off_dF, off_wpack, off_partial, total;
 };
 
@@ -470,7 +492,9 @@ static TbLayout tb_layout(int64_t B, int m, int H, int D, int N, int precision) 
   L.n_ktiles = (kpp + 255) / 256;
   L.KPADT = L.n_ktiles * 256;
   const int64_t Mrows = B * (int64_t)D;
-  L.slabs = (int)((Mrows + TB_SLAB - 1) / TB_SLAB);
+  L.slab_rows = tune_variant("RM_TUNE_CIN_SLAB", TB_SLAB_DEFAULT) / 32 * 32;
+  if (L.slab_rows < 32) L.slab_rows = 32;
+  L.slabs = (int)((Mrows + L.slab_rows - 1) / L.slab_rows);
   if (L.slabs < 1) L.slabs = 1;
   size_t off = 0;
   L.off_status = off; off += 256;
@@ -522,7 +546,7 @@ int cin_bwd_tc(const float* x0, int64_t bs0, const float* xk, int64_t bsk, const
   float* partial = (float*)(ws + L.off_partial);
   RM_CUDA(cudaMemsetAsync(status, 0, 256, st));
   {
-    const int rc = cin_dF_dbias(dout, pre, B, N, D, act, dF, dbias, st);
+    const int rc = cin_dF_dbias(dout, pre, B, N, D, act, dF, dbias, partial, (size_t)L.slabs * L.KPADT * L.NPAD, st);
     if (rc) return rc;
   }
   cin_pack_wT_kernel<<<grid_for((int64_t)L.n_qg * L.spq * L.NMMA * 8, 256, 8), 256, 0, st>>>(
@@ -532,6 +556,7 @@ int cin_bwd_tc(const float* x0, int64_t bs0, const float* xk, int64_t bsk, const
   P.x0 = x0; P.bs0 = bs0; P.xk = xk; P.bsk = bsk; P.dF = dF; P.wpack = wpack; P.dx0 = dx0; P.dxk = dxk; P.dbsk = dbsk;
   P.partial = partial; P.status = status; P.Mrows = B * (int64_t)D; P.m = m; P.H = H; P.D = D; P.N = N;
   P.NPAD = L.NPAD; P.MPAD = L.MPAD; P.QG = L.QG; P.NMMA = L.NMMA; P.spq = L.spq; P.n_qg = L.n_qg; P.KPADT = L.KPADT;
+  P.slab_rows = L.slab_rows;
   // ---- kernel A ----
   {
     const uint32_t stage_bytes = (uint32_t)((256 * 128 + L.NMMA * 128 + 1023) / 1024 * 1024);
@@ -557,6 +582,7 @@ int cin_bwd_tc(const float* x0, int64_t bs0, const float* xk, int64_t bsk, const
     const int max_xrows = L.MPAD + 256 / L.MPAD + 2;
     const size_t smem = (size_t)TB_STAGES * stage_bytes + 128 + (size_t)2 * max_xrows * (KS + 4) * 4 + 1024;
     RM_UNSUPPORTED(smem <= 227 * 1024, "shared memory budget exceeded in the dW kernel");
+    RM_UNSUPPORTED(max_xrows * (KS / 4) <= 3 * 256, "staged slice too large for the dW kernel's prefetch registers");
     dim3 grid((unsigned)L.n_ktiles, (unsigned)L.slabs);
     if (split3) {
       RM_CUDA(cudaFuncSetAttribute(cin_bwd_dw_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) pack_grad_rows_kernel(const float* __rest
   const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
   const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / LPR;
   for (int64_t j = group; j < n; j += n_groups) {
-    const uint32_t p = (uint32_t)pos[j];
+    const uint32_t p = pos ? (uint32_t)pos[j] : (uint32_t)j;  // pos == NULL: rows stay in position order
     const uint32_t b = p / m, f = p - b * m;
     const int64_t o = (int64_t)b * ld + (int64_t)f * k;
     const float gf = g_fm ? g_fm[b] : 0.f;
@@ -109,7 +109,7 @@ int rm_pack_grad_rows(const float* dx, const float* x, int64_t ld, const float* 
   using namespace rm;
   RM_CHECK_ARG(n >= 0 && m > 0 && k > 0 && KP >= k + 4, "bad shape");
   if (n == 0) return 0;
-  RM_CHECK_ARG(pos && send, "null pointer");
+  RM_CHECK_ARG(send, "null pointer");
   RM_CHECK_ARG(!g_fm || (x && sum), "g_fm needs x and sum");
   RM_UNSUPPORTED(k % 4 == 0 && KP % 4 == 0 && ld % 4 == 0 && (!dx || aligned16(dx)) && (!x || aligned16(x)) &&
                      (!sum || aligned16(sum)) && aligned16(send),

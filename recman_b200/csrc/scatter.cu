@@ -20,6 +20,7 @@
 #include <thrust/iterator/counting_iterator.h>
 
 #include "common.cuh"
+#include "optim.cuh"
 
 namespace rm {
 
@@ -95,6 +96,7 @@ static PlanWorkspace plan_layout(int64_t N, void* base) {
 // segments follow, U at a time.  Every segment is still summed in ascending position order.
 template <bool FUSED>
 struct RowSrc {
+  static constexpr bool kScalars = FUSED;
   const float* grad;
   const float* x;
   const float* sum;
@@ -124,19 +126,51 @@ struct RowSrc {
   }
 };
 
-template <int LPR, int SEG, int U, bool FUSED>
+
+// Row source for row-sharded tables: position gp = src_rank * rows_per_rank + local position; the row lives in rank
+// src_rank's gradient buffer G[rows_per_rank, KP] = [g_0..g_{k-1} | g_bias | g_lin | 0 | 0], read over NVLink (peer
+// memory) for src_rank != this rank.
+#define RM_MAX_PEERS 8
+struct PeerRowSrc {
+  static constexpr bool kScalars = true;
+  const float* G[RM_MAX_PEERS];
+  uint32_t rows_per_rank;
+  int KP, k;
+  __device__ __forceinline__ void load(uint32_t gp, int c, float4& v, float& gf, float& gl) const {
+    const uint32_t r = gp / rows_per_rank, lp = gp - r * rows_per_rank;
+    const float* row = G[r] + (int64_t)lp * KP;
+    v = ldg_stream4(row + 4 * c);
+    gf = 0.f;
+    gl = 0.f;
+    if (c == 0) {
+      const float4 t = ldg_stream4(row + k);
+      gf = t.x;
+      gl = t.y;
+    }
+  }
+};
+
+// Optional fused optimizer (N1): instead of (or in addition to) storing the summed rows, apply the stateless
+// first-step update to table[uniq_rows[u]] in the same pass - the summed gradient never round-trips through HBM.
+struct UpdateSink {
+  float* table;       // nullptr = disabled
+  float* bias_table;  // k = 1 tables in the same row numbering (nullable)
+  float* lin_table;
+  const int64_t* uniq_rows;
+  OptParams o;
+};
+
+template <int LPR, int SEG, int U, class Src>
 __global__ void __launch_bounds__(256) segment_reduce_kernel(
-    const float* __restrict__ grad, const float* __restrict__ x, int64_t ld, const float* __restrict__ sum,
-    const float* __restrict__ g_fm, const float* __restrict__ g_lin, uint32_t m, int k,
-    const int32_t* __restrict__ sorted_pos, const int32_t* __restrict__ seg_start,
+    const Src src, int k, const int32_t* __restrict__ sorted_pos, const int32_t* __restrict__ seg_start,
     const int32_t* __restrict__ n_unique, float* __restrict__ out_rows, float* __restrict__ out_bias,
-    float* __restrict__ out_lin) {
+    float* __restrict__ out_lin, const UpdateSink sink) {
+  constexpr bool FUSED = Src::kScalars;
   const int lir = threadIdx.x % LPR;
   const int k4 = k >> 2;
   const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
   const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / LPR;
   const int32_t NU = *n_unique;
-  const RowSrc<FUSED> src{grad, x, sum, g_fm, g_lin, ld, m, k};
   for (int64_t u0 = group * SEG; u0 < NU; u0 += n_groups * SEG) {
     int32_t s[SEG], e[SEG];
 #pragma unroll
@@ -145,10 +179,21 @@ __global__ void __launch_bounds__(256) segment_reduce_kernel(
       s[t] = live ? seg_start[u0 + t] : 0;
       e[t] = live ? seg_start[u0 + t + 1] : 0;
     }
+    int64_t urow[SEG];
+    if (sink.table) {
+#pragma unroll
+      for (int t = 0; t < SEG; ++t) urow[t] = u0 + t < NU ? sink.uniq_rows[u0 + t] : 0;
+    }
     for (int c = lir; c < k4; c += LPR) {  // lane 0 always owns column chunk 0, so it also carries the k=1 sums
       uint32_t p0[SEG];
 #pragma unroll
       for (int t = 0; t < SEG; ++t) p0[t] = s[t] < e[t] ? (uint32_t)sorted_pos[s[t]] : 0u;
+      float4 tv[SEG];  // the parameter rows to update, loaded beside the first gradient rows
+      if (sink.table) {
+#pragma unroll
+        for (int t = 0; t < SEG; ++t)
+          tv[t] = u0 + t < NU ? ld4(sink.table + urow[t] * k + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       float4 acc[SEG];
       float ba[SEG], la[SEG];
 #pragma unroll
@@ -188,6 +233,18 @@ __global__ void __launch_bounds__(256) segment_reduce_kernel(
             if (out_bias) out_bias[u0 + t] = ba[t];
             if (out_lin) out_lin[u0 + t] = la[t];
           }
+          if (sink.table) {
+            float4 pv = tv[t];
+            pv.x = opt_update(pv.x, acc[t].x, sink.o);
+            pv.y = opt_update(pv.y, acc[t].y, sink.o);
+            pv.z = opt_update(pv.z, acc[t].z, sink.o);
+            pv.w = opt_update(pv.w, acc[t].w, sink.o);
+            st4(sink.table + urow[t] * k + 4 * c, pv);
+            if (FUSED && c == 0) {
+              if (sink.bias_table) sink.bias_table[urow[t]] = opt_update(sink.bias_table[urow[t]], ba[t], sink.o);
+              if (sink.lin_table) sink.lin_table[urow[t]] = opt_update(sink.lin_table[urow[t]], la[t], sink.o);
+            }
+          }
         }
       }
     }
@@ -221,15 +278,14 @@ static inline int pow2ceil__(int v) {
   return p;
 }
 
-template <int LPR, bool FUSED>
-static int launch_segment_reduce(const float* grad, const float* x, int64_t ld, const float* sum, const float* g_fm,
-                                 const float* g_lin, int m, int k, int64_t N, const int32_t* sorted_pos,
-                                 const int32_t* seg_start, const int32_t* n_unique, float* out_rows, float* out_bias,
-                                 float* out_lin, cudaStream_t st) {
-  const int variant = tune_variant("RM_TUNE_SEGRED", FUSED ? 2 : 4);  // measured best on B200 (profiles/r1_kbench.json)
-#define RM_SRK(SEG)                                                                                                  \
-  segment_reduce_kernel<LPR, SEG, 4, FUSED><<<grid_for(N, (256 / LPR) * SEG, 8), 256, 0, st>>>(                       \
-      grad, x, ld, sum, g_fm, g_lin, (uint32_t)m, k, sorted_pos, seg_start, n_unique, out_rows, out_bias, out_lin)
+template <int LPR, class Src>
+static int launch_segment_reduce(const Src& src, int k, int64_t N, const int32_t* sorted_pos, const int32_t* seg_start,
+                                 const int32_t* n_unique, float* out_rows, float* out_bias, float* out_lin,
+                                 const UpdateSink& sink, int dflt_variant, cudaStream_t st) {
+  const int variant = tune_variant("RM_TUNE_SEGRED", dflt_variant);  // measured best on B200 (profiles/r1_kbench.json)
+#define RM_SRK(SEG)                                                                                               \
+  segment_reduce_kernel<LPR, SEG, 4, Src><<<grid_for(N, (256 / LPR) * SEG, 8), 256, 0, st>>>(                      \
+      src, k, sorted_pos, seg_start, n_unique, out_rows, out_bias, out_lin, sink)
   // n_unique <= N lives on the device: the grid is sized for the worst case
   if (variant == 1) RM_SRK(1);
   else if (variant == 2) RM_SRK(2);
@@ -239,17 +295,17 @@ static int launch_segment_reduce(const float* grad, const float* x, int64_t ld, 
   return 0;
 }
 
-template <bool FUSED>
-static int dispatch_segment_reduce(const float* grad, const float* x, int64_t ld, const float* sum, const float* g_fm,
-                                   const float* g_lin, int m, int k, int64_t N, const int32_t* sorted_pos,
+template <class Src>
+static int dispatch_segment_reduce(const Src& src, int k, int64_t N, const int32_t* sorted_pos,
                                    const int32_t* seg_start, const int32_t* n_unique, float* out_rows,
-                                   float* out_bias, float* out_lin, cudaStream_t st) {
+                                   float* out_bias, float* out_lin, const UpdateSink& sink, int dflt_variant,
+                                   cudaStream_t st) {
   int lpr = pow2ceil__(k / 4);
   if (lpr > 32) lpr = 32;
-#define RM_SR(L)                                                                                                    \
-  case L:                                                                                                           \
-    return launch_segment_reduce<L, FUSED>(grad, x, ld, sum, g_fm, g_lin, m, k, N, sorted_pos, seg_start, n_unique, \
-                                           out_rows, out_bias, out_lin, st)
+#define RM_SR(L)                                                                                              \
+  case L:                                                                                                     \
+    return launch_segment_reduce<L, Src>(src, k, N, sorted_pos, seg_start, n_unique, out_rows, out_bias,       \
+                                         out_lin, sink, dflt_variant, st)
   switch (lpr) {
     RM_SR(1);
     RM_SR(2);
@@ -257,10 +313,110 @@ static int dispatch_segment_reduce(const float* grad, const float* x, int64_t ld
     RM_SR(8);
     RM_SR(16);
     default:
-      return launch_segment_reduce<32, FUSED>(grad, x, ld, sum, g_fm, g_lin, m, k, N, sorted_pos, seg_start, n_unique,
-                                              out_rows, out_bias, out_lin, st);
+      return launch_segment_reduce<32, Src>(src, k, N, sorted_pos, seg_start, n_unique, out_rows, out_bias, out_lin,
+                                            sink, dflt_variant, st);
   }
 #undef RM_SR
+}
+
+// ---------------------------------------------------------------------------
+// owner-side plan for row-sharded tables (row r of a table lives on rank r mod W at local row r div W, W = 2^s):
+// from the ids of ALL ranks (gids [W*b, m], rank-major) select the entries this rank owns, in ascending global
+// position, key them by owner-local row and sort.  The owned count lives on the device (no host sync); the sort runs
+// over a fixed capacity N_cap with sentinel keys behind the live entries.
+// ---------------------------------------------------------------------------
+struct OwnedBy {
+  const int64_t* gids;
+  const int64_t* feat_sizes;
+  uint32_t m;
+  int64_t wmask, rank;
+  __host__ __device__ __forceinline__ bool operator()(const int32_t& i) const {
+    const int64_t id = gids[i];
+    return id >= 0 && id < feat_sizes[(uint32_t)i % m] && (id & wmask) == rank;
+  }
+};
+
+__global__ void __launch_bounds__(256) shard_keys_kernel(const int64_t* __restrict__ gids,
+                                                         const int64_t* __restrict__ local_offs, uint32_t m,
+                                                         int wshift, const int32_t* __restrict__ own_gpos,
+                                                         const int32_t* __restrict__ n_own, int32_t N_cap,
+                                                         uint32_t sentinel, uint32_t* __restrict__ keys,
+                                                         int32_t* __restrict__ pos, int32_t* status) {
+  const int32_t n_all = *n_own;
+  const int32_t n = n_all < N_cap ? n_all : N_cap;
+  if (n_all > N_cap && blockIdx.x == 0 && threadIdx.x == 0 && status) atomicOr(status, 4);  // capacity exceeded
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N_cap; i += gridDim.x * blockDim.x) {
+    if (i < n) {
+      const int32_t gp = own_gpos[i];
+      keys[i] = (uint32_t)(local_offs[(uint32_t)gp % m] + (gids[gp] >> wshift));
+      pos[i] = gp;
+    } else {
+      keys[i] = sentinel;
+      pos[i] = 0;
+    }
+  }
+}
+
+struct HeadOfLiveRun {
+  const uint32_t* keys;
+  const int32_t* n_own;
+  int32_t N_cap;
+  __device__ __forceinline__ bool operator()(const int32_t& i) const {
+    const int32_t n_all = *n_own;
+    const int32_t n = n_all < N_cap ? n_all : N_cap;
+    return i < n && (i == 0 || keys[i] != keys[i - 1]);
+  }
+};
+
+__global__ void __launch_bounds__(256) finish_shard_plan_kernel(const uint32_t* __restrict__ sorted_keys,
+                                                                int32_t* __restrict__ seg_start,
+                                                                const int32_t* __restrict__ n_unique,
+                                                                const int32_t* __restrict__ n_own, int32_t N_cap,
+                                                                int64_t* __restrict__ uniq_rows) {
+  const int32_t U = *n_unique;
+  const int32_t n_all = *n_own;
+  const int32_t n = n_all < N_cap ? n_all : N_cap;
+  for (int32_t u = blockIdx.x * blockDim.x + threadIdx.x; u <= U; u += gridDim.x * blockDim.x) {
+    if (u == U)
+      seg_start[U] = n;
+    else
+      uniq_rows[u] = (int64_t)sorted_keys[seg_start[u]];
+  }
+}
+
+struct ShardPlanWs {
+  int32_t* own_gpos;
+  uint32_t* keys_in;
+  uint32_t* keys_out;
+  int32_t* pos_in;
+  void* cub_temp;
+  size_t cub_bytes;
+  size_t total;
+};
+
+static ShardPlanWs shard_plan_layout(int64_t Ntot, int64_t N_cap, void* base) {
+  ShardPlanWs w;
+  size_t sort_bytes = 0, sel1 = 0, sel2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)N_cap, 0, 32);
+  thrust::counting_iterator<int32_t> counting(0);
+  OwnedBy own{nullptr, nullptr, 1, 0, 0};
+  cub::DeviceSelect::If(nullptr, sel1, counting, (int32_t*)nullptr, (int32_t*)nullptr, (int)Ntot, own);
+  HeadOfLiveRun head{nullptr, nullptr, 0};
+  cub::DeviceSelect::If(nullptr, sel2, counting, (int32_t*)nullptr, (int32_t*)nullptr, (int)N_cap, head);
+  w.cub_bytes = sort_bytes;
+  if (sel1 > w.cub_bytes) w.cub_bytes = sel1;
+  if (sel2 > w.cub_bytes) w.cub_bytes = sel2;
+  size_t off = 0;
+  char* b = (char*)base;
+  w.own_gpos = (int32_t*)(b + off); off += align_up((size_t)Ntot * 4, 256);
+  const size_t arr = align_up((size_t)N_cap * 4, 256);
+  w.keys_in = (uint32_t*)(b + off); off += arr;
+  w.keys_out = (uint32_t*)(b + off); off += arr;
+  w.pos_in = (int32_t*)(b + off); off += arr;
+  w.cub_temp = (void*)(b + off); off += align_up(w.cub_bytes, 256);
+  w.total = off;
+  return w;
 }
 
 }  // namespace rm
@@ -320,28 +476,146 @@ int rm_segment_reduce(const float* grad, int64_t ld, int32_t m, int32_t k, int64
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = (k % 4 == 0) && (ld % 4 == 0) && aligned16(grad) && aligned16(out_rows);
-  if (vec)
-    return dispatch_segment_reduce<false>(grad, nullptr, ld, nullptr, nullptr, nullptr, m, k, N, sorted_pos, seg_start,
-                                          n_unique, out_rows, nullptr, nullptr, st);
+  if (vec) {
+    const RowSrc<false> src{grad, nullptr, nullptr, nullptr, nullptr, ld, (uint32_t)m, k};
+    return dispatch_segment_reduce(src, k, N, sorted_pos, seg_start, n_unique, out_rows, nullptr, nullptr, UpdateSink{}, 4,
+                                   st);
+  }
   segment_reduce_scalar_kernel<<<grid_for(N * k, 256, 8), 256, 0, st>>>(grad, ld, (uint32_t)m, (uint32_t)k, sorted_pos,
                                                                         seg_start, n_unique, out_rows);
   RM_LAUNCH_CHECK();
   return 0;
 }
 
-int rm_emb_fm_bwd(const float* dx, const float* x, int64_t ld, const float* sum, const float* g_fm, const float* g_lin,
-                  int32_t m, int32_t k, int64_t N, const int32_t* sorted_pos, const int32_t* seg_start,
-                  const int32_t* n_unique, float* out_rows, float* out_bias, float* out_lin, void* stream) {
+static int emb_fm_bwd_impl(const float* dx, const float* x, int64_t ld, const float* sum, const float* g_fm,
+                           const float* g_lin, int32_t m, int32_t k, int64_t N, const int32_t* sorted_pos,
+                           const int32_t* seg_start, const int32_t* n_unique, float* out_rows, float* out_bias,
+                           float* out_lin, const rm::UpdateSink& sink, void* stream) {
   using namespace rm;
   RM_CHECK_ARG(sorted_pos && seg_start && n_unique, "null pointer");
   RM_CHECK_ARG(N >= 0 && m > 0 && k > 0 && ld >= (int64_t)m * k, "bad shape");
   RM_CHECK_ARG(!g_fm || (x && sum), "g_fm needs x and sum");
   RM_UNSUPPORTED((k % 4 == 0) && (ld % 4 == 0) && (!dx || aligned16(dx)) && (!x || aligned16(x)) &&
-                     (!sum || aligned16(sum)) && (!out_rows || aligned16(out_rows)),
+                     (!sum || aligned16(sum)) && (!out_rows || aligned16(out_rows)) &&
+                     (!sink.table || aligned16(sink.table)),
                  "fused embedding backward needs k % 4 == 0 and 16-byte aligned rows");
   if (N == 0) return 0;
-  return dispatch_segment_reduce<true>(dx, x, ld, sum, g_fm, g_lin, m, k, N, sorted_pos, seg_start, n_unique, out_rows,
-                                       out_bias, out_lin, (cudaStream_t)stream);
+  const RowSrc<true> src{dx, x, sum, g_fm, g_lin, ld, (uint32_t)m, k};
+  return dispatch_segment_reduce(src, k, N, sorted_pos, seg_start, n_unique, out_rows, out_bias, out_lin, sink, 2,
+                                 (cudaStream_t)stream);
+}
+
+int rm_emb_fm_bwd(const float* dx, const float* x, int64_t ld, const float* sum, const float* g_fm, const float* g_lin,
+                  int32_t m, int32_t k, int64_t N, const int32_t* sorted_pos, const int32_t* seg_start,
+                  const int32_t* n_unique, float* out_rows, float* out_bias, float* out_lin, void* stream) {
+  return emb_fm_bwd_impl(dx, x, ld, sum, g_fm, g_lin, m, k, N, sorted_pos, seg_start, n_unique, out_rows, out_bias,
+                         out_lin, rm::UpdateSink{}, stream);
+}
+
+int rm_emb_fm_bwd_update(const float* dx, const float* x, int64_t ld, const float* sum, const float* g_fm,
+                         const float* g_lin, int32_t m, int32_t k, int64_t N, const int32_t* sorted_pos,
+                         const int32_t* seg_start, const int64_t* uniq_rows, const int32_t* n_unique, float* table,
+                         float* bias_table, float* lin_table, int32_t opt, float lr, float l2, void* stream) {
+  using namespace rm;
+  RM_CHECK_ARG(table && uniq_rows, "null pointer");
+  UpdateSink sink{table, g_fm ? bias_table : nullptr, g_lin ? lin_table : nullptr, uniq_rows, OptParams{}};
+  const int rc = make_params(opt, lr, l2, &sink.o);
+  if (rc) return rc;
+  return emb_fm_bwd_impl(dx, x, ld, sum, g_fm, g_lin, m, k, N, sorted_pos, seg_start, n_unique, nullptr, nullptr,
+                         nullptr, sink, stream);
+}
+
+size_t rm_shard_plan_workspace_bytes(int64_t Ntot, int64_t N_cap) {
+  if (Ntot <= 0 || N_cap <= 0) return 256;
+  return rm::shard_plan_layout(Ntot, N_cap, nullptr).total;
+}
+
+int rm_shard_plan(const int64_t* gids, int64_t Ntot, int32_t m, int32_t W, int32_t rank, const int64_t* feat_sizes,
+                  const int64_t* local_offsets, int64_t total_local, int64_t N_cap, void* workspace,
+                  size_t workspace_bytes, int32_t* sorted_gpos, int32_t* seg_start, int64_t* uniq_rows,
+                  int32_t* n_unique, int32_t* n_own, int32_t* status, void* stream) {
+  using namespace rm;
+  RM_CHECK_ARG(gids && feat_sizes && local_offsets && workspace && sorted_gpos && seg_start && uniq_rows && n_unique &&
+                   n_own, "null pointer");
+  RM_CHECK_ARG(Ntot > 0 && m > 0 && N_cap > 0 && total_local > 0 && rank >= 0 && rank < W, "bad shape");
+  RM_UNSUPPORTED(W >= 1 && W <= RM_MAX_PEERS && (W & (W - 1)) == 0, "world size must be a power of two <= 8");
+  RM_UNSUPPORTED(Ntot < ((int64_t)1 << 31) - 1 && N_cap <= Ntot, "W*B*m must be < 2^31 - 1 and N_cap <= W*B*m");
+  RM_UNSUPPORTED(total_local < ((int64_t)1 << 31), "local rows must be < 2^31 (32-bit sort keys + sentinel)");
+  cudaStream_t st = (cudaStream_t)stream;
+  ShardPlanWs w = shard_plan_layout(Ntot, N_cap, workspace);
+  if (workspace_bytes < w.total) {
+    set_error("rm_shard_plan: workspace %zu < required %zu", workspace_bytes, w.total);
+    return RM_E_WORKSPACE;
+  }
+  int wshift = 0;
+  while ((1 << wshift) < W) ++wshift;
+  thrust::counting_iterator<int32_t> counting(0);
+  OwnedBy own{gids, feat_sizes, (uint32_t)m, (int64_t)(W - 1), (int64_t)rank};
+  size_t bytes = w.cub_bytes;
+  RM_CUDA(cub::DeviceSelect::If(w.cub_temp, bytes, counting, w.own_gpos, n_own, (int)Ntot, own, st));
+  count_launch();
+  int end_bit = 1;
+  while (end_bit < 31 && ((int64_t)1 << end_bit) < total_local) ++end_bit;
+  const uint32_t sentinel = 1u << end_bit;
+  shard_keys_kernel<<<grid_for(N_cap, 256, 8), 256, 0, st>>>(gids, local_offsets, (uint32_t)m, wshift, w.own_gpos, n_own,
+                                                            (int32_t)N_cap, sentinel, w.keys_in, w.pos_in, status);
+  RM_LAUNCH_CHECK();
+  bytes = w.cub_bytes;
+  RM_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, bytes, (const uint32_t*)w.keys_in, w.keys_out,
+                                          (const int32_t*)w.pos_in, sorted_gpos, (int)N_cap, 0, end_bit + 1, st));
+  count_launch();
+  HeadOfLiveRun head{w.keys_out, n_own, (int32_t)N_cap};
+  bytes = w.cub_bytes;
+  RM_CUDA(cub::DeviceSelect::If(w.cub_temp, bytes, counting, seg_start, n_unique, (int)N_cap, head, st));
+  count_launch();
+  finish_shard_plan_kernel<<<grid_for(N_cap + 1, 256, 8), 256, 0, st>>>(w.keys_out, seg_start, n_unique, n_own,
+                                                                       (int32_t)N_cap, uniq_rows);
+  RM_LAUNCH_CHECK();
+  return 0;
+}
+
+static int segment_reduce_p2p_impl(const float* const* G, int32_t W, int64_t rows_per_rank, int32_t KP, int32_t k,
+                                   int64_t N_cap, const int32_t* sorted_gpos, const int32_t* seg_start,
+                                   const int32_t* n_unique, float* out_rows, float* out_bias, float* out_lin,
+                                   const rm::UpdateSink& sink, void* stream) {
+  using namespace rm;
+  RM_CHECK_ARG(G && sorted_gpos && seg_start && n_unique, "null pointer");
+  RM_CHECK_ARG(W >= 1 && W <= RM_MAX_PEERS && rows_per_rank > 0 && k > 0 && KP >= k + 4 && N_cap >= 0, "bad shape");
+  RM_UNSUPPORTED(k % 4 == 0 && KP % 4 == 0 && (!out_rows || aligned16(out_rows)) &&
+                     (!sink.table || aligned16(sink.table)),
+                 "peer segment reduce needs k % 4 == 0 and 16-byte aligned rows");
+  RM_UNSUPPORTED(rows_per_rank * W < ((int64_t)1 << 31), "W * rows_per_rank must be < 2^31");
+  if (N_cap == 0) return 0;
+  PeerRowSrc src;
+  for (int r = 0; r < RM_MAX_PEERS; ++r) {
+    src.G[r] = r < W ? G[r] : nullptr;
+    RM_CHECK_ARG(r >= W || (G[r] && aligned16(G[r])), "null / misaligned peer buffer");
+  }
+  src.rows_per_rank = (uint32_t)rows_per_rank;
+  src.KP = KP;
+  src.k = k;
+  return dispatch_segment_reduce(src, k, N_cap, sorted_gpos, seg_start, n_unique, out_rows, out_bias, out_lin, sink, 2,
+                                 (cudaStream_t)stream);
+}
+
+int rm_segment_reduce_p2p(const float* const* G, int32_t W, int64_t rows_per_rank, int32_t KP, int32_t k,
+                          int64_t N_cap, const int32_t* sorted_gpos, const int32_t* seg_start,
+                          const int32_t* n_unique, float* out_rows, float* out_bias, float* out_lin, void* stream) {
+  return segment_reduce_p2p_impl(G, W, rows_per_rank, KP, k, N_cap, sorted_gpos, seg_start, n_unique, out_rows,
+                                 out_bias, out_lin, rm::UpdateSink{}, stream);
+}
+
+int rm_segment_reduce_p2p_update(const float* const* G, int32_t W, int64_t rows_per_rank, int32_t KP, int32_t k,
+                                 int64_t N_cap, const int32_t* sorted_gpos, const int32_t* seg_start,
+                                 const int64_t* uniq_rows, const int32_t* n_unique, float* table, float* bias_table,
+                                 float* lin_table, int32_t opt, float lr, float l2, void* stream) {
+  using namespace rm;
+  RM_CHECK_ARG(table && uniq_rows, "null pointer");
+  UpdateSink sink{table, bias_table, lin_table, uniq_rows, OptParams{}};
+  const int rc = make_params(opt, lr, l2, &sink.o);
+  if (rc) return rc;
+  return segment_reduce_p2p_impl(G, W, rows_per_rank, KP, k, N_cap, sorted_gpos, seg_start, n_unique, nullptr, nullptr,
+                                 nullptr, sink, stream);
 }
 
 }  // extern "C"

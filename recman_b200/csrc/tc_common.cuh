@@ -105,6 +105,45 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t& a0, uint32_t&
                : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
                : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* a) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16p(uint32_t taddr, uint32_t* a) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]),
+        "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* a) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
+      "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]),
+        "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]), "=r"(a[16]),
+        "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]),
+        "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31])
+      : "r"(taddr));
+}
+// NCOL (multiple of 4) consecutive columns -> a[0..NCOL), widest loads first; the caller issues tmem_ld_wait()
+template <int NCOL>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* a) {
+  static_assert(NCOL % 4 == 0, "column count must be a multiple of 4");
+  if constexpr (NCOL >= 32) {
+    tmem_ld32(taddr, a);
+    if constexpr (NCOL > 32) tmem_ld_cols<NCOL - 32>(taddr + 32, a + 32);
+  } else if constexpr (NCOL >= 16) {
+    tmem_ld16p(taddr, a);
+    if constexpr (NCOL > 16) tmem_ld_cols<NCOL - 16>(taddr + 16, a + 16);
+  } else if constexpr (NCOL >= 8) {
+    tmem_ld8(taddr, a);
+    if constexpr (NCOL > 8) tmem_ld_cols<NCOL - 8>(taddr + 8, a + 8);
+  } else if constexpr (NCOL == 4) {
+    tmem_ld4(taddr, a[0], a[1], a[2], a[3]);
+  }
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc512(uint32_t slot_smem) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(slot_smem) : "memory");

@@ -233,6 +233,24 @@ def emb_fm_bwd(dx, x, ld, S, g_fm, g_lin, plan: SegmentPlan, k, want_rows=True, 
     return out_rows, out_bias, out_lin
 
 
+def segment_reduce_p2p_update(G_ptrs, rows_per_rank, KP, k, plan: SegmentPlan, table, bias_table, lin_table, opt, lr,
+                              l2=0.0):
+    _C.call(
+        "rm_segment_reduce_p2p_update", _ptr_array(G_ptrs), len(G_ptrs), int(rows_per_rank), KP, k, plan.N,
+        _p(plan.sorted_pos), _p(plan.seg_start), _p(plan.uniq_rows), _p(plan.n_unique), _p(table), _p(bias_table),
+        _p(lin_table), opt, float(lr), float(l2), _stream(),
+    )
+
+
+def emb_fm_bwd_update(dx, x, ld, S, g_fm, g_lin, plan: SegmentPlan, k, table, bias_table, lin_table, opt, lr, l2=0.0):
+    """rm_emb_fm_bwd + rm_sparse_opt_step in one pass: the tables are updated in place, nothing is returned."""
+    _C.call(
+        "rm_emb_fm_bwd_update", _p(dx), _p(x), ld, _p(S), _p(g_fm), _p(g_lin), plan.m, k, plan.N, _p(plan.sorted_pos),
+        _p(plan.seg_start), _p(plan.uniq_rows), _p(plan.n_unique), _p(table), _p(bias_table), _p(lin_table), opt,
+        float(lr), float(l2), _stream(),
+    )
+
+
 @dataclass
 class SparseGrad:
     """K2's output for one table: rows ``uniq_rows[:n]`` received ``rows[:n]``."""
@@ -385,9 +403,84 @@ def unpack_rows(recv, pos, m, k, x, bias_out=None, lin_out=None):
     _C.call("rm_unpack_rows", _p(recv), n, KP, _p(pos), m, k, _p(x), x.stride(0), _p(bias_out), _p(lin_out), _stream())
 
 
-def pack_grad_rows(dx, x, ld, S, g_fm, g_lin, pos, m, k, KP):
-    n = pos.numel()
-    send = torch.empty(n, KP, dtype=torch.float32, device=pos.device)
+def pack_grad_rows(dx, x, ld, S, g_fm, g_lin, pos, m, k, KP, out=None, n=None):
+    """Gradient rows [n, KP] = [dx + g_fm*(S - x) | g_fm | g_lin | 0 | 0]; ``pos`` None keeps position order."""
+    if n is None:
+        n = pos.numel()
+    send = out if out is not None else torch.empty(n, KP, dtype=torch.float32, device=x.device)
+    assert send.is_contiguous() and send.shape == (n, KP)
     _C.call("rm_pack_grad_rows", _p(dx), _p(x), ld, _p(S), _p(g_fm), _p(g_lin), n, KP, _p(pos), m, k, _p(send),
             _stream())
     return send
+
+
+# --------------------------------------------------------------------------- #
+# (e') row-sharded tables over NVLink peer memory
+# --------------------------------------------------------------------------- #
+def _ptr_array(ptrs):
+    """Host array of device pointers (``const float* const*`` in the C ABI)."""
+    import ctypes
+
+    return (ctypes.c_void_p * len(ptrs))(*[int(q) for q in ptrs])
+
+
+def gather_fm_fwd_p2p(tab_ptrs, bias_ptrs, lin_ptrs, k, feat_sizes, local_offs, ids, dense, lin_dense, status=None):
+    """Fused front end with every row read from its owner's table (peer memory).  Returns (x, fm, lin, S)."""
+    _dev_check(ids)
+    B, m = ids.shape
+    W = len(tab_ptrs)
+    n_dense = 0 if dense is None else dense.shape[1]
+    d = m * k + n_dense
+    ld = (d + 3) // 4 * 4
+    dev = ids.device
+    x = torch.empty(B, ld, dtype=torch.float32, device=dev)
+    if ld > d:
+        x[:, d:].zero_()
+    fm = torch.empty(B, dtype=torch.float32, device=dev)
+    lin = torch.empty(B, dtype=torch.float32, device=dev)
+    S = torch.empty(B, k, dtype=torch.float32, device=dev)
+    if dense is not None:
+        dense = _f32c(dense, "dense").contiguous()
+    assert ids.dtype == torch.int64 and ids.is_contiguous()
+    _C.call(
+        "rm_gather_fm_fwd_p2p", _ptr_array(tab_ptrs), None if bias_ptrs is None else _ptr_array(bias_ptrs),
+        None if lin_ptrs is None else _ptr_array(lin_ptrs), W, _p(feat_sizes), _p(local_offs), _p(ids), _p(dense),
+        _p(lin_dense), n_dense, B, m, k, _p(x), ld, _p(fm), _p(lin), _p(S), _p(status), _stream(),
+    )
+    return x, fm, lin, S
+
+
+def shard_plan(gids, W, rank, feat_sizes, local_offs, total_local, n_cap, status=None):
+    """Owner-side K2 plan over the ids of all ranks (gids [W*b, m]) -> SegmentPlan of global positions + n_own."""
+    _dev_check(gids)
+    assert gids.dtype == torch.int64 and gids.is_contiguous() and gids.dim() == 2
+    Ntot, m = gids.numel(), gids.shape[1]
+    n_cap = int(min(n_cap, Ntot))
+    dev = gids.device
+    ws_bytes = _C.lib.rm_shard_plan_workspace_bytes(Ntot, n_cap)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    sorted_gpos = torch.empty(n_cap, dtype=torch.int32, device=dev)
+    seg_start = torch.empty(n_cap + 1, dtype=torch.int32, device=dev)
+    uniq_rows = torch.empty(n_cap, dtype=torch.int64, device=dev)
+    n_unique = torch.empty(1, dtype=torch.int32, device=dev)
+    n_own = torch.empty(1, dtype=torch.int32, device=dev)
+    _C.call(
+        "rm_shard_plan", _p(gids), Ntot, m, W, rank, _p(feat_sizes), _p(local_offs), int(total_local), n_cap, _p(ws),
+        ws_bytes, _p(sorted_gpos), _p(seg_start), _p(uniq_rows), _p(n_unique), _p(n_own), _p(status), _stream(),
+    )
+    plan = SegmentPlan(n_cap, 1, sorted_gpos, seg_start, uniq_rows, n_unique, ws)
+    plan.n_own = n_own
+    return plan
+
+
+def segment_reduce_p2p(G_ptrs, rows_per_rank, KP, k, plan: SegmentPlan, want_bias=True, want_lin=True):
+    dev = plan.sorted_pos.device
+    n = max(plan.N, 1)
+    out_rows = torch.empty(n, k, dtype=torch.float32, device=dev)
+    out_bias = torch.empty(n, dtype=torch.float32, device=dev) if want_bias else None
+    out_lin = torch.empty(n, dtype=torch.float32, device=dev) if want_lin else None
+    _C.call(
+        "rm_segment_reduce_p2p", _ptr_array(G_ptrs), len(G_ptrs), int(rows_per_rank), KP, k, plan.N,
+        _p(plan.sorted_pos), _p(plan.seg_start), _p(plan.n_unique), _p(out_rows), _p(out_bias), _p(out_lin), _stream(),
+    )
+    return out_rows, out_bias, out_lin

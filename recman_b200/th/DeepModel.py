@@ -127,7 +127,11 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
 
     def check_ids(self):
         """Raises if any id seen so far was outside its table (host sync; call it outside hot loops)."""
-        if self._emb_status is not None and int(self._emb_status.item()) != 0:
+        st = 0 if self._emb_status is None else int(self._emb_status.item())
+        if st & 4:
+            raise _C.RecmanB200Error("row-sharded tables: a rank owned more ids than the plan capacity "
+                                     "(ShardPlan.slack); gradients of the overflowing ids were dropped")
+        if st:
             raise _C.RecmanB200Error("an embedding id was outside its table (rows were zero-filled)")
 
     def _fused_front_end(self, layer: FeatEmbeddingLayer, inputs: DataInputs, linear: Optional[LinearLayer],
@@ -155,8 +159,11 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
                 return None
             if self.shard is not None:
                 linear.total = self.shard.total_local + n_dense  # id rows are sharded like the tables, tail replicated
+                linear.alloc = self.shard.alloc
             linear._upsert_variables()
             W = linear.effective_weight()
+            if self.shard is not None and W is not self.variables[f"{linear.prefix}linear_w"]:
+                raise NotImplementedError("row-sharded tables: inference-time feature weights are not supported")
             flat = W.reshape(-1)
             lin_table = flat[: layer.total_rows]
             lin_dense = flat[layer.total_rows :] if n_dense else None
@@ -167,14 +174,21 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
             W_lin = self.variables[f"{linear.prefix}linear_w"]
             lin_table = lin_table.detach()
             lin_dense = None if lin_dense is None else lin_dense.detach().contiguous()
+        # N1: inside a training step the sparse update is applied by the backward kernel itself (no summed-gradient
+        # round trip) when nothing else needs the embedding gradients: no dense L2 on the tables, no touched-rows L2
+        fused = getattr(self, "_fused_opt", None)
+        if fused is not None and (layer.l2_reg or (linear is not None and linear.l2_reg)
+                                  or getattr(table, "rm_l2_touched", 0.0)):
+            fused = None
         if self.shard is not None:
-            from .dist import ShardedFrontEndFunction
+            from .dist import P2PFrontEndFunction, ShardedFrontEndFunction
 
-            x, fm, lin = ShardedFrontEndFunction.apply(table, bias_table, W_lin, lin_table, lin_dense, self.shard,
-                                                       self._status(), ids, dense)
+            fn = P2PFrontEndFunction if self.shard.peer is not None else ShardedFrontEndFunction
+            x, fm, lin = fn.apply(table, bias_table, W_lin, lin_table, lin_dense, self.shard, self._status(), ids,
+                                  dense, fused)
         else:
             x, fm, lin = FrontEndFunction.apply(table, bias_table, W_lin, lin_table, lin_dense, lay.runs[0].offsets,
-                                                layer.total_rows, self._status(), ids, dense)
+                                                layer.total_rows, self._status(), ids, dense, fused)
         d = lay.m * k + n_dense
         if linear is not None:
             lin = lin + self.variables[f"{linear.prefix}linear_w0"]
@@ -266,8 +280,9 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
         buffers and replays.  Not available with row-sharded tables yet (the exchange has a host-side split-size
         sync).  The ``warmup`` eager steps are real optimisation steps on ``example``.
         """
-        if self.shard is not None:
-            raise NotImplementedError("compile_step with row-sharded tables")
+        if self.shard is not None and self.shard.peer is None:
+            raise NotImplementedError("compile_step with the all-to-all exchange (split sizes need a host sync); "
+                                      "use peer-memory sharding")
         from .. import ops as _ops
 
         st = DataInputs.from_tensors(
@@ -289,12 +304,25 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
         self._graph, self._graph_inputs, self._graph_loss = graph, st, loss
         return self
 
+    def _fused_opt_config(self):
+        """(optimizer kind, lr) when the embedding update may be fused into the backward kernel, else None."""
+        if not self.hparams.get("fuse_sparse_update", True):
+            return None
+        opt = self.hparams.get("optimizer", "adam")
+        if not isinstance(opt, str) or opt not in _C.OPT_KINDS:
+            return None
+        return _C.OPT_KINDS[opt], float(self.hparams.get("learning_rate", 0.001))
+
     def _eager_step(self, inputs: DataInputs):
-        loss = self._loss(inputs)
-        if self.shard is not None:
-            (loss / self.shard.world).backward()
-        else:
-            loss.backward()
+        self._fused_opt = self._fused_opt_config()
+        try:
+            loss = self._loss(inputs)
+            if self.shard is not None:
+                (loss / self.shard.world).backward()
+            else:
+                loss.backward()
+        finally:
+            self._fused_opt = None
         self.optimizer_step()
         return loss.detach()
 
@@ -348,6 +376,9 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
                 ops.dense_opt_step(p.data, g.contiguous(), kind, lr, 0.0)
             elif p.grad is not None:
                 ops.dense_opt_step(p.data, p.grad.contiguous(), kind, lr, 0.0)
+            elif tail is not None:  # id rows already updated by the fused backward kernel: only the dense tail is left
+                first, g = tail
+                ops.dense_opt_step(p.data.reshape(-1)[first:], g.contiguous(), kind, lr, 0.0)
             p.grad = None
 
     def _eval_at_epoch(self, X_train, y_train, X_valid=None, y_valid=None, start_time=None, epoch=0,

@@ -13,6 +13,18 @@ lives on rank ``r mod W`` at local row ``r div W`` (cyclic: immune to id-range s
 
 The routing arithmetic (``ShardPlan``, ``build_exchange``) is pure torch and device agnostic so that it is
 tested on CPU with the gloo backend (tests/test_dist_gloo.py); the row movement is CUDA kernels + NCCL.
+
+Peer-memory mode (default when the world size is a power of two <= 8, i.e. one NVSwitch box; ``PeerMemory``,
+``P2PFrontEndFunction``): the tables and one gradient-row buffer per rank are cudaIpc-mapped into every rank, and
+
+    forward   all-gather of the ids (13.6 MB per rank at C5; also the step's cross-rank barrier)
+              ONE fused front-end kernel per rank that reads every row from its owner: local HBM or NVLink loads
+    backward  rm_pack_grad_rows (position order, into this rank's buffer G) ; 4-byte all-reduce (= "all G written")
+              owner-side plan over the gathered ids + deterministic segmented reduce that pulls its rows from the
+              peers' G over NVLink, summed in ascending GLOBAL position (the single-GPU order of the global batch)
+
+There is no all-to-all, no pack/unpack of the forward rows, no split-size host sync, so the step is CUDA-graph
+capturable; NVLink traffic is exactly one row per remote id each way.
 """
 
 from __future__ import annotations
@@ -24,7 +36,61 @@ import torch
 import torch.distributed as dist
 from torch.autograd import Function
 
-__all__ = ["ShardPlan", "Exchange", "build_exchange", "shard_model", "ShardedFrontEndFunction", "allreduce_dense"]
+__all__ = ["ShardPlan", "Exchange", "build_exchange", "shard_model", "ShardedFrontEndFunction", "allreduce_dense",
+           "PeerMemory", "P2PFrontEndFunction"]
+
+
+class _DevicePointer:
+    """Raw device allocation exposed through __cuda_array_interface__ so that torch can wrap it without a copy."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
+class PeerMemory:
+    """cudaIpc-shared device allocations of one process group: ``alloc`` is collective (every rank, same order)."""
+
+    def __init__(self, world: int, rank: int, group=None):
+        self.world, self.rank, self.group = world, rank, group
+        self._ptrs = {}  # local base pointer -> [pointer of that allocation in rank 0..W-1's address space mapping]
+        self._keep = []
+
+    def alloc(self, shape, dtype=torch.float32, zero=True) -> torch.Tensor:
+        import ctypes
+
+        from .. import _C
+
+        n = 1
+        for v in shape:
+            n *= int(v)
+        nbytes = max(n * torch.empty((), dtype=dtype).element_size(), 256)
+        ptr = ctypes.c_void_p()
+        handle = (ctypes.c_uint8 * 64)()
+        _C.check(_C.lib.rm_p2p_alloc(nbytes, ctypes.byref(ptr), handle), "rm_p2p_alloc")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=self.group)
+        ptrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                ptrs.append(int(ptr.value))
+                continue
+            q = ctypes.c_void_p()
+            hb = (ctypes.c_uint8 * 64).from_buffer_copy(h)
+            _C.check(_C.lib.rm_p2p_open(hb, ctypes.byref(q)), "rm_p2p_open")
+            ptrs.append(int(q.value))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        raw = torch.as_tensor(_DevicePointer(ptr.value, nbytes), device=dev)
+        t = raw[: n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(*shape)
+        if zero:
+            t.zero_()
+        self._ptrs[int(ptr.value)] = ptrs
+        self._keep.append(raw)
+        return t
+
+    def ptrs_of(self, t: torch.Tensor):
+        """Pointers of ``t``'s allocation in every rank (``t`` must start at the allocation's base)."""
+        return self._ptrs[int(t.data_ptr())]
 
 
 class ShardPlan:
@@ -40,6 +106,43 @@ class ShardPlan:
         self.local_offsets = offs
         self.total_local = offs[-1]
         self._offs_dev = {}
+        self.peer: Optional[PeerMemory] = None  # set by enable_peer_memory(): tables live in cudaIpc-shared memory
+        self._bufs = {}
+        self.slack = 0.25  # owner-side plan capacity = (1 + slack) * b*m + 1024 entries
+
+    # ---- peer-memory mode -------------------------------------------------------------------------------
+    def enable_peer_memory(self):
+        if self.world & (self.world - 1) or self.world > 8:
+            raise ValueError("peer-memory sharding needs a power-of-two world size <= 8 (one NVSwitch box)")
+        self.peer = PeerMemory(self.world, self.rank, self.group)
+        return self
+
+    def alloc(self, shape, zero=True) -> torch.Tensor:
+        """Parameter storage: cudaIpc-shared in peer-memory mode, plain torch memory otherwise."""
+        if self.peer is not None:
+            return self.peer.alloc(shape, zero=zero)
+        return (torch.zeros if zero else torch.empty)(*shape, dtype=torch.float32, device="cuda")
+
+    def feat_sizes_on(self, device) -> torch.Tensor:
+        key = ("fs", str(device))
+        if key not in self._offs_dev:
+            self._offs_dev[key] = torch.tensor(self.feat_sizes, dtype=torch.int64, device=device)
+        return self._offs_dev[key]
+
+    def grad_buffer(self, n: int, KP: int) -> torch.Tensor:
+        key = ("G", n, KP)
+        if key not in self._bufs:
+            self._bufs[key] = self.peer.alloc((n, KP), zero=True)
+        return self._bufs[key]
+
+    def flag(self, device) -> torch.Tensor:
+        key = ("flag", str(device))
+        if key not in self._bufs:
+            self._bufs[key] = torch.zeros(1, dtype=torch.float32, device=device)
+        return self._bufs[key]
+
+    def capacity(self, n_local: int) -> int:
+        return min(self.world * n_local, int(n_local * (1.0 + self.slack)) + 1024)
 
     def offsets_on(self, device) -> torch.Tensor:
         key = str(device)
@@ -103,7 +206,8 @@ class ShardedFrontEndFunction(Function):
     """Sharded version of autograd.FrontEndFunction: same outputs (xbuf, fm, lin), rows fetched over NVLink."""
 
     @staticmethod
-    def forward(ctx, table, bias_table, W_lin, lin_table, lin_dense, plan: ShardPlan, status, ids, dense):
+    def forward(ctx, table, bias_table, W_lin, lin_table, lin_dense, plan: ShardPlan, status, ids, dense,
+                fused_opt=None):
         from .. import ops
 
         b, m = ids.shape
@@ -177,6 +281,75 @@ class ShardedFrontEndFunction(Function):
         return (None,) * 10
 
 
+class P2PFrontEndFunction(Function):
+    """Peer-memory version of autograd.FrontEndFunction: same outputs (xbuf, fm, lin); rows come from their owners."""
+
+    @staticmethod
+    def forward(ctx, table, bias_table, W_lin, lin_table, lin_dense, plan: ShardPlan, status, ids, dense,
+                fused_opt=None):
+        from .. import ops
+
+        b, m = ids.shape
+        k = table.shape[1]
+        W, dev, peer = plan.world, table.device, plan.peer
+        ctx.fused_opt, ctx.lin_table = fused_opt, lin_table
+        ids = ids.contiguous()
+        gids = torch.empty(W * b, m, dtype=torch.int64, device=dev)
+        # every rank has finished the previous step's table update once this returns (it is also the barrier that
+        # protects the peers' tables and gradient buffers)
+        dist.all_gather_into_tensor(gids, ids, group=plan.group)
+        x, fm, lin, S = ops.gather_fm_fwd_p2p(
+            peer.ptrs_of(table), None if bias_table is None else peer.ptrs_of(bias_table),
+            None if lin_table is None else peer.ptrs_of(lin_table), k, plan.feat_sizes_on(dev), plan.offsets_on(dev),
+            ids, dense, lin_dense, status=status)
+        ctx.plan, ctx.status = plan, status
+        ctx.table, ctx.bias_table, ctx.W_lin = table, bias_table, W_lin
+        ctx.has_lin = lin_table is not None
+        ctx.has_lin_dense = lin_dense is not None and dense is not None and dense.shape[1] > 0
+        ctx.save_for_backward(x, S, dense, gids)
+        ctx.b, ctx.m, ctx.k = b, m, k
+        ctx.set_materialize_grads(False)
+        return x, fm.reshape(-1, 1), lin.reshape(-1, 1)
+
+    @staticmethod
+    def backward(ctx, dx, dfm, dlin):
+        from .. import ops
+        from ..autograd import attach_sparse_grad
+
+        x, S, dense, gids = ctx.saved_tensors
+        plan: ShardPlan = ctx.plan
+        b, m, k = ctx.b, ctx.m, ctx.k
+        KP = k + 4
+        ld = x.shape[1]
+        dev = x.device
+        if dx is not None and (dx.stride(1) != 1 or dx.stride(0) != ld):
+            dx = dx.contiguous()
+        g_fm = None if dfm is None else dfm.reshape(-1).contiguous()
+        g_lin = None if dlin is None else dlin.reshape(-1).contiguous()
+        sp = ops.shard_plan(gids, plan.world, plan.rank, plan.feat_sizes_on(dev), plan.offsets_on(dev),
+                            plan.total_local, plan.capacity(b * m), ctx.status)
+        G = plan.grad_buffer(b * m, KP)
+        ops.pack_grad_rows(dx, x, ld, S, g_fm, g_lin, None, m, k, KP, out=G, n=b * m)
+        dist.all_reduce(plan.flag(dev), group=plan.group)  # every rank's G is complete
+        want_bias = ctx.bias_table is not None and g_fm is not None
+        want_lin = ctx.has_lin and ctx.W_lin is not None and g_lin is not None
+        if ctx.has_lin_dense and ctx.W_lin is not None and g_lin is not None:
+            ctx.W_lin.rm_dense_tail = (plan.total_local, dense.t() @ g_lin)
+        if ctx.fused_opt is not None:
+            kind, lr = ctx.fused_opt
+            ops.segment_reduce_p2p_update(plan.peer.ptrs_of(G), b * m, KP, k, sp, ctx.table.data,
+                                          ctx.bias_table.data if want_bias else None,
+                                          ctx.lin_table if want_lin else None, kind, lr)
+            return (None,) * 10
+        rows, ob, ol = ops.segment_reduce_p2p(plan.peer.ptrs_of(G), b * m, KP, k, sp, want_bias, want_lin)
+        attach_sparse_grad(ctx.table, ops.SparseGrad(sp.uniq_rows, rows, sp.n_unique))
+        if want_bias:
+            attach_sparse_grad(ctx.bias_table, ops.SparseGrad(sp.uniq_rows, ob, sp.n_unique))
+        if want_lin:
+            attach_sparse_grad(ctx.W_lin, ops.SparseGrad(sp.uniq_rows, ol, sp.n_unique))
+        return (None,) * 10
+
+
 def allreduce_dense(grads: List[torch.Tensor], group=None) -> None:
     """One flat bucket: the replicated parameters are ~1.5 M floats at most, latency bound."""
     if not grads:
@@ -190,10 +363,16 @@ def allreduce_dense(grads: List[torch.Tensor], group=None) -> None:
         off += n
 
 
-def shard_model(model, world: int, rank: int, group=None):
-    """Switch a recman.th model to row-sharded tables + DP dense layers (before its variables are created)."""
+def shard_model(model, world: int, rank: int, group=None, mode: str = "auto"):
+    """Switch a recman.th model to row-sharded tables + DP dense layers (before its variables are created).
+
+    ``mode``: "p2p" (NVLink peer memory, power-of-two world <= 8), "a2a" (NCCL all-to-all exchange) or "auto"."""
     if model.variables:
         raise RuntimeError("shard_model must be called before the first forward creates the variables")
     sizes = [f.feat_size for f in model.feat_dict.embedding_feats]
     model.shard = ShardPlan(sizes, world, rank, group)
+    if mode == "auto":
+        mode = "p2p" if (world & (world - 1)) == 0 and world <= 8 and torch.cuda.is_available() else "a2a"
+    if mode == "p2p":
+        model.shard.enable_peer_memory()
     return model

@@ -197,7 +197,10 @@ class FeatEmbeddingLayer:
     def _upsert_variables(self):
         k = self.embedding_size
         if self.table_name not in self.variables:
-            table = torch.empty(self.total_rows, k, dtype=torch.float32, device=DEVICE)
+            if self.shard is not None:
+                table = self.shard.alloc((self.total_rows, k), zero=True)  # cudaIpc-shared in peer-memory mode
+            else:
+                table = torch.empty(self.total_rows, k, dtype=torch.float32, device=DEVICE)
             for i, (f, lo) in enumerate(zip(self.feats, self.row_offsets)):
                 rows = f.feat_size if self.shard is None else self.shard.local_sizes[i]
                 # fans come from the full table shape so that the init scale does not depend on the world size
@@ -208,7 +211,9 @@ class FeatEmbeddingLayer:
                 torch.nn.init.trunc_normal_(table[lo : lo + rows], mean=0.0, std=std, a=-2 * std, b=2 * std, generator=g)
             self.variables[self.table_name] = _param(table)
         if self.use_bias and self.bias_name not in self.variables:
-            self.variables[self.bias_name] = _param(torch.zeros(self.total_rows, dtype=torch.float32, device=DEVICE))
+            bias = (self.shard.alloc((self.total_rows,)) if self.shard is not None
+                    else torch.zeros(self.total_rows, dtype=torch.float32, device=DEVICE))
+            self.variables[self.bias_name] = _param(bias)
 
     def feature_tables(self) -> Dict[str, torch.Tensor]:
         """Reference-named views: ``{prefix}{feat}_feat_embed`` [V_f, k], ``{prefix}{feat}_feat_bias`` [V_f, 1]."""
@@ -348,6 +353,7 @@ class LinearLayer:
         sizes = [f.feat_size for f in self.linear_feats]
         self.offsets = [0] + list(np.cumsum(sizes))
         self.total = int(self.offsets[-1])
+        self.alloc = None  # th.dist.ShardPlan.alloc when linear_w's id rows are row-sharded
 
     def _upsert_variables(self):
         name = f"{self.prefix}linear_w0"
@@ -355,7 +361,9 @@ class LinearLayer:
             self.variables[name] = _param(torch.zeros(1, dtype=torch.float32, device=DEVICE))
         name = f"{self.prefix}linear_w"
         if name not in self.variables:
-            self.variables[name] = _param(torch.zeros(self.total, 1, dtype=torch.float32, device=DEVICE))
+            w = self.alloc((self.total, 1)) if self.alloc is not None else torch.zeros(
+                self.total, 1, dtype=torch.float32, device=DEVICE)
+            self.variables[name] = _param(w)
 
     def effective_weight(self):
         W = self.variables[f"{self.prefix}linear_w"]

@@ -43,7 +43,8 @@ def main():
 
     # ---- sharded model ----
     model = DeepFM(fd, **kw)
-    rdist.shard_model(model, world, rank)
+    mode = os.environ.get("DIST_MODE", "auto")
+    rdist.shard_model(model, world, rank, mode=mode)
     with torch.no_grad():
         model._out(DataInputs("cuda").load(fd, Xr, yr))
     plan = model.shard
@@ -103,9 +104,23 @@ def main():
     model.fit_on_batch(Xr, yr)
     torch.cuda.synchronize()
     dist.barrier()
+    if model.shard.peer is not None and os.environ.get("DIST_GRAPH", "0") == "1":
+        # the peer-memory step has no host sync: capture it and replay twice
+        inputs = DataInputs("cuda").load(fd, Xr, yr)
+        model.compile_step(inputs, warmup=1)
+        l1 = model.fit_on_batch(inputs, None).clone()
+        l2 = model.fit_on_batch(inputs, None).clone()
+        torch.cuda.synchronize()
+        model.check_ids()
+        assert torch.isfinite(l1).all() and torch.isfinite(l2).all() and float(l2) < float(l1) + 1e-3, (l1, l2)
+        dist.barrier()
     if rank == 0:
-        print(f"dist_check ok: world={world} k={k} sharded DeepFM == single-GPU on the global batch", flush=True)
-    dist.destroy_process_group()
+        print(f"dist_check ok: world={world} k={k} mode={'p2p' if model.shard.peer is not None else 'a2a'} "
+              f"sharded DeepFM == single-GPU on the global batch", flush=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":

@@ -150,3 +150,34 @@ def test_cuda_graph_step_equals_eager(model_name):
         torch.testing.assert_close(graph2.variables[name].data, eager2.variables[name].data, rtol=1e-6, atol=1e-7,
                                    msg=lambda m_: f"{name}: {m_}")
     graph2.check_ids()
+
+
+@pytest.mark.parametrize("model_name", ["DeepFM", "DCN"])
+@pytest.mark.parametrize("opt", ["adam", "adagrad"])
+def test_fused_sparse_update_is_bit_identical(model_name, opt):
+    """N1: the optimizer update applied inside the backward kernel (rm_emb_fm_bwd_update) == K2 then rm_sparse_opt_step."""
+    from recman_b200 import th
+
+    fd = pu.make_feat_dict(CRITEO_SMALL, n_dense=13)
+    X, y = pu.synth_batch(fd, 700, seed=21)  # duplicates guaranteed (tables of 2..1000 rows)
+    models = []
+    for fuse in (True, False):
+        kw = dict(embedding_size=16, deep_hidden_units=(32, 32), deep_dropout=(1, 1, 1), batch_size=700,
+                  embedding_l2_reg=0.0, linear_l2_reg=0.0, optimizer=opt, learning_rate=0.01)
+        if model_name == "DCN":
+            kw["cross_layer_num"] = 3
+        model = getattr(th, model_name)(fd, **kw)
+        model.hparams["fuse_sparse_update"] = fuse
+        from recman_b200.th.input import DataInputs
+
+        with torch.no_grad():
+            model._out(DataInputs("cuda").load(fd, X, y))
+        pu.randomize_variables(model, seed=3)
+        for _ in range(2):
+            model.fit_on_batch(X, y)
+        torch.cuda.synchronize()
+        models.append(model)
+    a, b = models
+    assert set(a.variables) == set(b.variables)
+    for name in a.variables:
+        assert torch.equal(a.variables[name].data, b.variables[name].data), name
