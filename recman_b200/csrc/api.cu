@@ -42,6 +42,9 @@ int rm_device_check(int device) {
                   prop.major, prop.minor);
     return RM_E_ARCH;
   }
+  // tuning run only: L2 sector-promotion granularity (32 / 64 / 128 bytes) for the k=1 random lookups
+  const int l2g = rm::tune_variant("RM_TUNE_L2_FETCH", 0);
+  if (l2g > 0) RM_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)l2g));
   return 0;
 }
 

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256, MINB) gather_fm_p2p_kernel(
     const PeerTables pt, int wshift, const int64_t* __restrict__ feat_sizes, const int64_t* __restrict__ local_offs,
     const int64_t* __restrict__ ids, const float* __restrict__ dense, const float* __restrict__ lin_dense, int n_dense,
     int64_t B, int m, int k, float* __restrict__ x, int64_t ld, float* __restrict__ fm_out, float* __restrict__ lin_out,
-    float* __restrict__ sum_out, int32_t* status, int scalar_mode) {
+    float* __restrict__ sum_out, int32_t* status) {
   const int lir = threadIdx.x % LPR;
   const int k4 = k >> 2;
   const bool col_ok = lir < k4;
@@ -45,23 +45,17 @@ __global__ void __launch_bounds__(256, MINB) gather_fm_p2p_kernel(
     if (live) {
       const int64_t* my_ids = ids + b * m;
       float* xrow = x + b * ld;
-      // scalar_mode bit 2 (tuning): every sample starts its walk at a different field, so that the requests in flight
-      // at any moment are spread over all tables instead of marching through them in lockstep
-      const int rot = (scalar_mode & 4) ? (int)((b * 7) % m) : 0;
       for (int f0 = 0; f0 < m; f0 += U) {
         int64_t row[U];
-        int owner[U], fi[U];
+        int owner[U];
         bool ok[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int fl = f0 + u;
-          int f = fl + rot;
-          if (f >= m) f -= m;
-          fi[u] = f;
+          const int f = f0 + u;
           ok[u] = false;
           row[u] = 0;
           owner[u] = 0;
-          if (fl < m) {
+          if (f < m) {
             const int64_t id = my_ids[f];
             ok[u] = (id >= 0) && (id < feat_sizes[f]);
             if (ok[u]) {
@@ -81,21 +75,16 @@ __global__ void __launch_bounds__(256, MINB) gather_fm_p2p_kernel(
           lv[u] = 0.f;
           if (ok[u]) {
             if (col_ok) v[u] = ldg_stream4(pt.tab[owner[u]] + row[u] * (int64_t)k + 4 * lir);
-            if (lir == (u % LPR)) {
-              if ((scalar_mode & 3) == 0) {
-                if (has_bias) bv[u] = ldg_stream1(pt.bias[owner[u]] + row[u]);
-                if (has_lin) lv[u] = ldg_stream1(pt.lin[owner[u]] + row[u]);
-              } else if ((scalar_mode & 3) == 1) {
-                if (has_bias) bv[u] = *(const volatile float*)(pt.bias[owner[u]] + row[u]);
-                if (has_lin) lv[u] = *(const volatile float*)(pt.lin[owner[u]] + row[u]);
-              }
+            if (lir == (u % LPR)) {  // spread the k=1 lookups over the lanes of the group
+              if (has_bias) bv[u] = ldg_stream1(pt.bias[owner[u]] + row[u]);
+              if (has_lin) lv[u] = ldg_stream1(pt.lin[owner[u]] + row[u]);
             }
           }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int f = fi[u];
-          if (f0 + u < m) {
+          const int f = f0 + u;
+          if (f < m) {
             if (col_ok) st4(xrow + (int64_t)f * k + 4 * lir, v[u]);
             S.x += v[u].x; S.y += v[u].y; S.z += v[u].z; S.w += v[u].w;
             Q.x += v[u].x * v[u].x; Q.y += v[u].y * v[u].y; Q.z += v[u].z * v[u].z; Q.w += v[u].w * v[u].w;
@@ -199,13 +188,12 @@ int rm_gather_fm_fwd_p2p(const float* const* tables, const float* const* bias_ta
   int wshift = 0;
   while ((1 << wshift) < W) ++wshift;
   cudaStream_t st = (cudaStream_t)stream;
-  const int smode = tune_variant("RM_TUNE_P2P_SCALAR", 0);
   const int lpr = pow2ceil_p(k / 4);
   const int grid = grid_for(B, 256 / (lpr > 32 ? 32 : lpr), 8);
 #define RM_GP(L)                                                                                                      \
   case L:                                                                                                             \
     gather_fm_p2p_kernel<L, 4, 4><<<grid, 256, 0, st>>>(pt, wshift, feat_sizes, local_offsets, ids, dense, lin_dense,  \
-                                                        n_dense, B, m, k, x, ld, fm_out, lin_out, sum_out, status, smode); \
+                                                        n_dense, B, m, k, x, ld, fm_out, lin_out, sum_out, status);        \
     break
   switch (lpr) {
     RM_GP(1);
@@ -215,7 +203,7 @@ int rm_gather_fm_fwd_p2p(const float* const* tables, const float* const* bias_ta
     RM_GP(16);
     default:
       gather_fm_p2p_kernel<32, 4, 4><<<grid, 256, 0, st>>>(pt, wshift, feat_sizes, local_offsets, ids, dense, lin_dense,
-                                                           n_dense, B, m, k, x, ld, fm_out, lin_out, sum_out, status, smode);
+                                                           n_dense, B, m, k, x, ld, fm_out, lin_out, sum_out, status);
   }
 #undef RM_GP
   RM_LAUNCH_CHECK();

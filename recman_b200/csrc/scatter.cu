@@ -97,6 +97,7 @@ static PlanWorkspace plan_layout(int64_t N, void* base) {
 template <bool FUSED>
 struct RowSrc {
   static constexpr bool kScalars = FUSED;
+  static constexpr int kTailU = FUSED ? 2 : 4;  // rows in flight while walking the tail of a longer segment
   const float* grad;
   const float* x;
   const float* sum;
@@ -133,6 +134,7 @@ struct RowSrc {
 #define RM_MAX_PEERS 8
 struct PeerRowSrc {
   static constexpr bool kScalars = true;
+  static constexpr int kTailU = 2;
   const float* G[RM_MAX_PEERS];
   uint32_t rows_per_rank;
   int KP, k;
@@ -160,94 +162,150 @@ struct UpdateSink {
   OptParams o;
 };
 
-template <int LPR, int SEG, int U, class Src>
-__global__ void __launch_bounds__(256) segment_reduce_kernel(
+// Work distribution: a warp owns chunks of 32 consecutive unique rows.  Lane l loads the index chain of row
+// chunk*32 + l (seg_start -> sorted_pos head, uniq_rows) with coalesced loads, software-pipelined two chunks deep
+// (bounds of chunk i+2 and heads of chunk i+1 are requested while the rows of chunk i are in flight), and the row
+// groups (LPR lanes each) pick their segments' indices up by shuffle - so the three dependent latencies of the index
+// chain are off the critical path and cost one load instruction per 32 segments.  A group has UB segments' rows in
+// flight at a time; at step i the groups of a warp work on consecutive unique rows (coalesced output).
+template <int LPR, int UBT, int U, int MINB, class Src>
+__global__ void __launch_bounds__(256, MINB) segment_reduce_kernel(
     const Src src, int k, const int32_t* __restrict__ sorted_pos, const int32_t* __restrict__ seg_start,
     const int32_t* __restrict__ n_unique, float* __restrict__ out_rows, float* __restrict__ out_bias,
     float* __restrict__ out_lin, const UpdateSink sink) {
   constexpr bool FUSED = Src::kScalars;
-  const int lir = threadIdx.x % LPR;
-  const int k4 = k >> 2;
-  const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-  const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / LPR;
+  constexpr int GPW = 32 / LPR;              // row groups per warp
+  constexpr int UB = UBT < LPR ? UBT : LPR;  // segments in flight per group (a group owns LPR segments per chunk)
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int lir = lane % LPR, giw = lane / LPR;
+  const int c = lir;  // column chunk of this lane (k <= 128: exactly one; lane 0 owns chunk 0 and the k=1 sums)
+  const bool col = c < (k >> 2);
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t stride = (((int64_t)gridDim.x * blockDim.x) >> 5) * 32;
   const int32_t NU = *n_unique;
-  for (int64_t u0 = group * SEG; u0 < NU; u0 += n_groups * SEG) {
-    int32_t s[SEG], e[SEG];
-#pragma unroll
-    for (int t = 0; t < SEG; ++t) {
-      const bool live = u0 + t < NU;
-      s[t] = live ? seg_start[u0 + t] : 0;
-      e[t] = live ? seg_start[u0 + t + 1] : 0;
+  int64_t ub = warp * 32;
+  if (ub >= NU) return;  // warp-uniform
+  const bool upd = sink.table != nullptr;
+
+  int32_t sA = 0, sB = 0, nA = 0, nB = 0;
+  uint32_t hp = 0;
+  int64_t ur = 0;
+  {
+    const int64_t u = ub + lane;
+    if (u < NU) {
+      sA = seg_start[u];
+      sB = seg_start[u + 1];
+      hp = (uint32_t)sorted_pos[sA];
+      if (upd) ur = sink.uniq_rows[u];
     }
-    int64_t urow[SEG];
-    if (sink.table) {
-#pragma unroll
-      for (int t = 0; t < SEG; ++t) urow[t] = u0 + t < NU ? sink.uniq_rows[u0 + t] : 0;
+    const int64_t un = u + stride;
+    if (un < NU) {
+      nA = seg_start[un];
+      nB = seg_start[un + 1];
     }
-    for (int c = lir; c < k4; c += LPR) {  // lane 0 always owns column chunk 0, so it also carries the k=1 sums
-      uint32_t p0[SEG];
-#pragma unroll
-      for (int t = 0; t < SEG; ++t) p0[t] = s[t] < e[t] ? (uint32_t)sorted_pos[s[t]] : 0u;
-      float4 tv[SEG];  // the parameter rows to update, loaded beside the first gradient rows
-      if (sink.table) {
-#pragma unroll
-        for (int t = 0; t < SEG; ++t)
-          tv[t] = u0 + t < NU ? ld4(sink.table + urow[t] * k + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (; ub < NU; ub += stride) {
+    // ---- prefetch: heads of the next chunk (its bounds arrived during the previous chunk), bounds of the one after
+    uint32_t nhp = 0;
+    int64_t nur = 0;
+    int32_t n2A = 0, n2B = 0;
+    {
+      const int64_t un = ub + stride + lane;
+      if (un < NU) {
+        nhp = (uint32_t)sorted_pos[nA];
+        if (upd) nur = sink.uniq_rows[un];
       }
-      float4 acc[SEG];
-      float ba[SEG], la[SEG];
-#pragma unroll
-      for (int t = 0; t < SEG; ++t) {
-        acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-        ba[t] = 0.f;
-        la[t] = 0.f;
-        if (s[t] < e[t]) src.load(p0[t], c, acc[t], ba[t], la[t]);
+      const int64_t u2 = un + stride;
+      if (u2 < NU) {
+        n2A = seg_start[u2];
+        n2B = seg_start[u2 + 1];
       }
+    }
+#pragma unroll 1
+    for (int t0 = 0; t0 < LPR; t0 += UB) {
+      int32_t s[UB], e[UB];
+      uint32_t p0[UB];
+      int64_t urow[UB];
+      bool live[UB];
 #pragma unroll
-      for (int t = 0; t < SEG; ++t) {
-        for (int32_t j0 = s[t] + 1; j0 < e[t]; j0 += U) {  // longer segments: U rows in flight, added in order
-          float4 v[U];
-          float gf[U], gl[U];
-#pragma unroll
-          for (int i = 0; i < U; ++i) {
-            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            gf[i] = 0.f;
-            gl[i] = 0.f;
-            if (j0 + i < e[t]) src.load((uint32_t)sorted_pos[j0 + i], c, v[i], gf[i], gl[i]);
-          }
-#pragma unroll
-          for (int i = 0; i < U; ++i) {
-            if (j0 + i < e[t]) {
-              acc[t].x += v[i].x; acc[t].y += v[i].y; acc[t].z += v[i].z; acc[t].w += v[i].w;
-              ba[t] += gf[i];
-              la[t] += gl[i];
-            }
-          }
-        }
+      for (int j = 0; j < UB; ++j) {
+        const int sl = giw + GPW * (t0 + j);  // lane that holds this segment's indices
+        s[j] = __shfl_sync(FULL, sA, sl);
+        e[j] = __shfl_sync(FULL, sB, sl);
+        p0[j] = __shfl_sync(FULL, hp, sl);
+        urow[j] = __shfl_sync(FULL, ur, sl);
+        live[j] = col && (ub + sl < NU);
       }
+      float4 acc[UB], tv[UB];
+      float ba[UB], la[UB], bo[UB], lo[UB];
 #pragma unroll
-      for (int t = 0; t < SEG; ++t) {
-        if (u0 + t < NU) {
-          if (out_rows) st4(out_rows + (u0 + t) * k + 4 * c, acc[t]);
-          if (FUSED && c == 0) {
-            if (out_bias) out_bias[u0 + t] = ba[t];
-            if (out_lin) out_lin[u0 + t] = la[t];
-          }
-          if (sink.table) {
-            float4 pv = tv[t];
-            pv.x = opt_update(pv.x, acc[t].x, sink.o);
-            pv.y = opt_update(pv.y, acc[t].y, sink.o);
-            pv.z = opt_update(pv.z, acc[t].z, sink.o);
-            pv.w = opt_update(pv.w, acc[t].w, sink.o);
-            st4(sink.table + urow[t] * k + 4 * c, pv);
+      for (int j = 0; j < UB; ++j) {
+        acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        tv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ba[j] = la[j] = bo[j] = lo[j] = 0.f;
+        if (live[j]) {
+          src.load(p0[j], c, acc[j], ba[j], la[j]);
+          if (upd) {  // the parameter row to update is loaded beside its first gradient row
+            tv[j] = ld4(sink.table + urow[j] * k + 4 * c);
             if (FUSED && c == 0) {
-              if (sink.bias_table) sink.bias_table[urow[t]] = opt_update(sink.bias_table[urow[t]], ba[t], sink.o);
-              if (sink.lin_table) sink.lin_table[urow[t]] = opt_update(sink.lin_table[urow[t]], la[t], sink.o);
+              if (sink.bias_table) bo[j] = sink.bias_table[urow[j]];
+              if (sink.lin_table) lo[j] = sink.lin_table[urow[j]];
+            }
+          }
+        }
+      }
+      // longer segments: U rows in flight, added in ascending position order
+#pragma unroll
+      for (int j = 0; j < UB; ++j) {
+        if (live[j]) {
+          for (int32_t j0 = s[j] + 1; j0 < e[j]; j0 += U) {
+            float4 v[U];
+            float gf[U], gl[U];
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+              v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              gf[i] = 0.f;
+              gl[i] = 0.f;
+              if (j0 + i < e[j]) src.load((uint32_t)sorted_pos[j0 + i], c, v[i], gf[i], gl[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+              if (j0 + i < e[j]) {
+                acc[j].x += v[i].x; acc[j].y += v[i].y; acc[j].z += v[i].z; acc[j].w += v[i].w;
+                ba[j] += gf[i];
+                la[j] += gl[i];
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < UB; ++j) {
+        if (live[j]) {
+          const int64_t u = ub + giw + GPW * (t0 + j);
+          if (out_rows) st4(out_rows + u * k + 4 * c, acc[j]);
+          if (FUSED && c == 0) {
+            if (out_bias) out_bias[u] = ba[j];
+            if (out_lin) out_lin[u] = la[j];
+          }
+          if (upd) {
+            float4 pv = tv[j];
+            pv.x = opt_update(pv.x, acc[j].x, sink.o);
+            pv.y = opt_update(pv.y, acc[j].y, sink.o);
+            pv.z = opt_update(pv.z, acc[j].z, sink.o);
+            pv.w = opt_update(pv.w, acc[j].w, sink.o);
+            st4(sink.table + urow[j] * k + 4 * c, pv);
+            if (FUSED && c == 0) {
+              if (sink.bias_table) sink.bias_table[urow[j]] = opt_update(bo[j], ba[j], sink.o);
+              if (sink.lin_table) sink.lin_table[urow[j]] = opt_update(lo[j], la[j], sink.o);
             }
           }
         }
       }
     }
+    sA = nA; sB = nB; hp = nhp; ur = nur;
+    nA = n2A; nB = n2B;
   }
 }
 
@@ -283,13 +341,15 @@ static int launch_segment_reduce(const Src& src, int k, int64_t N, const int32_t
                                  const int32_t* n_unique, float* out_rows, float* out_bias, float* out_lin,
                                  const UpdateSink& sink, int dflt_variant, cudaStream_t st) {
   const int variant = tune_variant("RM_TUNE_SEGRED", dflt_variant);  // measured best on B200 (profiles/r1_kbench.json)
-#define RM_SRK(SEG)                                                                                               \
-  segment_reduce_kernel<LPR, SEG, 4, Src><<<grid_for(N, (256 / LPR) * SEG, 8), 256, 0, st>>>(                      \
-      src, k, sorted_pos, seg_start, n_unique, out_rows, out_bias, out_lin, sink)
-  // n_unique <= N lives on the device: the grid is sized for the worst case
-  if (variant == 1) RM_SRK(1);
-  else if (variant == 2) RM_SRK(2);
-  else RM_SRK(4);
+  // n_unique <= N lives on the device: the grid is sized for the worst case (a CTA iteration = 8 warps x 32 rows)
+  const int grid = grid_for(N, 256, 8);
+#define RM_SRK(UB, MINB)                                                                                         \
+  segment_reduce_kernel<LPR, UB, Src::kTailU, MINB, Src><<<grid, 256, 0, st>>>(src, k, sorted_pos, seg_start, n_unique, \
+                                                                     out_rows, out_bias, out_lin, sink)
+  if (variant == 1) RM_SRK(1, 4);
+  else if (variant == 2) RM_SRK(2, 4);
+  else if (variant == 3) RM_SRK(2, 3);
+  else RM_SRK(4, 2);
 #undef RM_SRK
   RM_LAUNCH_CHECK();
   return 0;
@@ -475,10 +535,10 @@ int rm_segment_reduce(const float* grad, int64_t ld, int32_t m, int32_t k, int64
   RM_CHECK_ARG(N >= 0 && m > 0 && k > 0 && ld >= (int64_t)m * k, "bad shape");
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool vec = (k % 4 == 0) && (ld % 4 == 0) && aligned16(grad) && aligned16(out_rows);
+  const bool vec = (k % 4 == 0) && (k <= 128) && (ld % 4 == 0) && aligned16(grad) && aligned16(out_rows);
   if (vec) {
     const RowSrc<false> src{grad, nullptr, nullptr, nullptr, nullptr, ld, (uint32_t)m, k};
-    return dispatch_segment_reduce(src, k, N, sorted_pos, seg_start, n_unique, out_rows, nullptr, nullptr, UpdateSink{}, 4,
+    return dispatch_segment_reduce(src, k, N, sorted_pos, seg_start, n_unique, out_rows, nullptr, nullptr, UpdateSink{}, 2,
                                    st);
   }
   segment_reduce_scalar_kernel<<<grid_for(N * k, 256, 8), 256, 0, st>>>(grad, ld, (uint32_t)m, (uint32_t)k, sorted_pos,
@@ -495,13 +555,13 @@ static int emb_fm_bwd_impl(const float* dx, const float* x, int64_t ld, const fl
   RM_CHECK_ARG(sorted_pos && seg_start && n_unique, "null pointer");
   RM_CHECK_ARG(N >= 0 && m > 0 && k > 0 && ld >= (int64_t)m * k, "bad shape");
   RM_CHECK_ARG(!g_fm || (x && sum), "g_fm needs x and sum");
-  RM_UNSUPPORTED((k % 4 == 0) && (ld % 4 == 0) && (!dx || aligned16(dx)) && (!x || aligned16(x)) &&
+  RM_UNSUPPORTED((k % 4 == 0) && (k <= 128) && (ld % 4 == 0) && (!dx || aligned16(dx)) && (!x || aligned16(x)) &&
                      (!sum || aligned16(sum)) && (!out_rows || aligned16(out_rows)) &&
                      (!sink.table || aligned16(sink.table)),
-                 "fused embedding backward needs k % 4 == 0 and 16-byte aligned rows");
+                 "fused embedding backward needs k % 4 == 0, k <= 128 and 16-byte aligned rows");
   if (N == 0) return 0;
   const RowSrc<true> src{dx, x, sum, g_fm, g_lin, ld, (uint32_t)m, k};
-  return dispatch_segment_reduce(src, k, N, sorted_pos, seg_start, n_unique, out_rows, out_bias, out_lin, sink, 2,
+  return dispatch_segment_reduce(src, k, N, sorted_pos, seg_start, n_unique, out_rows, out_bias, out_lin, sink, 1,
                                  (cudaStream_t)stream);
 }
 
@@ -581,7 +641,7 @@ static int segment_reduce_p2p_impl(const float* const* G, int32_t W, int64_t row
   using namespace rm;
   RM_CHECK_ARG(G && sorted_gpos && seg_start && n_unique, "null pointer");
   RM_CHECK_ARG(W >= 1 && W <= RM_MAX_PEERS && rows_per_rank > 0 && k > 0 && KP >= k + 4 && N_cap >= 0, "bad shape");
-  RM_UNSUPPORTED(k % 4 == 0 && KP % 4 == 0 && (!out_rows || aligned16(out_rows)) &&
+  RM_UNSUPPORTED(k % 4 == 0 && k <= 128 && KP % 4 == 0 && (!out_rows || aligned16(out_rows)) &&
                      (!sink.table || aligned16(sink.table)),
                  "peer segment reduce needs k % 4 == 0 and 16-byte aligned rows");
   RM_UNSUPPORTED(rows_per_rank * W < ((int64_t)1 << 31), "W * rows_per_rank must be < 2^31");
@@ -594,7 +654,7 @@ static int segment_reduce_p2p_impl(const float* const* G, int32_t W, int64_t row
   src.rows_per_rank = (uint32_t)rows_per_rank;
   src.KP = KP;
   src.k = k;
-  return dispatch_segment_reduce(src, k, N_cap, sorted_gpos, seg_start, n_unique, out_rows, out_bias, out_lin, sink, 2,
+  return dispatch_segment_reduce(src, k, N_cap, sorted_gpos, seg_start, n_unique, out_rows, out_bias, out_lin, sink, 1,
                                  (cudaStream_t)stream);
 }
 

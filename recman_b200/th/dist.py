@@ -29,6 +29,7 @@ capturable; NVLink traffic is exactly one row per remote id each way.
 
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Callable, List, Optional, Sequence
 
@@ -65,6 +66,10 @@ class PeerMemory:
         for v in shape:
             n *= int(v)
         nbytes = max(n * torch.empty((), dtype=dtype).element_size(), 256)
+        # whole 2 MiB pages: an allocation with a ragged tail is imported by the peers with small pages, and random
+        # NVLink reads over a multi-GB small-page mapping fall off a TLB cliff (scripts/p2p_bench3.py)
+        gran = int(os.environ.get("RM_P2P_ALLOC_GRAN", str(2 << 20)))
+        nbytes = (nbytes + gran - 1) // gran * gran
         ptr = ctypes.c_void_p()
         handle = (ctypes.c_uint8 * 64)()
         _C.check(_C.lib.rm_p2p_alloc(nbytes, ctypes.byref(ptr), handle), "rm_p2p_alloc")

@@ -8,7 +8,7 @@ dev = "cuda"
 B, m, k, nd = 65536, 26, int(os.environ.get("KB_K", "64")), 13
 rows = int(os.environ.get("KB_ROWS", "1000000"))
 torch.manual_seed(0)
-table = torch.randn(m * rows, k, device=dev) * 0.01
+table = torch.empty(m * rows, k, device=dev).normal_(0.0, 0.01)
 bias_t = torch.zeros(m * rows, device=dev); lin_t = torch.zeros(m * rows, device=dev)
 offs = (torch.arange(m + 1, device=dev) * rows).long()
 ids_pool = [torch.randint(0, rows, (B, m), device=dev) for _ in range(4)]
@@ -40,13 +40,16 @@ x, fm, lin, S = ops.gather_fm_fwd(table, bias_t, lin_t, offs, ids_pool[0], dense
 ld = x.shape[1]
 dx = torch.randn(B, ld, device=dev); g_fm = torch.randn(B, device=dev); g_lin = torch.randn(B, device=dev)
 bwd_bytes = B * m * (4 + 8 * k) + B * (4 * k + 8) + nu * (4 * k + 8)
-for var in os.environ.get("KB_SEG_VARIANTS", "1,2,4").split(","):
+for var in os.environ.get("KB_SEG_VARIANTS", "1,2,3,4").split(","):
     os.environ["RM_TUNE_SEGRED"] = var
     t = timeit(lambda i: ops.emb_fm_bwd(dx, x, ld, S, g_fm, g_lin, plans[i % 4], k, True, True, True))
     res[f"emb_fm_bwd seg{var}"] = (round(t, 4), round(bwd_bytes / t / 1e6, 1))
     grad = dx[:, : m * k].contiguous()
     t = timeit(lambda i: ops.segment_reduce(grad, plans[i % 4], k, ld=m * k))
     res[f"segment_reduce seg{var}"] = (round(t, 4), round((B * m * (4 + 4 * k) + nu * (4 * k + 8)) / t / 1e6, 1))
+    upd_bytes = bwd_bytes - nu * (4 * k + 8) + nu * (8 + 8 * k + 16)  # uniq id + row r/w + bias/lin r/w per unique row
+    t = timeit(lambda i: ops.emb_fm_bwd_update(dx, x, ld, S, g_fm, g_lin, plans[i % 4], k, table, bias_t, lin_t, 0, 1e-3))
+    res[f"emb_fm_bwd_update seg{var}"] = (round(t, 4), round(upd_bytes / t / 1e6, 1))
 rows_out, ob, ol = ops.emb_fm_bwd(dx, x, ld, S, g_fm, g_lin, plans[0], k, True, True, True)
 sg = ops.SparseGrad(plans[0].uniq_rows, rows_out, plans[0].n_unique)
 t = timeit(lambda i: ops.sparse_opt_step(table, sg, 0, 1e-3, 0.0))
