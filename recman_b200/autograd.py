@@ -248,6 +248,8 @@ class FrontEndFunction(Function):
         ctx.total_rows = total_rows
         ctx.fused_opt = fused_opt  # (opt kind, lr): apply the sparse update inside the backward kernel (N1)
         ctx.lin_table = lin_table
+        # K2's plan needs the ids only: build it on the side stream, under the front-end kernel and the MLP forward
+        ctx.plan = ops.segment_plan(ids, offsets, total_rows, side=True) if any(ctx.needs_input_grad) else None
         ctx.save_for_backward(x, S, ids, offsets, dense)
         ctx.set_materialize_grads(False)
         return x, fm.reshape(-1, 1), lin.reshape(-1, 1)
@@ -257,7 +259,9 @@ class FrontEndFunction(Function):
         x, S, ids, offsets, dense = ctx.saved_tensors
         k = ctx.table.shape[1]
         ld = x.shape[1]
-        plan = ops.segment_plan(ids, offsets, ctx.total_rows)
+        plan, ctx.plan = ctx.plan, None
+        if plan is None:
+            plan = ops.segment_plan(ids, offsets, ctx.total_rows)
         if dx is not None and (dx.stride(1) != 1 or dx.stride(0) != ld):
             dx = dx.contiguous()
         g_fm = None if dfm is None else dfm.reshape(-1).contiguous()

@@ -143,14 +143,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cin_fwd_tc_kernel(const TcParam
         if (slot == 0) ok = mbar_wait(empty(s), (((uint32_t)(it / TC_STAGES)) & 1u) ^ 1u) && ok;
         const float v0 = x0r[4 * c + 0] * xkv, v1 = x0r[4 * c + 1] * xkv, v2 = x0r[4 * c + 2] * xkv,
                     v3 = x0r[4 * c + 3] * xkv;
-        const uint32_t h0 = f32_to_tf32(v0), h1 = f32_to_tf32(v1), h2 = f32_to_tf32(v2), h3 = f32_to_tf32(v3);
+        uint4 hi, lo;
+        split_trunc4(make_float4(v0, v1, v2, v3), hi, lo);
         uint8_t* arow = gen_base + (size_t)s * stage_bytes + row_off;
-        *reinterpret_cast<uint4*>(arow + ((((uint32_t)slot) ^ rx) << 4)) = make_uint4(h0, h1, h2, h3);
-        if (SPLIT3) {
-          const uint4 lo = make_uint4(__float_as_uint(v0 - __uint_as_float(h0)), __float_as_uint(v1 - __uint_as_float(h1)),
-                                      __float_as_uint(v2 - __uint_as_float(h2)), __float_as_uint(v3 - __uint_as_float(h3)));
-          *reinterpret_cast<uint4*>(arow + ((((uint32_t)(slot + 4)) ^ rx) << 4)) = lo;
-        }
+        *reinterpret_cast<uint4*>(arow + ((((uint32_t)slot) ^ rx) << 4)) = hi;
+        if (SPLIT3) *reinterpret_cast<uint4*>(arow + ((((uint32_t)(slot + 4)) ^ rx) << 4)) = lo;
         if (slot == CPS - 1) {
           fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
           mbar_arrive(full_a(s));

@@ -19,7 +19,7 @@ namespace rm {
 
 constexpr int TB_STAGES = 3;
 constexpr int TB_THREADS = 320;   // kernel A: 8 producer/epilogue warps + MMA warp + W loader warp
-constexpr int TB_THREADS_B = 288;  // kernel B: 8 producer/epilogue warps + MMA warp
+constexpr int TB_THREADS_B = 544;  // kernel B: 8 A-producer/epilogue warps + 8 B-producer warps + MMA warp
 constexpr int TB_SLAB_DEFAULT = 512;  // rows of (b,d) accumulated in TMEM per CTA in kernel B (RM_TUNE_CIN_SLAB)
 
 // ------------------------------------------------------------------------------------------------ pack W'' (kernel A)
@@ -152,12 +152,10 @@ __global__ void __launch_bounds__(TB_THREADS, 1) cin_bwd_dx_tc_kernel(const TbPa
         uint8_t* arow = gen_base + (size_t)s * stage_bytes + row_off;
 #pragma unroll
         for (int c = 0; c < KS / 4; ++c) {
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) split_tf32(v[4 * c + e], hi[e], lo[e]);
-          *reinterpret_cast<uint4*>(arow + ((((uint32_t)c) ^ rx) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          if (SPLIT3)
-            *reinterpret_cast<uint4*>(arow + ((((uint32_t)(c + 4)) ^ rx) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          uint4 hi, lo;
+          split_trunc4(make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]), hi, lo);
+          *reinterpret_cast<uint4*>(arow + ((((uint32_t)c) ^ rx) << 4)) = hi;
+          if (SPLIT3) *reinterpret_cast<uint4*>(arow + ((((uint32_t)(c + 4)) ^ rx) << 4)) = lo;
         }
         fence_proxy_async_smem();
         mbar_arrive(full_a(s));
@@ -257,9 +255,15 @@ __global__ void __launch_bounds__(TB_THREADS, 1) cin_bwd_dx_tc_kernel(const TbPa
 
 // ------------------------------------------------------------------------------------------------ kernel B
 // CTA (ktile, slab): accumulators [256 k'' rows x NPAD] over the slab's rows; needs D % 4 == 0.
+// Warp roles: 0-7 build the A tile (thread t owns row k'' = k_lo + t: products x0[b,p,d]*xk[b,q,d] from a staged
+// slice), 8-15 build the B tile (thread t owns row n = t - 256 of dF), 16 issues the MMAs.  The two producer groups
+// run concurrently, and neither has a division or a 64-bit multiply in its stage loop: (sample, d) positions advance
+// incrementally.  On-the-fly operands are split by truncation (the tensor core drops the low 13 mantissa bits of a
+// tf32 operand anyway): hi = raw bits, lo = v - trunc(v), exact in fp32.
 template <bool SPLIT3>
 __global__ void __launch_bounds__(TB_THREADS_B, 1) cin_bwd_dw_tc_kernel(const TbParams P) {
   constexpr int KS = SPLIT3 ? 16 : 32;  // (b,d) rows per stage
+  constexpr int KC = KS / 4;            // float4 chunks per row and stage
   constexpr int XS = KS + 4;            // padded row stride of the staged x0 / xk slices (bank-conflict free LDS.128)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -284,14 +288,14 @@ __global__ void __launch_bounds__(TB_THREADS_B, 1) cin_bwd_dw_tc_kernel(const Tb
 
   if (tid == 0) {
     for (int s = 0; s < TB_STAGES; ++s) {
-      mbar_init(full(s), 256);
+      mbar_init(full(s), 512);
       mbar_init(empty(s), 1);
     }
     mbar_init(accum_full, 1);
     fence_barrier_init();
   }
   __syncthreads();
-  if (warp == 8) tmem_alloc512(tmem_slot);
+  if (warp == 16) tmem_alloc512(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -301,98 +305,83 @@ __global__ void __launch_bounds__(TB_THREADS_B, 1) cin_bwd_dw_tc_kernel(const Tb
   const int64_t r_begin = (int64_t)slab * P.slab_rows;
   const int64_t r_end = min(P.Mrows, r_begin + P.slab_rows);
   const int n_stages = (int)((r_end - r_begin + KS - 1) / KS);
+  const uint32_t Du = (uint32_t)P.D;
+  const uint32_t rb = (uint32_t)r_begin, re = (uint32_t)r_end;
 
   if (warp < 8) {
-    // this thread's A row: k'' = k_lo + tid -> (q, p); its B row: n = tid
+    // =========================== A producers: row k'' = k_lo + tid -> (q, p) ===========================
     const int kk = k_lo + tid;
     const int q = kk / P.MPAD, p = kk - q * P.MPAD;
     const bool a_ok = q < P.H && p < P.m;
     const int ql = q - q_lo;
-    const bool b_ok = tid < P.N;
-    const bool b_row = tid < P.NPAD;
     const uint32_t row_off = (uint32_t)tid * 128u;
     const uint32_t rx = (uint32_t)(tid & 7);
-    const int n_chunks = xrows * (KS / 4);  // float4 chunks of the staged slices per stage (<= 3 per thread)
-    // Software pipeline: the global loads of stage st+1 (x0 / xk slices and this thread's dF row) are issued before
-    // the products of stage st are formed, so their latency hides behind the smem work instead of stalling it.
-    float4 stg[3], df[KS / 4];
-    auto issue_loads = [&](int st) {
-      const int64_t r0 = r_begin + (int64_t)st * KS;
+    const int n_chunks = xrows * KC;  // float4 chunks of the staged slices per stage (<= 3 per thread)
+    // per-thread staging slots: chunk i = tid + u*256 -> (row, c4) is the same every stage; only (sample, d) moves
+    const float* sp[3];   // nullptr = zero row
+    int64_t sbs[3];       // batch stride of the slot's source
+    int64_t sob[3];       // sample * batch stride
+    uint32_t sd[3], sr[3];
+    int sdst[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int i = tid + u * 256;
+      sp[u] = nullptr;
+      sbs[u] = 0; sob[u] = 0; sd[u] = 0; sr[u] = re; sdst[u] = 0;
+      if (i < n_chunks) {
+        const int row = i / KC, c4 = i - row * KC;
+        sdst[u] = row * XS + 4 * c4;
+        if (row < P.MPAD) {
+          if (row < P.m) { sp[u] = P.x0 + (int64_t)row * P.D; sbs[u] = P.bs0; }
+        } else {
+          sp[u] = P.xk + (int64_t)(q_lo + row - P.MPAD) * P.D; sbs[u] = P.bsk;
+        }
+        sr[u] = rb + 4u * c4;
+        const uint32_t b = sr[u] / Du;
+        sd[u] = sr[u] - b * Du;
+        sob[u] = (int64_t)b * sbs[u];
+      }
+    }
+    const bool slot_live[3] = {tid < n_chunks, tid + 256 < n_chunks, tid + 512 < n_chunks};
+    float4 stg[3];
+    auto issue_loads = [&]() {  // loads of the next stage's slices, then advance the slots by KS rows
 #pragma unroll
       for (int u = 0; u < 3; ++u) {
-        const int i = tid + u * 256;
         stg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < n_chunks) {
-          const int row = i / (KS / 4), c4 = i - row * (KS / 4);
-          const int64_t r = r0 + 4 * c4;
-          if (r < r_end) {
-            const int64_t b = r / P.D;
-            const int d = (int)(r - b * P.D);
-            if (row < P.MPAD) {
-              if (row < P.m) stg[u] = ld4(P.x0 + b * P.bs0 + (int64_t)row * P.D + d);
-            } else {
-              stg[u] = ld4(P.xk + b * P.bsk + (int64_t)(q_lo + row - P.MPAD) * P.D + d);
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int c4 = 0; c4 < KS / 4; ++c4) {
-        const int64_t r = r0 + 4 * c4;
-        df[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (b_ok && r < r_end) {
-          const int64_t b = r / P.D;
-          const int d = (int)(r - b * P.D);
-          df[c4] = ld4(P.dF + (b * P.N + tid) * (int64_t)P.D + d);
+        if (sp[u] && sr[u] < re) stg[u] = ld4(sp[u] + sob[u] + sd[u]);
+        sr[u] += KS;
+        sd[u] += KS;
+        while (sd[u] >= Du) {
+          sd[u] -= Du;
+          sob[u] += sbs[u];
         }
       }
     };
-    if (n_stages > 0) issue_loads(0);
+    if (n_stages > 0) issue_loads();
+    const float* xa_src = xs + p * XS;
+    const float* xb_src = xs + (P.MPAD + ql) * XS;
     for (int st = 0; st < n_stages; ++st) {
       const int s = st % TB_STAGES;
-      float* buf = xs + (size_t)(st & 1) * xrows * XS;
-      // ---- stage x0[b, 0..MPAD), xk[b, q_lo..q_hi] for the KS rows of this stage ----
+      const int boff = (st & 1) * xrows * XS;
 #pragma unroll
-      for (int u = 0; u < 3; ++u) {
-        const int i = tid + u * 256;
-        if (i < n_chunks) {
-          const int row = i / (KS / 4), c4 = i - row * (KS / 4);
-          *reinterpret_cast<float4*>(buf + row * XS + 4 * c4) = stg[u];
-        }
-      }
-      float4 dfc[KS / 4];
-#pragma unroll
-      for (int c4 = 0; c4 < KS / 4; ++c4) dfc[c4] = df[c4];
-      named_bar_sync(1, 256);  // staged slices visible to all producer threads
-      if (st + 1 < n_stages) issue_loads(st + 1);
+      for (int u = 0; u < 3; ++u)
+        if (slot_live[u]) *reinterpret_cast<float4*>(xs + boff + sdst[u]) = stg[u];
+      named_bar_sync(1, 256);  // staged slices visible to all A producers
+      if (st + 1 < n_stages) issue_loads();
       ok = mbar_wait(empty(s), (((uint32_t)(st / TB_STAGES)) & 1u) ^ 1u) && ok;
       uint8_t* arow = gen_base + (size_t)s * stage_bytes + row_off;
-      uint8_t* brow = arow + a_bytes;
 #pragma unroll
-      for (int c4 = 0; c4 < KS / 4; ++c4) {
+      for (int c4 = 0; c4 < KC; ++c4) {
         float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         if (a_ok) {
-          const float4 xa = *reinterpret_cast<const float4*>(buf + p * XS + 4 * c4);
-          const float4 xb = *reinterpret_cast<const float4*>(buf + (P.MPAD + ql) * XS + 4 * c4);
+          const float4 xa = *reinterpret_cast<const float4*>(xa_src + boff + 4 * c4);
+          const float4 xb = *reinterpret_cast<const float4*>(xb_src + boff + 4 * c4);
           z = make_float4(xa.x * xb.x, xa.y * xb.y, xa.z * xb.z, xa.w * xb.w);
         }
-        uint32_t hi[4], lo[4];
-        split_tf32(z.x, hi[0], lo[0]);
-        split_tf32(z.y, hi[1], lo[1]);
-        split_tf32(z.z, hi[2], lo[2]);
-        split_tf32(z.w, hi[3], lo[3]);
-        *reinterpret_cast<uint4*>(arow + ((((uint32_t)c4) ^ rx) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        if (SPLIT3)
-          *reinterpret_cast<uint4*>(arow + ((((uint32_t)(c4 + 4)) ^ rx) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        if (b_row) {
-          split_tf32(dfc[c4].x, hi[0], lo[0]);
-          split_tf32(dfc[c4].y, hi[1], lo[1]);
-          split_tf32(dfc[c4].z, hi[2], lo[2]);
-          split_tf32(dfc[c4].w, hi[3], lo[3]);
-          *reinterpret_cast<uint4*>(brow + ((((uint32_t)c4) ^ rx) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          if (SPLIT3)
-            *reinterpret_cast<uint4*>(brow + ((((uint32_t)(c4 + 4)) ^ rx) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
+        uint4 hi, lo;
+        split_trunc4(z, hi, lo);
+        *reinterpret_cast<uint4*>(arow + ((((uint32_t)c4) ^ rx) << 4)) = hi;
+        if (SPLIT3) *reinterpret_cast<uint4*>(arow + ((((uint32_t)(c4 + 4)) ^ rx) << 4)) = lo;
       }
       fence_proxy_async_smem();
       mbar_arrive(full(s));
@@ -412,6 +401,56 @@ __global__ void __launch_bounds__(TB_THREADS_B, 1) cin_bwd_dw_tc_kernel(const Tb
       for (int j = 0; j < 16; j += 4)
         *reinterpret_cast<uint4*>(dst + col0 + j) = make_uint4(a[j], a[j + 1], a[j + 2], a[j + 3]);
     }
+  } else if (warp < 16) {
+    // =========================== B producers: row n = tid - 256 of dF ===========================
+    const int n = tid - 256;
+    const bool b_ok = n < P.N;
+    const bool b_row = n < P.NPAD;
+    const uint32_t row_off = (uint32_t)n * 128u;
+    const uint32_t rx = (uint32_t)(n & 7);
+    const int64_t ND = (int64_t)P.N * P.D;
+    uint32_t r = rb;
+    uint32_t d = rb % Du;
+    const float* dfp = P.dF + ((int64_t)(rb / Du) * P.N + (b_ok ? n : 0)) * P.D;  // (sample, n, 0)
+    float4 df[2][KC];
+    auto issue_loads = [&](float4 (&dst)[KC]) {
+#pragma unroll
+      for (int c4 = 0; c4 < KC; ++c4) {
+        dst[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b_ok && r < re) dst[c4] = ld4(dfp + d);
+        r += 4;
+        d += 4;
+        if (d >= Du) {  // D % 4 == 0: a chunk never straddles two samples
+          d -= Du;
+          dfp += ND;
+        }
+      }
+    };
+    auto stage = [&](int st, float4 (&cur)[KC], float4 (&nxt)[KC]) {
+      const int s = st % TB_STAGES;
+      if (st + 1 < n_stages) issue_loads(nxt);
+      ok = mbar_wait(empty(s), (((uint32_t)(st / TB_STAGES)) & 1u) ^ 1u) && ok;
+      if (b_row) {
+        uint8_t* brow = gen_base + (size_t)s * stage_bytes + a_bytes + row_off;
+#pragma unroll
+        for (int c4 = 0; c4 < KC; ++c4) {
+          uint4 hi, lo;
+          split_trunc4(cur[c4], hi, lo);
+          *reinterpret_cast<uint4*>(brow + ((((uint32_t)c4) ^ rx) << 4)) = hi;
+          if (SPLIT3) *reinterpret_cast<uint4*>(brow + ((((uint32_t)(c4 + 4)) ^ rx) << 4)) = lo;
+        }
+        fence_proxy_async_smem();
+      }
+      mbar_arrive(full(s));
+    };
+    if (n_stages > 0) issue_loads(df[0]);
+    int st = 0;
+#pragma unroll 1
+    for (; st + 1 < n_stages; st += 2) {  // unrolled by two: the prefetch registers alternate without moves
+      stage(st, df[0], df[1]);
+      stage(st + 1, df[1], df[0]);
+    }
+    if (st < n_stages) stage(st, df[0], df[1]);
   } else {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(128, P.NPAD);
@@ -444,7 +483,7 @@ __global__ void __launch_bounds__(TB_THREADS_B, 1) cin_bwd_dw_tc_kernel(const Tb
   if (!ok && P.status) atomicOr(P.status, 2);
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 16) {
     tc_fence_after();
     tmem_free512(tmem_base);
   }
@@ -539,6 +578,7 @@ int cin_bwd_tc(const float* x0, int64_t bs0, const float* xk, int64_t bsk, const
     return RM_E_WORKSPACE;
   }
   RM_UNSUPPORTED(bs0 % 4 == 0 && bsk % 4 == 0 && aligned16(x0) && aligned16(xk), "tensor-core backward needs 16-byte aligned rows");
+  RM_UNSUPPORTED(B * (int64_t)D < ((int64_t)1 << 31), "tensor-core backward needs B*D < 2^31 (32-bit row indices)");
   char* ws = (char*)workspace;
   int32_t* status = (int32_t*)(ws + L.off_status);
   float* dF = (float*)(ws + L.off_dF);

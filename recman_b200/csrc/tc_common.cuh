@@ -161,4 +161,15 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(v - __uint_as_float(hi));
 }
 
+// Split of an operand that is produced on the fly, by truncation: the tensor core ignores the low 13 mantissa bits of
+// a tf32 operand, so "hi" is the raw fp32 word and lo = v - trunc(v) is exact in fp32 (2 instructions per value;
+// cvt.rna.tf32 is emulated with 4 on sm_100).  Pre-packed operands (W) keep the round-to-nearest split.
+__device__ __forceinline__ void split_trunc4(const float4 v, uint4& hi, uint4& lo) {
+  hi = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+  lo.x = __float_as_uint(v.x - __uint_as_float(hi.x & 0xffffe000u));
+  lo.y = __float_as_uint(v.y - __uint_as_float(hi.y & 0xffffe000u));
+  lo.z = __float_as_uint(v.z - __uint_as_float(hi.z & 0xffffe000u));
+  lo.w = __float_as_uint(v.w - __uint_as_float(hi.w & 0xffffe000u));
+}
+
 }  // namespace rm

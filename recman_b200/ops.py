@@ -176,12 +176,43 @@ class SegmentPlan:
     uniq_rows: torch.Tensor  # int64 [N]
     n_unique: torch.Tensor  # int32 [1] (device)
     workspace: torch.Tensor
+    ready: Optional["torch.cuda.Event"] = None  # set when the plan was built on the side stream
 
     def num_unique(self) -> int:
+        self.wait()
         return int(self.n_unique.item())  # host sync: tests / densify only
 
+    def wait(self) -> None:
+        """Make the current stream wait for a plan that was built on the side stream (no-op otherwise)."""
+        if self.ready is not None:
+            torch.cuda.current_stream().wait_event(self.ready)
+            self.ready = None
 
-def segment_plan(ids, table_offsets, total_rows) -> SegmentPlan:
+
+_side_streams = {}
+
+
+def _launch_maybe_side(side: bool, launch):
+    """Run ``launch()`` (kernel launches only, every buffer already allocated) on the current stream, or - the plan
+    depends on the ids alone - on a side stream forked from it, so that it overlaps the forward.  Returns the event to
+    wait for, or None."""
+    if not side:
+        launch()
+        return None
+    cur = torch.cuda.current_stream()
+    key = (cur.device.index, cur.cuda_stream)
+    st = _side_streams.get(key)
+    if st is None:
+        st = _side_streams[key] = torch.cuda.Stream(device=cur.device)
+    st.wait_stream(cur)
+    with torch.cuda.stream(st):
+        launch()
+        ev = torch.cuda.Event()
+        ev.record(st)
+    return ev
+
+
+def segment_plan(ids, table_offsets, total_rows, side: bool = False) -> SegmentPlan:
     _dev_check(ids)
     assert ids.dtype == torch.int64 and ids.is_contiguous()
     if ids.dim() == 2:
@@ -196,11 +227,11 @@ def segment_plan(ids, table_offsets, total_rows) -> SegmentPlan:
     seg_start = torch.empty(N + 1, dtype=torch.int32, device=dev)
     uniq_rows = torch.empty(max(N, 1), dtype=torch.int64, device=dev)
     n_unique = torch.empty(1, dtype=torch.int32, device=dev)
-    _C.call(
+    ev = _launch_maybe_side(side, lambda: _C.call(
         "rm_segment_plan", _p(ids), _p(table_offsets), N, m, int(total_rows), _p(ws), ws_bytes, _p(sorted_pos),
         _p(seg_start), _p(uniq_rows), _p(n_unique), _stream(),
-    )
-    return SegmentPlan(N, m, sorted_pos, seg_start, uniq_rows, n_unique, ws)
+    ))
+    return SegmentPlan(N, m, sorted_pos, seg_start, uniq_rows, n_unique, ws, ev)
 
 
 def segment_reduce(grad, plan: SegmentPlan, k: int, ld: Optional[int] = None, out_rows=None):
@@ -213,6 +244,7 @@ def segment_reduce(grad, plan: SegmentPlan, k: int, ld: Optional[int] = None, ou
         ld = plan.m * k
     if out_rows is None:
         out_rows = torch.empty(max(plan.N, 1), k, dtype=torch.float32, device=grad.device)
+    plan.wait()
     _C.call(
         "rm_segment_reduce", _p(grad), ld, plan.m, k, plan.N, _p(plan.sorted_pos), _p(plan.seg_start),
         _p(plan.n_unique), _p(out_rows), _stream(),
@@ -226,6 +258,7 @@ def emb_fm_bwd(dx, x, ld, S, g_fm, g_lin, plan: SegmentPlan, k, want_rows=True, 
     out_rows = torch.empty(n, k, dtype=torch.float32, device=dev) if want_rows else None
     out_bias = torch.empty(n, dtype=torch.float32, device=dev) if want_bias else None
     out_lin = torch.empty(n, dtype=torch.float32, device=dev) if want_lin else None
+    plan.wait()
     _C.call(
         "rm_emb_fm_bwd", _p(dx), _p(x), ld, _p(S), _p(g_fm), _p(g_lin), plan.m, k, plan.N, _p(plan.sorted_pos),
         _p(plan.seg_start), _p(plan.n_unique), _p(out_rows), _p(out_bias), _p(out_lin), _stream(),
@@ -235,6 +268,7 @@ def emb_fm_bwd(dx, x, ld, S, g_fm, g_lin, plan: SegmentPlan, k, want_rows=True, 
 
 def segment_reduce_p2p_update(G_ptrs, rows_per_rank, KP, k, plan: SegmentPlan, table, bias_table, lin_table, opt, lr,
                               l2=0.0):
+    plan.wait()
     _C.call(
         "rm_segment_reduce_p2p_update", _ptr_array(G_ptrs), len(G_ptrs), int(rows_per_rank), KP, k, plan.N,
         _p(plan.sorted_pos), _p(plan.seg_start), _p(plan.uniq_rows), _p(plan.n_unique), _p(table), _p(bias_table),
@@ -244,6 +278,7 @@ def segment_reduce_p2p_update(G_ptrs, rows_per_rank, KP, k, plan: SegmentPlan, t
 
 def emb_fm_bwd_update(dx, x, ld, S, g_fm, g_lin, plan: SegmentPlan, k, table, bias_table, lin_table, opt, lr, l2=0.0):
     """rm_emb_fm_bwd + rm_sparse_opt_step in one pass: the tables are updated in place, nothing is returned."""
+    plan.wait()
     _C.call(
         "rm_emb_fm_bwd_update", _p(dx), _p(x), ld, _p(S), _p(g_fm), _p(g_lin), plan.m, k, plan.N, _p(plan.sorted_pos),
         _p(plan.seg_start), _p(plan.uniq_rows), _p(plan.n_unique), _p(table), _p(bias_table), _p(lin_table), opt,
@@ -450,7 +485,7 @@ def gather_fm_fwd_p2p(tab_ptrs, bias_ptrs, lin_ptrs, k, feat_sizes, local_offs, 
     return x, fm, lin, S
 
 
-def shard_plan(gids, W, rank, feat_sizes, local_offs, total_local, n_cap, status=None):
+def shard_plan(gids, W, rank, feat_sizes, local_offs, total_local, n_cap, status=None, side: bool = False):
     """Owner-side K2 plan over the ids of all ranks (gids [W*b, m]) -> SegmentPlan of global positions + n_own."""
     _dev_check(gids)
     assert gids.dtype == torch.int64 and gids.is_contiguous() and gids.dim() == 2
@@ -464,11 +499,11 @@ def shard_plan(gids, W, rank, feat_sizes, local_offs, total_local, n_cap, status
     uniq_rows = torch.empty(n_cap, dtype=torch.int64, device=dev)
     n_unique = torch.empty(1, dtype=torch.int32, device=dev)
     n_own = torch.empty(1, dtype=torch.int32, device=dev)
-    _C.call(
+    ev = _launch_maybe_side(side, lambda: _C.call(
         "rm_shard_plan", _p(gids), Ntot, m, W, rank, _p(feat_sizes), _p(local_offs), int(total_local), n_cap, _p(ws),
         ws_bytes, _p(sorted_gpos), _p(seg_start), _p(uniq_rows), _p(n_unique), _p(n_own), _p(status), _stream(),
-    )
-    plan = SegmentPlan(n_cap, 1, sorted_gpos, seg_start, uniq_rows, n_unique, ws)
+    ))
+    plan = SegmentPlan(n_cap, 1, sorted_gpos, seg_start, uniq_rows, n_unique, ws, ev)
     plan.n_own = n_own
     return plan
 
@@ -479,6 +514,7 @@ def segment_reduce_p2p(G_ptrs, rows_per_rank, KP, k, plan: SegmentPlan, want_bia
     out_rows = torch.empty(n, k, dtype=torch.float32, device=dev)
     out_bias = torch.empty(n, dtype=torch.float32, device=dev) if want_bias else None
     out_lin = torch.empty(n, dtype=torch.float32, device=dev) if want_lin else None
+    plan.wait()
     _C.call(
         "rm_segment_reduce_p2p", _ptr_array(G_ptrs), len(G_ptrs), int(rows_per_rank), KP, k, plan.N,
         _p(plan.sorted_pos), _p(plan.seg_start), _p(plan.n_unique), _p(out_rows), _p(out_bias), _p(out_lin), _stream(),

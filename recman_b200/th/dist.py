@@ -113,7 +113,7 @@ class ShardPlan:
         self._offs_dev = {}
         self.peer: Optional[PeerMemory] = None  # set by enable_peer_memory(): tables live in cudaIpc-shared memory
         self._bufs = {}
-        self.slack = 0.25  # owner-side plan capacity = (1 + slack) * b*m + 1024 entries
+        self.slack = 0.25  # owner-side plan capacity, see capacity()
 
     # ---- peer-memory mode -------------------------------------------------------------------------------
     def enable_peer_memory(self):
@@ -146,8 +146,13 @@ class ShardPlan:
             self._bufs[key] = torch.zeros(1, dtype=torch.float32, device=device)
         return self._bufs[key]
 
-    def capacity(self, n_local: int) -> int:
-        return min(self.world * n_local, int(n_local * (1.0 + self.slack)) + 1024)
+    def capacity(self, b: int) -> int:
+        """Entries of the owner-side plan for a local batch of ``b`` samples: the largest share any rank owns under
+        uniform ids (tables with fewer rows than ranks load the low ranks), plus ``slack``; exceeding it sets status
+        bit 2 (``DeepModel.check_ids`` raises)."""
+        W, m = self.world, len(self.feat_sizes)
+        share = max(sum(((v - r + W - 1) // W) / v for v in self.feat_sizes if v > 0) for r in range(W))
+        return min(W * b * m, int(W * b * share * (1.0 + self.slack)) + 1024)
 
     def offsets_on(self, device) -> torch.Tensor:
         key = str(device)
@@ -308,6 +313,12 @@ class P2PFrontEndFunction(Function):
             None if lin_table is None else peer.ptrs_of(lin_table), k, plan.feat_sizes_on(dev), plan.offsets_on(dev),
             ids, dense, lin_dense, status=status)
         ctx.plan, ctx.status = plan, status
+        # the owner-side K2 plan needs the gathered ids only: build it on the side stream, under the NVLink-bound
+        # front-end kernel and the MLP forward
+        ctx.sp = None
+        if any(ctx.needs_input_grad):
+            ctx.sp = ops.shard_plan(gids, W, plan.rank, plan.feat_sizes_on(dev), plan.offsets_on(dev),
+                                    plan.total_local, plan.capacity(b), status, side=True)
         ctx.table, ctx.bias_table, ctx.W_lin = table, bias_table, W_lin
         ctx.has_lin = lin_table is not None
         ctx.has_lin_dense = lin_dense is not None and dense is not None and dense.shape[1] > 0
@@ -331,8 +342,10 @@ class P2PFrontEndFunction(Function):
             dx = dx.contiguous()
         g_fm = None if dfm is None else dfm.reshape(-1).contiguous()
         g_lin = None if dlin is None else dlin.reshape(-1).contiguous()
-        sp = ops.shard_plan(gids, plan.world, plan.rank, plan.feat_sizes_on(dev), plan.offsets_on(dev),
-                            plan.total_local, plan.capacity(b * m), ctx.status)
+        sp, ctx.sp = ctx.sp, None
+        if sp is None:
+            sp = ops.shard_plan(gids, plan.world, plan.rank, plan.feat_sizes_on(dev), plan.offsets_on(dev),
+                                plan.total_local, plan.capacity(b), ctx.status)
         G = plan.grad_buffer(b * m, KP)
         ops.pack_grad_rows(dx, x, ld, S, g_fm, g_lin, None, m, k, KP, out=G, n=b * m)
         dist.all_reduce(plan.flag(dev), group=plan.group)  # every rank's G is complete
