@@ -220,6 +220,10 @@ int rm_sparse_opt_step(float* table, int32_t k, const int64_t* uniq_rows, const 
                        void* stream);
 int rm_dense_opt_step(float* p, const float* g, int64_t n, int32_t opt, float lr, float l2,
                       void* stream);
+/* The same update for `count` tensors in one launch (per 96 tensors): ps / gs / ns are HOST arrays of device
+ * pointers and element counts; bit-identical to `count` calls of rm_dense_opt_step. */
+int rm_dense_opt_step_multi(float* const* ps, const float* const* gs, const int64_t* ns, int32_t count,
+                            int32_t opt, float lr, float l2, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * (e) multi-GPU: row-sharded tables (row r of a table lives on rank r mod W at

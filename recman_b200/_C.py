@@ -95,6 +95,7 @@ _SIGS = {
     ),
     "rm_sparse_opt_step": (ctypes.c_int, [P, c_int32, P, P, P, c_int64, c_int32, c_float, c_float, P]),
     "rm_dense_opt_step": (ctypes.c_int, [P, P, c_int64, c_int32, c_float, c_float, P]),
+    "rm_dense_opt_step_multi": (ctypes.c_int, [P, P, P, c_int32, c_int32, c_float, c_float, P]),
 }
 
 EXPORTS = tuple(_SIGS)

@@ -531,7 +531,22 @@ static TbLayout tb_layout(int64_t B, int m, int H, int D, int N, int precision) 
   L.n_ktiles = (kpp + 255) / 256;
   L.KPADT = L.n_ktiles * 256;
   const int64_t Mrows = B * (int64_t)D;
-  L.slab_rows = tune_variant("RM_TUNE_CIN_SLAB", TB_SLAB_DEFAULT) / 32 * 32;
+  // slab size: 384..640 rows (the TMEM accumulation truncates, so slabs stay short), chosen so that the grid
+  // n_ktiles x slabs fills whole waves of 148 CTAs (1 CTA / SM) and the per-CTA prologue/epilogue is amortised
+  L.slab_rows = tune_variant("RM_TUNE_CIN_SLAB", 0) / 32 * 32;
+  if (L.slab_rows <= 0) {
+    double best = -1.0;
+    for (int cand = 384; cand <= 640; cand += 32) {
+      const int64_t slabs = (Mrows + cand - 1) / cand;
+      const int64_t total = slabs * L.n_ktiles;
+      const int64_t waves = (total + RM_NUM_SMS - 1) / RM_NUM_SMS;
+      const double score = (double)total / (double)(waves * RM_NUM_SMS) * cand / (cand + 96.0);
+      if (score > best) {
+        best = score;
+        L.slab_rows = cand;
+      }
+    }
+  }
   if (L.slab_rows < 32) L.slab_rows = 32;
   L.slabs = (int)((Mrows + L.slab_rows - 1) / L.slab_rows);
   if (L.slabs < 1) L.slabs = 1;

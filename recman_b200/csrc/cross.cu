@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(256) cross_bwd_reduce_kernel(const float* __re
   }
 }
 
-// Ordered final pass over the chunk partials + closed-form terms.
+// Ordered final pass over the chunk partials + closed-form terms: one thread per (layer l, column c), so the nblk-long
+// ordered sums run in parallel over (L+1)*d threads instead of serially per column.
 __global__ void __launch_bounds__(256) cross_bwd_final_kernel(const float* __restrict__ P, const float* __restrict__ Tp,
                                                               int nblk, const float* __restrict__ w,
                                                               const float* __restrict__ bias,
@@ -193,25 +194,23 @@ __global__ void __launch_bounds__(256) cross_bwd_final_kernel(const float* __res
   }
   __syncthreads();
   const float G = T[L];
-  if (blockIdx.x == 0 && threadIdx.x == 0 && dw0_out) dw0_out[0] = G;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < d; c += gridDim.x * blockDim.x) {
-    // db_l = w_out*G + sum_{j>l} w_j*T_j  (walk l downwards), dw_l = P_l + cb_l*T_l (cb_l = sum_{j<l} b_j)
-    float tail = __ldg(w_out + c) * G;
-    for (int l = L - 1; l >= 0; --l) {
-      if (db) db[(int64_t)l * d + c] = tail;
-      tail += __ldg(w + (int64_t)l * d + c) * T[l];
+  const int l = blockIdx.y;
+  if (blockIdx.x == 0 && l == 0 && threadIdx.x == 0 && dw0_out) dw0_out[0] = G;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  float p = 0.f;
+  for (int k = 0; k < nblk; ++k) p += P[((int64_t)k * L1 + l) * d + c];
+  float cb = 0.f;  // cb_l = sum_{j<l} b_j
+  for (int j = 0; j < l; ++j) cb += __ldg(bias + (int64_t)j * d + c);
+  if (l < L) {
+    if (dw) dw[(int64_t)l * d + c] = p + cb * T[l];
+    if (db) {  // db_l = w_out*G + sum_{j>l} w_j*T_j, summed from j = L-1 downwards
+      float tail = __ldg(w_out + c) * G;
+      for (int j = L - 1; j > l; --j) tail += __ldg(w + (int64_t)j * d + c) * T[j];
+      db[(int64_t)l * d + c] = tail;
     }
-    float cb = 0.f;
-    for (int l = 0; l <= L; ++l) {
-      float p = 0.f;
-      for (int k = 0; k < nblk; ++k) p += P[((int64_t)k * L1 + l) * d + c];
-      if (l < L) {
-        if (dw) dw[(int64_t)l * d + c] = p + cb * T[l];
-        cb += __ldg(bias + (int64_t)l * d + c);
-      } else if (dw_out) {
-        dw_out[c] = p + cb * G;
-      }
-    }
+  } else if (dw_out) {
+    dw_out[c] = p + cb * G;
   }
 }
 
@@ -228,7 +227,7 @@ struct CrossWs {
 static CrossWs cross_layout(int64_t B, int d, int L, void* base) {
   CrossWs w;
   const int L1 = L + 1;
-  int64_t nblk = ceil_div(B, 16);
+  int64_t nblk = ceil_div(B, 64);  // >= 64 samples per chunk: the ordered final sums stay short
   if (nblk > 2 * RM_NUM_SMS) nblk = 2 * RM_NUM_SMS;
   if (nblk < 1) nblk = 1;
   w.chunk = ceil_div(B, nblk);
@@ -325,8 +324,8 @@ int rm_cross_bwd(const float* x, int64_t ld, const float* w, const float* b, con
     RM_LAUNCH_CHECK();
   }
   const int nblk = B > 0 ? ws.nblk : 0;
-  cross_bwd_final_kernel<<<(int)ceil_div(d, 256), 256, 0, st>>>(ws.P, ws.Tp, nblk, w, b, w_out, d, L, dw, db, dw_out,
-                                                                dw0_out);
+  cross_bwd_final_kernel<<<dim3((unsigned)ceil_div(d, 256), (unsigned)(L + 1)), 256, 0, st>>>(
+      ws.P, ws.Tp, nblk, w, b, w_out, d, L, dw, db, dw_out, dw0_out);
   RM_LAUNCH_CHECK();
   return 0;
 }

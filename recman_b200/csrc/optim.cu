@@ -46,6 +46,24 @@ __global__ void __launch_bounds__(256) dense_opt_kernel(float* __restrict__ p, c
     p[i] = opt_update(p[i], g[i], o);
 }
 
+// Multi-tensor variant: the replicated (dense) parameters are many small tensors - one launch updates up to
+// DENSE_BATCH of them (descriptors travel as kernel parameters: no device table, CUDA-graph capturable).
+constexpr int DENSE_BATCH = 96;
+struct DenseBatch {
+  float* p[DENSE_BATCH];
+  const float* g[DENSE_BATCH];
+  uint32_t n[DENSE_BATCH];
+};
+
+__global__ void __launch_bounds__(256) dense_opt_multi_kernel(const DenseBatch batch, OptParams o) {
+  const int t = blockIdx.y;
+  float* __restrict__ p = batch.p[t];
+  const float* __restrict__ g = batch.g[t];
+  const uint32_t n = batch.n[t];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    p[i] = opt_update(p[i], g[i], o);
+}
+
 }  // namespace rm
 
 extern "C" {
@@ -80,6 +98,36 @@ int rm_dense_opt_step(float* p, const float* g, int64_t n, int32_t opt, float lr
   if (n == 0) return 0;
   dense_opt_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(p, g, n, o);
   RM_LAUNCH_CHECK();
+  return 0;
+}
+
+int rm_dense_opt_step_multi(float* const* ps, const float* const* gs, const int64_t* ns, int32_t count, int32_t opt,
+                            float lr, float l2, void* stream) {
+  using namespace rm;
+  RM_CHECK_ARG(count >= 0 && (count == 0 || (ps && gs && ns)), "bad argument");
+  OptParams o;
+  int rc = make_params(opt, lr, l2, &o);
+  if (rc) return rc;
+  for (int32_t base = 0; base < count; base += DENSE_BATCH) {
+    DenseBatch b;
+    int nb = 0;
+    int64_t max_n = 0;
+    for (int32_t i = base; i < count && nb < DENSE_BATCH; ++i) {
+      RM_CHECK_ARG(ns[i] >= 0 && ns[i] < ((int64_t)1 << 32), "tensor too large for the multi-tensor update");
+      if (ns[i] == 0) continue;
+      RM_CHECK_ARG(ps[i] && gs[i], "null pointer");
+      b.p[nb] = ps[i];
+      b.g[nb] = gs[i];
+      b.n[nb] = (uint32_t)ns[i];
+      if (ns[i] > max_n) max_n = ns[i];
+      ++nb;
+    }
+    if (nb == 0) continue;
+    int gx = (int)ceil_div(max_n, 256 * 4);
+    if (gx > 4 * RM_NUM_SMS) gx = 4 * RM_NUM_SMS;
+    dense_opt_multi_kernel<<<dim3((unsigned)gx, (unsigned)nb), 256, 0, (cudaStream_t)stream>>>(b, o);
+    RM_LAUNCH_CHECK();
+  }
   return 0;
 }
 

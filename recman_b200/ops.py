@@ -431,6 +431,23 @@ def dense_opt_step(p, g, opt: int, lr: float, l2: float = 0.0):
 # --------------------------------------------------------------------------- #
 # (e) a2a staging for row-sharded tables
 # --------------------------------------------------------------------------- #
+def dense_opt_step_multi(pairs, opt: int, lr: float, l2: float = 0.0):
+    """One launch for a list of (parameter, gradient) tensor pairs (contiguous fp32, same device)."""
+    import ctypes
+
+    if not pairs:
+        return
+    n = len(pairs)
+    ps = (ctypes.c_void_p * n)(*[p.data_ptr() for p, _ in pairs])
+    gs = (ctypes.c_void_p * n)(*[g.data_ptr() for _, g in pairs])
+    ns = (ctypes.c_int64 * n)(*[p.numel() for p, _ in pairs])
+    for p, g in pairs:
+        _dev_check(p)
+        assert p.is_contiguous() and g.is_contiguous() and p.dtype == torch.float32 and g.dtype == torch.float32
+        assert g.numel() == p.numel()
+    _C.call("rm_dense_opt_step_multi", ps, gs, ns, n, opt, float(lr), float(l2), _stream())
+
+
 def unpack_rows(recv, pos, m, k, x, bias_out=None, lin_out=None):
     _dev_check(recv)
     n, KP = recv.shape

@@ -355,6 +355,7 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
                 if tail is not None:
                     dense.append(tail[1])
             allreduce_dense(dense, self.shard.group)
+        dense_pairs = []  # (parameter, gradient) of every dense update: one multi-tensor launch at the end
         for name, p in self.variables.items():
             sparse = pop_sparse_grads(p)
             tail = getattr(p, "rm_dense_tail", None)
@@ -365,7 +366,7 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
                     ops.sparse_opt_step(p.data, sg, kind, lr, l2)
                 if tail is not None:
                     first, g = tail
-                    ops.dense_opt_step(p.data.reshape(-1)[first:], g.contiguous(), kind, lr, 0.0)
+                    dense_pairs.append((p.data.reshape(-1)[first:], g.contiguous()))
             elif sparse:
                 # a dense part exists (the reference's whole-table L2, layers.py:188-193): densify and update all rows
                 p.rm_sparse_grads = sparse
@@ -375,11 +376,12 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
                     g.reshape(-1)[first:] += gt
                 ops.dense_opt_step(p.data, g.contiguous(), kind, lr, 0.0)
             elif p.grad is not None:
-                ops.dense_opt_step(p.data, p.grad.contiguous(), kind, lr, 0.0)
+                dense_pairs.append((p.data, p.grad.contiguous()))
             elif tail is not None:  # id rows already updated by the fused backward kernel: only the dense tail is left
                 first, g = tail
-                ops.dense_opt_step(p.data.reshape(-1)[first:], g.contiguous(), kind, lr, 0.0)
+                dense_pairs.append((p.data.reshape(-1)[first:], g.contiguous()))
             p.grad = None
+        ops.dense_opt_step_multi(dense_pairs, kind, lr, 0.0)
 
     def _eval_at_epoch(self, X_train, y_train, X_valid=None, y_valid=None, start_time=None, epoch=0,
                        batch_number_to_show_progress=50):

@@ -316,3 +316,24 @@ def test_optimizer_steps(opt, k):
     pc = p.clone().cuda()
     ops.dense_opt_step(pc, gr.cuda(), _C.OPT_KINDS[opt], lr, 0.0)
     assert_close(pc, expd, rtol=1e-5, atol_scale=1e-6)
+
+
+@pytest.mark.parametrize("opt", ["adam", "adagrad", "gd"])
+def test_dense_opt_step_multi_matches_single(opt):
+    """One multi-tensor launch == one rm_dense_opt_step call per tensor, bit for bit (more tensors than one batch)."""
+    ops = _ops()
+    from recman_b200 import _C
+
+    g = torch.Generator().manual_seed(3)
+    sizes = [1, 7, 400 * 429, 33, 1025] + [5 + i for i in range(100)]
+    ps = [torch.randn(n, generator=g).cuda() for n in sizes]
+    gs = [torch.randn(n, generator=g).cuda() for n in sizes]
+    single = [p.clone() for p in ps]
+    for p, gr in zip(single, gs):
+        ops.dense_opt_step(p, gr, _C.OPT_KINDS[opt], 0.01, 0.0)
+    multi = [p.clone() for p in ps]
+    ops.dense_opt_step_multi(list(zip(multi, gs)), _C.OPT_KINDS[opt], 0.01, 0.0)
+    for a, b in zip(single, multi):
+        assert torch.equal(a, b)
+    exp = oracle.fresh_optimizer_step(ps[2].double().cpu(), gs[2].double().cpu(), opt, 0.01)
+    assert_close(multi[2], exp, rtol=1e-5, atol_scale=1e-6)
