@@ -309,7 +309,10 @@ class DataInputs(dict):
         self.batch_size = 0
 
     def _to_device(self, arr: np.ndarray) -> torch.Tensor:
-        t = torch.from_numpy(np.ascontiguousarray(arr))
+        arr = np.ascontiguousarray(arr)
+        if not arr.flags.writeable:  # pandas may hand out read-only views
+            arr = arr.copy()
+        t = torch.from_numpy(arr)
         if self.device.type == "cuda":
             t = t.pin_memory().to(self.device, non_blocking=True)
         self.h2d_bytes += t.numel() * t.element_size()
