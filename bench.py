@@ -173,6 +173,15 @@ def algorithmic_bytes(kind, B, m, k, n_dense, n_unique=None):
         # per id: position 4 + dx row 4k + x row 4k; S row + 2 scalars per sample; per unique row: 4k + 2*4 written
         nu = n_unique if n_unique is not None else B * m
         return B * m * (4 + 8 * k) + B * (4 * k + 8) + nu * (4 * k + 8)
+    if kind == "rm_emb_fm_bwd_update":
+        # rm_emb_fm_bwd with the optimizer fused in: instead of writing the summed rows, per unique row the row id (8) is
+        # read and the table row (4k) and its bias / linear weights (2*4) are read AND written
+        nu = n_unique if n_unique is not None else B * m
+        return B * m * (4 + 8 * k) + B * (4 * k + 8) + nu * (8 + 2 * (4 * k + 8))
+    if kind == "rm_segment_reduce_p2p_update":
+        # per owned id: global position 4 + gradient row (k+4)*4 (local or NVLink); per unique row as above
+        nu = n_unique if n_unique is not None else B * m
+        return B * m * (4 + 4 * (k + 4)) + nu * (8 + 2 * (4 * k + 8))
     if kind == "rm_segment_reduce_p2p":
         # per owned id: global position 4 + gradient row (k+4)*4 (local or NVLink); per unique row: 4k + 2*4 written
         nu = n_unique if n_unique is not None else B * m

@@ -245,6 +245,23 @@ int rm_pack_grad_rows(const float* dx, const float* x, int64_t ld, const float* 
                       float* send, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * A8' backward of a NARROW dense layer y[B,N] = x[B,d] W[d,N] + b, N <= 64, N % 4 == 0
+ * (DNN, recman/tf/core/layers.py:576-609; DeepFM's default hidden units are (32, 32),
+ * recman/tf/core/DeepFM.py:35).  The batch is the only large dimension of these
+ * products; exact fp32 FMA.  The forward and wide layers stay on cuBLAS.
+ *   rm_linear_bwd_input : dx[b, c] = sum_n g[b,n] * W[c,n]  for c < d; columns
+ *                         d <= c < d_ld (row padding, d_ld % 4 == 0) are set to 0.
+ *   rm_linear_bwd_weight: dW[f, n] = sum_b x[b*ld + f] * g[b,n]  for f < K; the
+ *                         batch is reduced in fixed slabs summed in slab order
+ *                         (deterministic); workspace from the _workspace_bytes query.
+ * ------------------------------------------------------------------------- */
+int rm_linear_bwd_input(const float* g, int64_t B, int32_t N, const float* W, int32_t d, float* dx, int64_t d_ld,
+                        void* stream);
+size_t rm_linear_bwd_weight_workspace_bytes(int64_t B, int32_t K, int32_t N);
+int rm_linear_bwd_weight(const float* x, int64_t ld, const float* g, int64_t B, int32_t K, int32_t N, float* dW,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * (e') row-sharded tables over NVLink PEER MEMORY (W a power of two <= 8, one
  * NVSwitch box): the lookup and the gradient reduction read their rows straight
  * from the owning rank - no all-to-all, no pack/unpack pass, no host sync.

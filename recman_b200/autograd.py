@@ -303,10 +303,39 @@ class FirstLinearFunction(Function):
         xbuf, W = ctx.saved_tensors
         d = ctx.d
         g = g.contiguous()
-        dW = xbuf[:, :d].t() @ g
         db = g.sum(0)
+        ld = xbuf.shape[1]
+        if ops.narrow_linear_ok(g.shape[1]) and xbuf.is_contiguous() and W.is_contiguous():
+            # narrow first layer (DeepFM default 32 units): the batch is the only large dimension of both products
+            dW = ops.linear_bwd_weight(xbuf, ld, d, g)
+            dxbuf = ops.linear_bwd_input(g, W, d_ld=ld)
+            return dxbuf, dW, db, None
+        dW = xbuf[:, :d].t() @ g
         dxbuf = torch.empty_like(xbuf)
         torch.mm(g, W.t(), out=dxbuf[:, :d])
         if xbuf.shape[1] > d:
             dxbuf[:, d:].zero_()
         return dxbuf, dW, db, None
+
+
+class NarrowLinearFunction(Function):
+    """y = x @ W + b for a hidden layer with a narrow output (N <= 64): library forward, own batch-reduced backward."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        ctx.save_for_backward(x, W)
+        return torch.addmm(b, x, W)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, W = ctx.saved_tensors
+        g = g.contiguous()
+        db = g.sum(0)
+        K = x.shape[1]
+        if K % 4 == 0 and x.is_contiguous() and W.is_contiguous():
+            dW = ops.linear_bwd_weight(x, K, K, g)
+            dx = ops.linear_bwd_input(g, W, d_ld=K) if ctx.needs_input_grad[0] else None
+        else:
+            dW = x.t() @ g
+            dx = g @ W.t() if ctx.needs_input_grad[0] else None
+        return dx, dW, db

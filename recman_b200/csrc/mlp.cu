@@ -1,0 +1,264 @@
+// Backward of a narrow dense layer  y[B,N] = x[B,d] W[d,N] + b  with N <= 64 (DeepFM's reference default is
+// deep_hidden_units = (32, 32), recman/tf/core/DeepFM.py:35; DNN layer recman/tf/core/layers.py:576-609):
+//
+//   rm_linear_bwd_input   dx[B, d_ld] = g[B,N] W^T          (K = N is tiny: one pass, W^T and the g tile live in smem)
+//   rm_linear_bwd_weight  dW[d, N]    = x^T g               (reduction over the batch: fixed slabs, ordered final sum)
+//
+// Both are "tall-skinny" products in which the batch is the only large dimension: the input-gradient is bound by
+// writing dx (4*d_ld B per sample), the weight-gradient by reading x once; a library SGEMM tiles them for square
+// problems (K = 32 leaves its pipeline empty, the 65536-long reduction gets split-K with atomics or a serial tail).
+// Exact fp32 FMA arithmetic on the CUDA cores (no TF32): the MLP stays inside the 1e-5 parity bound.  The forward
+// product and wide layers (N > 64) stay on cuBLAS.
+#include "common.cuh"
+
+namespace rm {
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, bool valid) {
+  const int bytes = valid ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dx tile 128 rows x 128 columns per CTA, 8 x 8 outputs per thread, reduction over n < N from shared memory.
+// Columns d <= c < d_ld (the 16-byte row padding of the row buffer) come out as exact zeros (their W rows are zero).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int DX_BM = 128, DX_BN = 128, DX_LD = 132;  // smem row stride (floats): 16-byte aligned, conflict-free
+
+template <int NT>
+__global__ void __launch_bounds__(256) linear_dx_kernel(const float* __restrict__ g, int64_t B, int N,
+                                                        const float* __restrict__ W, int d, float* __restrict__ dx,
+                                                        int64_t d_ld) {
+  extern __shared__ float smem_dx[];
+  float* Gs = smem_dx;               // [NT][DX_LD]: Gs[n][r] = g[r0 + r, n]
+  float* Ws = smem_dx + NT * DX_LD;  // [NT][DX_LD]: Ws[n][c] = W[c0 + c, n]
+  const int tid = threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * DX_BM;
+  const int c0 = blockIdx.y * DX_BN;
+#pragma unroll
+  for (int i = 0; i < (NT / 4) * 128 / 256; ++i) {
+    const int idx = tid + i * 256;
+    const int r = idx & 127, n4 = idx >> 7;
+    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f), wv = gv;
+    if (4 * n4 < N) {
+      if (r0 + r < B) gv = ld4(g + (r0 + r) * N + 4 * n4);
+      if (c0 + r < d) wv = ld4(W + (int64_t)(c0 + r) * N + 4 * n4);
+    }
+    Gs[(4 * n4 + 0) * DX_LD + r] = gv.x; Gs[(4 * n4 + 1) * DX_LD + r] = gv.y;
+    Gs[(4 * n4 + 2) * DX_LD + r] = gv.z; Gs[(4 * n4 + 3) * DX_LD + r] = gv.w;
+    Ws[(4 * n4 + 0) * DX_LD + r] = wv.x; Ws[(4 * n4 + 1) * DX_LD + r] = wv.y;
+    Ws[(4 * n4 + 2) * DX_LD + r] = wv.z; Ws[(4 * n4 + 3) * DX_LD + r] = wv.w;
+  }
+  __syncthreads();
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+  for (int n = 0; n < N; ++n) {
+    const float4 a0 = ld4(Gs + n * DX_LD + ty * 8), a1 = ld4(Gs + n * DX_LD + ty * 8 + 4);
+    const float4 b0 = ld4(Ws + n * DX_LD + tx * 4), b1 = ld4(Ws + n * DX_LD + 64 + tx * 4);
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t row = r0 + ty * 8 + i;
+    if (row < B) {
+      float* o = dx + row * d_ld;
+      const int ca = c0 + tx * 4, cb = c0 + 64 + tx * 4;
+      if (ca < d_ld) st4(o + ca, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+      if (cb < d_ld) st4(o + cb, make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dW: CTA (feature tile of 128, batch slab) -> partial[slab][f][n]; chunks of 32 samples double-buffered with cp.async.
+// Thread: 4 features x (NT / 8) outputs.  The slabs are summed in slab order by linear_dw_final_kernel.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int DW_BF = 128, DW_BK = 32;
+
+template <int NT>
+__global__ void __launch_bounds__(256) linear_dw_kernel(const float* __restrict__ x, int64_t ld,
+                                                        const float* __restrict__ g, int64_t B, int K, int N,
+                                                        int64_t slab_rows, float* __restrict__ partial, int Kpad) {
+  constexpr int NV = NT / 32;  // float4 output groups per thread along n
+  extern __shared__ float smem_dw[];
+  float* Xs = smem_dw;                          // [2][DW_BK][DW_BF]
+  float* Gs = smem_dw + 2 * DW_BK * DW_BF;      // [2][DW_BK][NT]
+  const int tid = threadIdx.x;
+  const int f0 = blockIdx.x * DW_BF;
+  const int64_t b_lo = (int64_t)blockIdx.y * slab_rows;
+  const int64_t b_hi = b_lo + slab_rows < B ? b_lo + slab_rows : B;
+  const int n_chunks = (int)((b_hi - b_lo + DW_BK - 1) / DW_BK);
+  const uint32_t xs_u32 = (uint32_t)__cvta_generic_to_shared(Xs), gs_u32 = (uint32_t)__cvta_generic_to_shared(Gs);
+
+  auto issue = [&](int ch) {
+    const int buf = ch & 1;
+    const int64_t b0 = b_lo + (int64_t)ch * DW_BK;
+#pragma unroll
+    for (int i = 0; i < DW_BK * DW_BF / 4 / 256; ++i) {  // 4 float4 of the x chunk per thread
+      const int idx = tid + i * 256;
+      const int r = idx >> 5, c4 = idx & 31;
+      const int64_t b = b0 + r;
+      const int f = f0 + 4 * c4;
+      const bool ok = b < b_hi && f < ld;  // ld % 4 == 0: a float4 never straddles the row end
+      cp_async16_zfill(xs_u32 + (uint32_t)((buf * DW_BK + r) * DW_BF + 4 * c4) * 4u, ok ? x + b * ld + f : x, ok);
+    }
+    for (int idx = tid; idx < DW_BK * NT / 4; idx += 256) {
+      const int r = idx / (NT / 4), c4 = idx - r * (NT / 4);
+      const int64_t b = b0 + r;
+      const bool ok = b < b_hi && 4 * c4 < N;
+      cp_async16_zfill(gs_u32 + (uint32_t)((buf * DW_BK + r) * NT + 4 * c4) * 4u, ok ? g + b * N + 4 * c4 : g, ok);
+    }
+    cp_async_commit_group();
+  };
+
+  const int tf = tid >> 3, tn = tid & 7;  // features tf*4 .. +3, outputs tn*4 .. +3 (+32 for NT = 64)
+  float acc[4][4 * NV];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4 * NV; ++j) acc[i][j] = 0.f;
+  if (n_chunks > 0) issue(0);
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    if (ch + 1 < n_chunks) issue(ch + 1);
+    else cp_async_commit_group();
+    cp_async_wait_group<1>();
+    __syncthreads();
+    const float* xb = Xs + (ch & 1) * DW_BK * DW_BF + tf * 4;
+    const float* gb = Gs + (ch & 1) * DW_BK * NT + tn * 4;
+#pragma unroll 8
+    for (int r = 0; r < DW_BK; ++r) {
+      const float4 xv = ld4(xb + r * DW_BF);
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const float4 gv = ld4(gb + r * NT + 32 * v);
+        const float ga[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][4 * v + j] = fmaf(xa[i], ga[j], acc[i][4 * v + j]);
+      }
+    }
+    __syncthreads();  // the buffer is refilled by the next iteration's issue
+  }
+  float* out = partial + ((int64_t)blockIdx.y * Kpad + f0 + tf * 4) * NT;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      st4(out + i * NT + 32 * v + tn * 4,
+          make_float4(acc[i][4 * v], acc[i][4 * v + 1], acc[i][4 * v + 2], acc[i][4 * v + 3]));
+}
+
+__global__ void __launch_bounds__(256) linear_dw_final_kernel(const float* __restrict__ partial, int slabs, int Kpad,
+                                                              int NT, int K, int N, float* __restrict__ dW) {
+  const int64_t total = (int64_t)K * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i % N);
+    const int64_t f = i / N;
+    float acc = 0.f;
+    for (int s = 0; s < slabs; ++s) acc += partial[((int64_t)s * Kpad + f) * NT + n];
+    dW[i] = acc;
+  }
+}
+
+struct DwLayout {
+  int NT, n_ftiles, Kpad, slabs;
+  int64_t slab_rows;
+  size_t total;
+};
+
+static DwLayout dw_layout(int64_t B, int K, int N) {
+  DwLayout L;
+  L.NT = N <= 32 ? 32 : 64;
+  L.n_ftiles = (int)ceil_div(K, DW_BF);
+  L.Kpad = L.n_ftiles * DW_BF;
+  int64_t slabs = (4 * RM_NUM_SMS) / L.n_ftiles;  // about four CTAs per SM in one wave
+  const int64_t max_slabs = ceil_div(B > 0 ? B : 1, 256);
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  L.slab_rows = ceil_div(ceil_div(B > 0 ? B : 1, slabs), DW_BK) * DW_BK;
+  L.slabs = (int)ceil_div(B > 0 ? B : 1, L.slab_rows);
+  L.total = align_up((size_t)L.slabs * L.Kpad * L.NT * sizeof(float), 256);
+  return L;
+}
+
+}  // namespace rm
+
+extern "C" {
+
+int rm_linear_bwd_input(const float* g, int64_t B, int32_t N, const float* W, int32_t d, float* dx, int64_t d_ld,
+                        void* stream) {
+  using namespace rm;
+  RM_CHECK_ARG(B >= 0 && N > 0 && d > 0 && d_ld >= d, "bad shape");
+  if (B == 0) return 0;
+  RM_CHECK_ARG(g && W && dx, "null pointer");
+  RM_UNSUPPORTED(N <= 64 && N % 4 == 0 && d_ld % 4 == 0 && aligned16(g) && aligned16(W) && aligned16(dx),
+                 "narrow-layer input gradient needs N <= 64, N % 4 == 0 and 16-byte aligned rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)ceil_div(B, DX_BM), (unsigned)ceil_div(d_ld, DX_BN));
+  if (N <= 32) {
+    const size_t smem = (size_t)2 * 32 * DX_LD * sizeof(float);
+    linear_dx_kernel<32><<<grid, 256, smem, st>>>(g, B, N, W, d, dx, d_ld);
+  } else {
+    const size_t smem = (size_t)2 * 64 * DX_LD * sizeof(float);
+    RM_CUDA(cudaFuncSetAttribute(linear_dx_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    linear_dx_kernel<64><<<grid, 256, smem, st>>>(g, B, N, W, d, dx, d_ld);
+  }
+  RM_LAUNCH_CHECK();
+  return 0;
+}
+
+size_t rm_linear_bwd_weight_workspace_bytes(int64_t B, int32_t K, int32_t N) {
+  if (B < 0 || K <= 0 || N <= 0 || N > 64) return 256;
+  return rm::dw_layout(B, K, N).total;
+}
+
+int rm_linear_bwd_weight(const float* x, int64_t ld, const float* g, int64_t B, int32_t K, int32_t N, float* dW,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace rm;
+  RM_CHECK_ARG(B >= 0 && K > 0 && N > 0 && ld >= K, "bad shape");
+  RM_CHECK_ARG(dW && workspace && (B == 0 || (x && g)), "null pointer");
+  RM_UNSUPPORTED(N <= 64 && N % 4 == 0 && ld % 4 == 0 && (B == 0 || (aligned16(x) && aligned16(g))) &&
+                     aligned16(workspace),
+                 "narrow-layer weight gradient needs N <= 64, N % 4 == 0 and 16-byte aligned rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) {
+    RM_CUDA(cudaMemsetAsync(dW, 0, (size_t)K * N * sizeof(float), st));
+    return 0;
+  }
+  const DwLayout L = dw_layout(B, K, N);
+  if (workspace_bytes < L.total) {
+    set_error("rm_linear_bwd_weight: workspace %zu < required %zu", workspace_bytes, L.total);
+    return RM_E_WORKSPACE;
+  }
+  float* partial = (float*)workspace;
+  dim3 grid((unsigned)L.n_ftiles, (unsigned)L.slabs);
+  const size_t smem = (size_t)2 * DW_BK * (DW_BF + L.NT) * sizeof(float);
+  if (L.NT == 32) {
+    linear_dw_kernel<32><<<grid, 256, smem, st>>>(x, ld, g, B, K, N, L.slab_rows, partial, L.Kpad);
+  } else {
+    RM_CUDA(cudaFuncSetAttribute(linear_dw_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    linear_dw_kernel<64><<<grid, 256, smem, st>>>(x, ld, g, B, K, N, L.slab_rows, partial, L.Kpad);
+  }
+  RM_LAUNCH_CHECK();
+  linear_dw_final_kernel<<<grid_for((int64_t)K * N, 256, 8), 256, 0, st>>>(partial, L.slabs, L.Kpad, L.NT, K, N, dW);
+  RM_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

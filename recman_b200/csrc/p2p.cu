@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(256, MINB) gather_fm_p2p_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Deep-queue variant (default for W > 1).  NVLink reads have several times the latency of local HBM, and with all 8
-// ranks pulling from each other the register-staged kernel above (64 B in flight per thread) is latency bound.  Here
+// Deep-queue variant (experiment, opt-in).  NVLink reads have several times the latency of local HBM; if the
+// register-staged kernel above (64 B in flight per thread) were latency bound, more bytes in flight would help.  Here
 // every lane requests its 16-byte piece of FCH rows at once with cp.async (LDGSTS) into a PRIVATE shared-memory slot
 // and reads the same slot back itself after cp.async.wait_group - no registers are held by loads in flight, no
 // block-level synchronisation is needed, and two chunks (double buffer) x FCH rows x 16 B are in flight per thread.
@@ -347,8 +347,10 @@ int rm_gather_fm_fwd_p2p(const float* const* tables, const float* const* bias_ta
   while ((1 << wshift) < W) ++wshift;
   cudaStream_t st = (cudaStream_t)stream;
   const int lpr = pow2ceil_p(k / 4);
-  // deep-queue (cp.async) variant: default whenever rows come over NVLink; RM_TUNE_P2P_ASYNC=0/1 overrides
-  if (tune_variant("RM_TUNE_P2P_ASYNC", W > 1 ? 1 : 0) && lpr <= 32) {
+  // deep-queue (cp.async) variant: opt-in with RM_TUNE_P2P_ASYNC=1.  Measured at W = 2 (C5, half the rows over NVLink)
+  // it is SLOWER than the register-staged kernel (0.72 ms vs 0.54 ms): the NVLink reads are not bound by registers held
+  // per load in flight (profiles/README.md)
+  if (tune_variant("RM_TUNE_P2P_ASYNC", 0) && lpr <= 32) {
 #define RM_GA(L, F)                                                                                                  \
   return launch_gather_fm_p2p_async<L, F>(pt, wshift, feat_sizes, local_offsets, ids, dense, lin_dense, n_dense, B, m, \
                                           k, x, ld, fm_out, lin_out, sum_out, status, st)

@@ -429,6 +429,39 @@ def dense_opt_step(p, g, opt: int, lr: float, l2: float = 0.0):
 
 
 # --------------------------------------------------------------------------- #
+# A8' narrow dense layer backward (N <= 64)
+# --------------------------------------------------------------------------- #
+def narrow_linear_ok(N: int) -> bool:
+    return 0 < N <= 64 and N % 4 == 0
+
+
+def linear_bwd_input(g, W, d_ld: Optional[int] = None, out=None):
+    """dx [B, d_ld] = g [B, N] @ W[d, N]^T, columns d..d_ld zero (g, W contiguous fp32, N <= 64, N % 4 == 0)."""
+    _dev_check(g)
+    B, N = g.shape
+    d = W.shape[0]
+    assert W.shape[1] == N and g.is_contiguous() and W.is_contiguous()
+    d_ld = (d + 3) // 4 * 4 if d_ld is None else int(d_ld)
+    if out is None:
+        out = torch.empty(B, d_ld, dtype=torch.float32, device=g.device)
+    assert out.shape == (B, d_ld) and out.is_contiguous()
+    _C.call("rm_linear_bwd_input", _p(g), B, N, _p(W), d, _p(out), d_ld, _stream())
+    return out
+
+
+def linear_bwd_weight(x, ld: int, K: int, g):
+    """dW [K, N] = x[:, :K]^T @ g, x rows ld floats apart (ld % 4 == 0), deterministic slabbed batch reduction."""
+    _dev_check(g)
+    B, N = g.shape
+    assert g.is_contiguous() and x.dtype == torch.float32
+    ws_bytes = _C.lib.rm_linear_bwd_weight_workspace_bytes(B, K, N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=g.device)
+    dW = torch.empty(K, N, dtype=torch.float32, device=g.device)
+    _C.call("rm_linear_bwd_weight", _p(x), int(ld), _p(g), B, K, N, _p(dW), _p(ws), ws_bytes, _stream())
+    return dW
+
+
+# --------------------------------------------------------------------------- #
 # (e) a2a staging for row-sharded tables
 # --------------------------------------------------------------------------- #
 def dense_opt_step_multi(pairs, opt: int, lr: float, l2: float = 0.0):

@@ -31,6 +31,7 @@ from ..autograd import (
     EmbeddingLayout,
     FirstLinearFunction,
     FMFunction,
+    NarrowLinearFunction,
     MultiField,
     SparseRun,
 )
@@ -531,6 +532,9 @@ class DNN:
             W, b = v[f"{p}dnn_layer_{i}_weights"], v[f"{p}dnn_layer_{i}_bias"]
             if i == 0 and padded:
                 y = FirstLinearFunction.apply(y.buf, W, b, y.d)
+            elif ops.narrow_linear_ok(W.shape[1]) and y.shape[1] % 4 == 0:
+                # narrow hidden layer: batch-reduced backward kernels (csrc/mlp.cu)
+                y = NarrowLinearFunction.apply(y.contiguous(), W, b)
             else:
                 y = torch.addmm(b, y, W)
             y = self.activation(y)

@@ -337,3 +337,22 @@ def test_dense_opt_step_multi_matches_single(opt):
         assert torch.equal(a, b)
     exp = oracle.fresh_optimizer_step(ps[2].double().cpu(), gs[2].double().cpu(), opt, 0.01)
     assert_close(multi[2], exp, rtol=1e-5, atol_scale=1e-6)
+
+
+@pytest.mark.parametrize("B,d,N", [(1, 5, 4), (300, 429, 32), (1000, 1677, 32), (257, 130, 64), (64, 32, 32), (513, 100, 12)])
+def test_narrow_linear_backward_kernels(B, d, N):
+    """dx = g W^T (padded row buffer, zero tail) and dW = x^T g (slabbed, deterministic) vs fp64; exact fp32 FMA."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(B + d + N)
+    ld = (d + 3) // 4 * 4
+    x = torch.zeros(B, ld)
+    x[:, :d] = torch.randn(B, d, generator=g)
+    W = torch.randn(d, N, generator=g) * 0.1
+    gy = torch.randn(B, N, generator=g)
+    dx = ops.linear_bwd_input(gy.cuda(), W.cuda(), d_ld=ld)
+    assert dx.shape == (B, ld)
+    assert_close(dx[:, :d], gy.double() @ W.double().t(), rtol=1e-5, atol_scale=2e-6)
+    assert torch.all(dx[:, d:] == 0)
+    dW = ops.linear_bwd_weight(x.cuda(), ld, d, gy.cuda())
+    assert_close(dW, x[:, :d].double().t() @ gy.double(), rtol=1e-5, atol_scale=2e-6)
+    assert torch.equal(dW, ops.linear_bwd_weight(x.cuda(), ld, d, gy.cuda()))  # run-to-run bit-identical
