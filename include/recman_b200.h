@@ -136,7 +136,14 @@ int rm_segment_plan(const int64_t* ids, const int64_t* table_offsets, int64_t N,
                     void* stream);
 int rm_segment_reduce(const float* grad, int64_t ld, int32_t m, int32_t k, int64_t N,
                       const int32_t* sorted_pos, const int32_t* seg_start, const int32_t* n_unique,
-                      float* out_rows, void* stream);
+                      float* out_rows, void* workspace, size_t workspace_bytes, void* stream);
+/* Workspace of every segmented-reduce entry point (rm_segment_reduce, rm_emb_fm_bwd[_update],
+ * rm_segment_reduce_p2p[_update]; N = number of positions / plan capacity).  Segments longer
+ * than 16 positions (skewed ids: a hot row) are not walked serially: every 32 consecutive
+ * positions are summed by one row group and the chunk partials are added in chunk order -
+ * still a fixed, position-determined association (oracle/segment.py restates it).  A NULL
+ * workspace disables this and walks every segment serially. */
+size_t rm_segment_reduce_workspace_bytes(int64_t N, int32_t k);
 
 /* Fused DeepFM embedding backward: the gradient row of position p=(b,f) is
  *   dx[b*ld + f*k + :] + g_fm[b] * (S[b,:] - x[b*ld + f*k + :])      (FM bwd, A5b)
@@ -146,7 +153,7 @@ int rm_segment_reduce(const float* grad, int64_t ld, int32_t m, int32_t k, int64
 int rm_emb_fm_bwd(const float* dx, const float* x, int64_t ld, const float* sum, const float* g_fm,
                   const float* g_lin, int32_t m, int32_t k, int64_t N, const int32_t* sorted_pos,
                   const int32_t* seg_start, const int32_t* n_unique, float* out_rows, float* out_bias,
-                  float* out_lin, void* stream);
+                  float* out_lin, void* workspace, size_t workspace_bytes, void* stream);
 
 /* rm_emb_fm_bwd fused with the optimizer (N1): instead of emitting the summed rows,
  * table[uniq_rows[u],:] (and bias_table / lin_table[uniq_rows[u]] when g_fm / g_lin
@@ -157,7 +164,7 @@ int rm_emb_fm_bwd_update(const float* dx, const float* x, int64_t ld, const floa
                          const int32_t* sorted_pos, const int32_t* seg_start,
                          const int64_t* uniq_rows, const int32_t* n_unique, float* table,
                          float* bias_table, float* lin_table, int32_t opt, float lr, float l2,
-                         void* stream);
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * K4  DCN cross network.  Call site recman/tf/core/DCN.py:135-137 (the class
@@ -287,6 +294,11 @@ int rm_linear_bwd_weight(const float* x, int64_t ld, const float* g, int64_t B, 
  *   rm_pack_grad_rows(pos = NULL).  G is a HOST array of W device pointers.
  *   Summation order = ascending global position, i.e. the single-GPU order of
  *   the concatenated batch, independent of W.
+ *   gscal (nullable, LOCAL memory): the two k=1 gradients are per-SAMPLE values, so
+ *   instead of riding in every row they can be all-gathered once as
+ *   gscal[W * rows_per_rank / m, 2] = (g_bias, g_lin) per global sample; then
+ *   KP >= k suffices (KP = k: 256-byte rows at k = 64, one NVLink request fewer
+ *   per row) and m (fields per sample) maps a position to its sample.
  * ------------------------------------------------------------------------- */
 int rm_p2p_alloc(size_t bytes, void** ptr, uint8_t* handle64);
 int rm_p2p_open(const uint8_t* handle64, void** ptr);
@@ -304,16 +316,18 @@ int rm_shard_plan(const int64_t* gids, int64_t Ntot, int32_t m, int32_t W, int32
                   int64_t N_cap, void* workspace, size_t workspace_bytes, int32_t* sorted_gpos,
                   int32_t* seg_start, int64_t* uniq_rows, int32_t* n_unique, int32_t* n_own,
                   int32_t* status, void* stream);
-int rm_segment_reduce_p2p(const float* const* G, int32_t W, int64_t rows_per_rank, int32_t KP,
-                          int32_t k, int64_t N_cap, const int32_t* sorted_gpos,
+int rm_segment_reduce_p2p(const float* const* G, const float* gscal, int32_t m, int32_t W,
+                          int64_t rows_per_rank, int32_t KP, int32_t k, int64_t N_cap, const int32_t* sorted_gpos,
                           const int32_t* seg_start, const int32_t* n_unique, float* out_rows,
-                          float* out_bias, float* out_lin, void* stream);
+                          float* out_bias, float* out_lin, void* workspace, size_t workspace_bytes,
+                          void* stream);
 /* ... fused with the optimizer update of the owner's local tables (bias_table / lin_table nullable). */
-int rm_segment_reduce_p2p_update(const float* const* G, int32_t W, int64_t rows_per_rank, int32_t KP,
-                                 int32_t k, int64_t N_cap, const int32_t* sorted_gpos,
+int rm_segment_reduce_p2p_update(const float* const* G, const float* gscal, int32_t m, int32_t W,
+                                 int64_t rows_per_rank, int32_t KP, int32_t k, int64_t N_cap, const int32_t* sorted_gpos,
                                  const int32_t* seg_start, const int64_t* uniq_rows,
                                  const int32_t* n_unique, float* table, float* bias_table,
-                                 float* lin_table, int32_t opt, float lr, float l2, void* stream);
+                                 float* lin_table, int32_t opt, float lr, float l2, void* workspace,
+                                 size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,11 @@ def global_rows(ids: np.ndarray, table_offsets: np.ndarray) -> np.ndarray:
     return ids + np.asarray(table_offsets, dtype=np.int64)[None, : ids.shape[1]]
 
 
-def segment_sum_sorted(keys: np.ndarray, grads: np.ndarray, scale: np.ndarray | None = None):
+SEG_LONG = 16   # segments longer than this are summed chunk-wise (recman_b200/csrc/scatter.cu: SEG_LONG)
+SEG_CHUNK = 32  # positions per chunk (SEG_CHUNK)
+
+
+def segment_sum_sorted(keys: np.ndarray, grads: np.ndarray, scale: np.ndarray | None = None, chunked: bool = True):
     """Deterministic scatter-add.
 
     keys  [N] int64 global rows (position p = b*m + f for one-hot fields)
@@ -34,7 +38,9 @@ def segment_sum_sorted(keys: np.ndarray, grads: np.ndarray, scale: np.ndarray | 
     Returns ``(unique_rows [U] int64 ascending, sums [U, k] float32,
     order [N] int64, seg_start [U+1] int64)`` where ``order`` is the stable
     sort permutation and ``sums[u] = sum over order[seg_start[u]:seg_start[u+1]]``
-    accumulated sequentially in that order in float32.
+    accumulated sequentially in that order in float32.  With ``chunked`` (the order the CUDA kernels commit to), a
+    segment longer than ``SEG_LONG`` positions - a hot row under skewed ids - is summed as: every ``SEG_CHUNK``
+    consecutive positions sequentially into a partial, then the partials sequentially in chunk order.
     """
     keys = np.asarray(keys, dtype=np.int64).reshape(-1)
     grads = np.asarray(grads)
@@ -56,9 +62,19 @@ def segment_sum_sorted(keys: np.ndarray, grads: np.ndarray, scale: np.ndarray | 
     # sequential accumulation in sorted order: vectorised over segments, stepping
     # through the j-th element of every segment at once (keeps fp32 add order).
     lens = np.diff(seg_start)
-    for j in range(int(lens.max())):
-        live = np.flatnonzero(lens > j)
+    short = lens <= SEG_LONG if chunked else np.ones_like(lens, dtype=bool)
+    max_short = int(lens[short].max()) if short.any() else 0
+    for j in range(max_short):
+        live = np.flatnonzero(short & (lens > j))
         sums[live] = (sums[live] + gs[seg_start[live] + j]).astype(g.dtype)
+    for u in np.flatnonzero(~short):  # long segments: chunk partials, then the partials in chunk order
+        total = np.zeros(k, dtype=g.dtype)
+        for c0 in range(int(seg_start[u]), int(seg_start[u + 1]), SEG_CHUNK):
+            part = np.zeros(k, dtype=g.dtype)
+            for j in range(c0, min(c0 + SEG_CHUNK, int(seg_start[u + 1]))):
+                part = (part + gs[j]).astype(g.dtype)
+            total = (total + part).astype(g.dtype)
+        sums[u] = total
     return uniq, sums, order, seg_start
 
 

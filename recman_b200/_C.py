@@ -44,17 +44,16 @@ _SIGS = {
         ctypes.c_int,
         [P, P, P, P, P, P, P, c_int32, c_int64, c_int32, c_int32, P, c_int64, P, P, P, P, P],
     ),
+    "rm_segment_reduce_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "rm_segment_plan_workspace_bytes": (c_size_t, [c_int64]),
     "rm_segment_plan": (ctypes.c_int, [P, P, c_int64, c_int32, c_int64, P, c_size_t, P, P, P, P, P]),
-    "rm_segment_reduce": (ctypes.c_int, [P, c_int64, c_int32, c_int32, c_int64, P, P, P, P, P]),
+    "rm_segment_reduce": (ctypes.c_int, [P, c_int64, c_int32, c_int32, c_int64, P, P, P, P, P, c_size_t, P]),
     "rm_emb_fm_bwd": (
         ctypes.c_int,
-        [P, P, c_int64, P, P, P, c_int32, c_int32, c_int64, P, P, P, P, P, P, P],
-    ),
+        [P, P, c_int64, P, P, P, c_int32, c_int32, c_int64, P, P, P, P, P, P, P, c_size_t, P]),
     "rm_emb_fm_bwd_update": (
         ctypes.c_int,
-        [P, P, c_int64, P, P, P, c_int32, c_int32, c_int64, P, P, P, P, P, P, P, c_int32, c_float, c_float, P],
-    ),
+        [P, P, c_int64, P, P, P, c_int32, c_int32, c_int64, P, P, P, P, P, P, P, c_int32, c_float, c_float, P, c_size_t, P]),
     "rm_cross_fwd": (ctypes.c_int, [P, c_int64, P, P, P, P, c_int64, c_int32, c_int32, P, P, P]),
     "rm_cross_bwd_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "rm_cross_bwd": (
@@ -88,11 +87,10 @@ _SIGS = {
         ctypes.c_int,
         [P, c_int64, c_int32, c_int32, c_int32, P, P, c_int64, c_int64, P, c_size_t, P, P, P, P, P, P, P],
     ),
-    "rm_segment_reduce_p2p": (ctypes.c_int, [P, c_int32, c_int64, c_int32, c_int32, c_int64, P, P, P, P, P, P, P]),
+    "rm_segment_reduce_p2p": (ctypes.c_int, [P, P, c_int32, c_int32, c_int64, c_int32, c_int32, c_int64, P, P, P, P, P, P, P, c_size_t, P]),
     "rm_segment_reduce_p2p_update": (
         ctypes.c_int,
-        [P, c_int32, c_int64, c_int32, c_int32, c_int64, P, P, P, P, P, P, P, c_int32, c_float, c_float, P],
-    ),
+        [P, P, c_int32, c_int32, c_int64, c_int32, c_int32, c_int64, P, P, P, P, P, P, P, c_int32, c_float, c_float, P, c_size_t, P]),
     "rm_sparse_opt_step": (ctypes.c_int, [P, c_int32, P, P, P, c_int64, c_int32, c_float, c_float, P]),
     "rm_dense_opt_step": (ctypes.c_int, [P, P, c_int64, c_int32, c_float, c_float, P]),
     "rm_linear_bwd_input": (ctypes.c_int, [P, c_int64, c_int32, P, c_int32, P, c_int64, P]),

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) pack_grad_rows_kernel(const float* __rest
       }
       st4(dst + 4 * c, v);
     }
-    if (lir == 0) st4(dst + k, make_float4(gf, g_lin ? g_lin[b] : 0.f, 0.f, 0.f));
+    if (lir == 0 && KP >= k + 4) st4(dst + k, make_float4(gf, g_lin ? g_lin[b] : 0.f, 0.f, 0.f));
   }
 }
 
@@ -107,7 +107,7 @@ int rm_pack_grad_rows(const float* dx, const float* x, int64_t ld, const float* 
                       const float* g_lin, int64_t n, int32_t KP, const int32_t* pos, int32_t m, int32_t k, float* send,
                       void* stream) {
   using namespace rm;
-  RM_CHECK_ARG(n >= 0 && m > 0 && k > 0 && KP >= k + 4, "bad shape");
+  RM_CHECK_ARG(n >= 0 && m > 0 && k > 0 && (KP == k || KP >= k + 4), "bad shape");
   if (n == 0) return 0;
   RM_CHECK_ARG(send, "null pointer");
   RM_CHECK_ARG(!g_fm || (x && sum), "g_fm needs x and sum");

@@ -339,10 +339,13 @@ int rm_gather_fm_fwd_p2p(const float* const* tables, const float* const* bias_ta
     pt.tab[r] = r < W ? tables[r] : nullptr;
     pt.bias[r] = (r < W && bias_tables) ? bias_tables[r] : nullptr;
     pt.lin[r] = (r < W && lin_tables) ? lin_tables[r] : nullptr;
+
     RM_CHECK_ARG(r >= W || (pt.tab[r] && aligned16(pt.tab[r])), "null / misaligned peer table");
     RM_CHECK_ARG(r >= W || !bias_tables || pt.bias[r], "null peer bias table");
     RM_CHECK_ARG(r >= W || !lin_tables || pt.lin[r], "null peer linear table");
   }
+  if (tune_variant("RM_TUNE_P2P_NOSCALAR", 0))  // timing experiment only: results lack the k=1 terms
+    for (int r = 0; r < RM_MAX_PEERS; ++r) pt.bias[r] = pt.lin[r] = nullptr;
   int wshift = 0;
   while ((1 << wshift) < W) ++wshift;
   cudaStream_t st = (cudaStream_t)stream;

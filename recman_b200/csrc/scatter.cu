@@ -136,7 +136,8 @@ struct PeerRowSrc {
   static constexpr bool kScalars = true;
   static constexpr int kTailU = 2;
   const float* G[RM_MAX_PEERS];
-  uint32_t rows_per_rank;
+  const float* gscal;  // nullable: [W * samples_per_rank, 2] = (g_bias, g_lin) of EVERY rank's samples, local memory
+  uint32_t rows_per_rank, m;
   int KP, k;
   __device__ __forceinline__ void load(uint32_t gp, int c, float4& v, float& gf, float& gl) const {
     const uint32_t r = gp / rows_per_rank, lp = gp - r * rows_per_rank;
@@ -145,9 +146,15 @@ struct PeerRowSrc {
     gf = 0.f;
     gl = 0.f;
     if (c == 0) {
-      const float4 t = ldg_stream4(row + k);
-      gf = t.x;
-      gl = t.y;
+      if (gscal) {  // the two k=1 gradients are per-sample values: all-gathered once, read from local L2 here
+        const float2 t = *reinterpret_cast<const float2*>(gscal + 2 * (int64_t)(gp / m));
+        gf = t.x;
+        gl = t.y;
+      } else {
+        const float4 t = ldg_stream4(row + k);
+        gf = t.x;
+        gl = t.y;
+      }
     }
   }
 };
@@ -162,6 +169,66 @@ struct UpdateSink {
   OptParams o;
 };
 
+// Long segments (skewed ids: a hot row can collect thousands of positions of one batch).  Walking such a segment
+// serially inside one row group would take milliseconds, so segments longer than SEG_LONG positions are not summed by
+// the main kernel: it appends them to a device work list, a second kernel sums every SEG_CHUNK consecutive positions
+// (chunk boundaries are fixed relative to the segment start), and a third adds the chunk partials in chunk order and
+// finishes the row.  The result depends only on the sorted positions - deterministic run to run and independent of the
+// world size; atomics are used only to hand out slots of the work list, never on data.  oracle.segment_sum_sorted
+// restates the same association (sequential up to SEG_LONG, chunked above), which keeps the unfused kernel bit-exact.
+constexpr int SEG_LONG = 16;
+constexpr int SEG_CHUNK = 32;
+struct LongWs {
+  int32_t* counters;    // [0] long segments, [1] chunk slots handed out (nullptr = long path disabled)
+  int32_t* long_u;      // [max_long]   unique-row index of the long segment
+  int32_t* long_base;   // [max_long]   its first chunk slot
+  int32_t* chunk_long;  // [max_chunks] long-list index of the chunk slot
+  float* part_rows;     // [max_chunks, k]
+  float* part_scal;     // [max_chunks, 2]
+  int32_t max_long, max_chunks;
+};
+
+static LongWs long_layout(int64_t N, int k, void* base, size_t* total) {
+  LongWs w;
+  w.max_long = (int32_t)(N / (SEG_LONG + 1) + 1);
+  w.max_chunks = (int32_t)(N / SEG_CHUNK + w.max_long + 1);
+  char* b = (char*)base;
+  size_t off = 0;
+  w.counters = (int32_t*)(b + off); off += 256;
+  w.long_u = (int32_t*)(b + off); off += align_up((size_t)w.max_long * 4, 256);
+  w.long_base = (int32_t*)(b + off); off += align_up((size_t)w.max_long * 4, 256);
+  w.chunk_long = (int32_t*)(b + off); off += align_up((size_t)w.max_chunks * 4, 256);
+  w.part_rows = (float*)(b + off); off += align_up((size_t)w.max_chunks * k * 4, 256);
+  w.part_scal = (float*)(b + off); off += align_up((size_t)w.max_chunks * 2 * 4, 256);
+  *total = off;
+  return w;
+}
+
+// store / update of one finished row: shared by the main kernel and the long-segment combine kernel
+template <bool FUSED>
+__device__ __forceinline__ void finish_row(int64_t u, int c, int k, const float4 acc, float ba, float la,
+                                           float* __restrict__ out_rows, float* __restrict__ out_bias,
+                                           float* __restrict__ out_lin, const UpdateSink& sink, int64_t urow,
+                                           const float4 tv, float bo, float lo) {
+  if (out_rows) st4(out_rows + u * k + 4 * c, acc);
+  if (FUSED && c == 0) {
+    if (out_bias) out_bias[u] = ba;
+    if (out_lin) out_lin[u] = la;
+  }
+  if (sink.table) {
+    float4 pv = tv;
+    pv.x = opt_update(pv.x, acc.x, sink.o);
+    pv.y = opt_update(pv.y, acc.y, sink.o);
+    pv.z = opt_update(pv.z, acc.z, sink.o);
+    pv.w = opt_update(pv.w, acc.w, sink.o);
+    st4(sink.table + urow * k + 4 * c, pv);
+    if (FUSED && c == 0) {
+      if (sink.bias_table) sink.bias_table[urow] = opt_update(bo, ba, sink.o);
+      if (sink.lin_table) sink.lin_table[urow] = opt_update(lo, la, sink.o);
+    }
+  }
+}
+
 // Work distribution: a warp owns chunks of 32 consecutive unique rows.  Lane l loads the index chain of row
 // chunk*32 + l (seg_start -> sorted_pos head, uniq_rows) with coalesced loads, software-pipelined two chunks deep
 // (bounds of chunk i+2 and heads of chunk i+1 are requested while the rows of chunk i are in flight), and the row
@@ -172,7 +239,7 @@ template <int LPR, int UBT, int U, int MINB, class Src>
 __global__ void __launch_bounds__(256, MINB) segment_reduce_kernel(
     const Src src, int k, const int32_t* __restrict__ sorted_pos, const int32_t* __restrict__ seg_start,
     const int32_t* __restrict__ n_unique, float* __restrict__ out_rows, float* __restrict__ out_bias,
-    float* __restrict__ out_lin, const UpdateSink sink) {
+    float* __restrict__ out_lin, const UpdateSink sink, const LongWs lw) {
   constexpr bool FUSED = Src::kScalars;
   constexpr int GPW = 32 / LPR;              // row groups per warp
   constexpr int UB = UBT < LPR ? UBT : LPR;  // segments in flight per group (a group owns LPR segments per chunk)
@@ -236,6 +303,17 @@ __global__ void __launch_bounds__(256, MINB) segment_reduce_kernel(
         p0[j] = __shfl_sync(FULL, hp, sl);
         urow[j] = __shfl_sync(FULL, ur, sl);
         live[j] = col && (ub + sl < NU);
+        if (lw.counters && e[j] - s[j] > SEG_LONG && ub + sl < NU) {  // long segment: hand it to the chunked path
+          if (lir == 0) {
+            const int nc = (e[j] - s[j] + SEG_CHUNK - 1) / SEG_CHUNK;
+            const int li = atomicAdd(lw.counters, 1);
+            const int base = atomicAdd(lw.counters + 1, nc);
+            lw.long_u[li] = (int32_t)(ub + sl);
+            lw.long_base[li] = base;
+            for (int t = 0; t < nc; ++t) lw.chunk_long[base + t] = li;
+          }
+          live[j] = false;
+        }
       }
       float4 acc[UB], tv[UB];
       float ba[UB], la[UB], bo[UB], lo[UB];
@@ -284,28 +362,105 @@ __global__ void __launch_bounds__(256, MINB) segment_reduce_kernel(
       for (int j = 0; j < UB; ++j) {
         if (live[j]) {
           const int64_t u = ub + giw + GPW * (t0 + j);
-          if (out_rows) st4(out_rows + u * k + 4 * c, acc[j]);
-          if (FUSED && c == 0) {
-            if (out_bias) out_bias[u] = ba[j];
-            if (out_lin) out_lin[u] = la[j];
-          }
-          if (upd) {
-            float4 pv = tv[j];
-            pv.x = opt_update(pv.x, acc[j].x, sink.o);
-            pv.y = opt_update(pv.y, acc[j].y, sink.o);
-            pv.z = opt_update(pv.z, acc[j].z, sink.o);
-            pv.w = opt_update(pv.w, acc[j].w, sink.o);
-            st4(sink.table + urow[j] * k + 4 * c, pv);
-            if (FUSED && c == 0) {
-              if (sink.bias_table) sink.bias_table[urow[j]] = opt_update(bo[j], ba[j], sink.o);
-              if (sink.lin_table) sink.lin_table[urow[j]] = opt_update(lo[j], la[j], sink.o);
-            }
-          }
+          finish_row<FUSED>(u, c, k, acc[j], ba[j], la[j], out_rows, out_bias, out_lin, sink, urow[j], tv[j], bo[j],
+                            lo[j]);
         }
       }
     }
     sA = nA; sB = nB; hp = nhp; ur = nur;
     nA = n2A; nB = n2B;
+  }
+}
+
+// long segments, pass 2: one row group per chunk slot sums its SEG_CHUNK positions in ascending order
+template <int LPR, class Src>
+__global__ void __launch_bounds__(256) segment_chunk_kernel(const Src src, int k,
+                                                            const int32_t* __restrict__ sorted_pos,
+                                                            const int32_t* __restrict__ seg_start, const LongWs lw) {
+  constexpr int U = 4;
+  const int lir = threadIdx.x % LPR;
+  const int c = lir;
+  const bool col = c < (k >> 2);
+  const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / LPR;
+  const int32_t n_chunks = lw.counters[1];
+  for (int64_t slot = group; slot < n_chunks; slot += n_groups) {
+    const int li = lw.chunk_long[slot];
+    const int u = lw.long_u[li];
+    const int jc = (int)slot - lw.long_base[li];
+    const int32_t s = seg_start[u] + jc * SEG_CHUNK;
+    const int32_t e_seg = seg_start[u + 1];
+    const int32_t e = s + SEG_CHUNK < e_seg ? s + SEG_CHUNK : e_seg;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ba = 0.f, la = 0.f;
+    if (col) {
+      for (int32_t j0 = s; j0 < e; j0 += U) {
+        float4 v[U];
+        float gf[U], gl[U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          gf[i] = 0.f;
+          gl[i] = 0.f;
+          if (j0 + i < e) src.load((uint32_t)sorted_pos[j0 + i], c, v[i], gf[i], gl[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+          if (j0 + i < e) {
+            acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w;
+            ba += gf[i];
+            la += gl[i];
+          }
+        }
+      }
+      st4(lw.part_rows + slot * k + 4 * c, acc);
+      if (c == 0) *reinterpret_cast<float2*>(lw.part_scal + 2 * slot) = make_float2(ba, la);
+    }
+  }
+}
+
+// long segments, pass 3: one row group per long segment adds its chunk partials in chunk order and finishes the row
+template <int LPR, class Src>
+__global__ void __launch_bounds__(256) segment_combine_kernel(int k, const int32_t* __restrict__ seg_start,
+                                                              float* __restrict__ out_rows,
+                                                              float* __restrict__ out_bias,
+                                                              float* __restrict__ out_lin, const UpdateSink sink,
+                                                              const LongWs lw) {
+  constexpr bool FUSED = Src::kScalars;
+  const int lir = threadIdx.x % LPR;
+  const int c = lir;
+  const bool col = c < (k >> 2);
+  const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / LPR;
+  const int32_t n_long = lw.counters[0];
+  for (int64_t li = group; li < n_long; li += n_groups) {
+    const int u = lw.long_u[li];
+    const int base = lw.long_base[li];
+    const int nc = (seg_start[u + 1] - seg_start[u] + SEG_CHUNK - 1) / SEG_CHUNK;
+    if (!col) continue;
+    int64_t urow = 0;
+    float4 tv = make_float4(0.f, 0.f, 0.f, 0.f);
+    float bo = 0.f, lo = 0.f;
+    if (sink.table) {
+      urow = sink.uniq_rows[u];
+      tv = ld4(sink.table + urow * k + 4 * c);
+      if (FUSED && c == 0) {
+        if (sink.bias_table) bo = sink.bias_table[urow];
+        if (sink.lin_table) lo = sink.lin_table[urow];
+      }
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ba = 0.f, la = 0.f;
+    for (int t = 0; t < nc; ++t) {
+      const float4 v = ld4(lw.part_rows + (int64_t)(base + t) * k + 4 * c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      if (FUSED && c == 0) {
+        const float2 sc = *reinterpret_cast<const float2*>(lw.part_scal + 2 * (int64_t)(base + t));
+        ba += sc.x;
+        la += sc.y;
+      }
+    }
+    finish_row<FUSED>(u, c, k, acc, ba, la, out_rows, out_bias, out_lin, sink, urow, tv, bo, lo);
   }
 }
 
@@ -320,11 +475,22 @@ __global__ void __launch_bounds__(256) segment_reduce_scalar_kernel(const float*
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t u = i / k;
     const uint32_t c = (uint32_t)(i - u * k);
-    float acc = 0.f;
-    for (int32_t j = seg_start[u]; j < seg_start[u + 1]; ++j) {
+    const int32_t s = seg_start[u], e = seg_start[u + 1];
+    auto at = [&](int32_t j) {
       const uint32_t p = (uint32_t)sorted_pos[j];
       const uint32_t b = p / m, f = p - b * m;
-      acc += grad[(int64_t)b * ld + (int64_t)f * k + c];
+      return grad[(int64_t)b * ld + (int64_t)f * k + c];
+    };
+    float acc = 0.f;
+    if (e - s <= SEG_LONG) {
+      for (int32_t j = s; j < e; ++j) acc += at(j);
+    } else {  // same association as the chunked long-segment path of the vector kernels
+      for (int32_t c0 = s; c0 < e; c0 += SEG_CHUNK) {
+        float part = 0.f;
+        const int32_t ce = c0 + SEG_CHUNK < e ? c0 + SEG_CHUNK : e;
+        for (int32_t j = c0; j < ce; ++j) part += at(j);
+        acc += part;
+      }
     }
     out_rows[i] = acc;
   }
@@ -339,19 +505,28 @@ static inline int pow2ceil__(int v) {
 template <int LPR, class Src>
 static int launch_segment_reduce(const Src& src, int k, int64_t N, const int32_t* sorted_pos, const int32_t* seg_start,
                                  const int32_t* n_unique, float* out_rows, float* out_bias, float* out_lin,
-                                 const UpdateSink& sink, int dflt_variant, cudaStream_t st) {
+                                 const UpdateSink& sink, int dflt_variant, const LongWs& lw, cudaStream_t st) {
   const int variant = tune_variant("RM_TUNE_SEGRED", dflt_variant);  // measured best on B200 (profiles/r1_kbench.json)
   // n_unique <= N lives on the device: the grid is sized for the worst case (a CTA iteration = 8 warps x 32 rows)
   const int grid = grid_for(N, 256, 8);
+  if (lw.counters) RM_CUDA(cudaMemsetAsync(lw.counters, 0, 2 * sizeof(int32_t), st));
 #define RM_SRK(UB, MINB)                                                                                         \
   segment_reduce_kernel<LPR, UB, Src::kTailU, MINB, Src><<<grid, 256, 0, st>>>(src, k, sorted_pos, seg_start, n_unique, \
-                                                                     out_rows, out_bias, out_lin, sink)
+                                                                     out_rows, out_bias, out_lin, sink, lw)
   if (variant == 1) RM_SRK(1, 4);
   else if (variant == 2) RM_SRK(2, 4);
   else if (variant == 3) RM_SRK(2, 3);
   else RM_SRK(4, 2);
 #undef RM_SRK
   RM_LAUNCH_CHECK();
+  if (lw.counters) {
+    // worst-case grids (the counts live on the device); both kernels exit at once when nothing was queued
+    segment_chunk_kernel<LPR, Src><<<grid_for(lw.max_chunks, 256 / LPR, 8), 256, 0, st>>>(src, k, sorted_pos, seg_start, lw);
+    RM_LAUNCH_CHECK();
+    segment_combine_kernel<LPR, Src><<<grid_for(lw.max_long, 256 / LPR, 8), 256, 0, st>>>(k, seg_start, out_rows, out_bias,
+                                                                                      out_lin, sink, lw);
+    RM_LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -359,13 +534,13 @@ template <class Src>
 static int dispatch_segment_reduce(const Src& src, int k, int64_t N, const int32_t* sorted_pos,
                                    const int32_t* seg_start, const int32_t* n_unique, float* out_rows,
                                    float* out_bias, float* out_lin, const UpdateSink& sink, int dflt_variant,
-                                   cudaStream_t st) {
+                                   const LongWs& lw, cudaStream_t st) {
   int lpr = pow2ceil__(k / 4);
   if (lpr > 32) lpr = 32;
 #define RM_SR(L)                                                                                              \
   case L:                                                                                                     \
     return launch_segment_reduce<L, Src>(src, k, N, sorted_pos, seg_start, n_unique, out_rows, out_bias,       \
-                                         out_lin, sink, dflt_variant, st)
+                                         out_lin, sink, dflt_variant, lw, st)
   switch (lpr) {
     RM_SR(1);
     RM_SR(2);
@@ -374,7 +549,7 @@ static int dispatch_segment_reduce(const Src& src, int k, int64_t N, const int32
     RM_SR(16);
     default:
       return launch_segment_reduce<32, Src>(src, k, N, sorted_pos, seg_start, n_unique, out_rows, out_bias, out_lin,
-                                            sink, dflt_variant, st);
+                                            sink, dflt_variant, lw, st);
   }
 #undef RM_SR
 }
@@ -483,6 +658,32 @@ static ShardPlanWs shard_plan_layout(int64_t Ntot, int64_t N_cap, void* base) {
 
 extern "C" {
 
+// long-segment workspace of the reduce entry points (NULL workspace = long path disabled: every segment is walked
+// serially, fine for near-uniform ids)
+static int long_ws_from(void* workspace, size_t workspace_bytes, int64_t N, int k, const char* who, rm::LongWs* lw) {
+  using namespace rm;
+  *lw = LongWs{};
+  if (!workspace) return 0;
+  size_t total = 0;
+  *lw = long_layout(N, k, workspace, &total);
+  if (workspace_bytes < total) {
+    set_error("%s: workspace %zu < required %zu", who, workspace_bytes, total);
+    return RM_E_WORKSPACE;
+  }
+  if (!aligned16(workspace)) {
+    set_error("%s: workspace must be 16-byte aligned", who);
+    return RM_E_INVALID;
+  }
+  return 0;
+}
+
+size_t rm_segment_reduce_workspace_bytes(int64_t N, int32_t k) {
+  if (N <= 0 || k <= 0) return 256;
+  size_t total = 0;
+  rm::long_layout(N, k, nullptr, &total);
+  return total;
+}
+
 size_t rm_segment_plan_workspace_bytes(int64_t N) {
   if (N <= 0) return 256;
   return rm::plan_layout(N, nullptr).total;
@@ -529,7 +730,8 @@ int rm_segment_plan(const int64_t* ids, const int64_t* table_offsets, int64_t N,
 }
 
 int rm_segment_reduce(const float* grad, int64_t ld, int32_t m, int32_t k, int64_t N, const int32_t* sorted_pos,
-                      const int32_t* seg_start, const int32_t* n_unique, float* out_rows, void* stream) {
+                      const int32_t* seg_start, const int32_t* n_unique, float* out_rows, void* workspace,
+                      size_t workspace_bytes, void* stream) {
   using namespace rm;
   RM_CHECK_ARG(grad && sorted_pos && seg_start && n_unique && out_rows, "null pointer");
   RM_CHECK_ARG(N >= 0 && m > 0 && k > 0 && ld >= (int64_t)m * k, "bad shape");
@@ -538,8 +740,11 @@ int rm_segment_reduce(const float* grad, int64_t ld, int32_t m, int32_t k, int64
   const bool vec = (k % 4 == 0) && (k <= 128) && (ld % 4 == 0) && aligned16(grad) && aligned16(out_rows);
   if (vec) {
     const RowSrc<false> src{grad, nullptr, nullptr, nullptr, nullptr, ld, (uint32_t)m, k};
+    LongWs lw;
+    const int rc = long_ws_from(workspace, workspace_bytes, N, k, "rm_segment_reduce", &lw);
+    if (rc) return rc;
     return dispatch_segment_reduce(src, k, N, sorted_pos, seg_start, n_unique, out_rows, nullptr, nullptr, UpdateSink{}, 2,
-                                   st);
+                                   lw, st);
   }
   segment_reduce_scalar_kernel<<<grid_for(N * k, 256, 8), 256, 0, st>>>(grad, ld, (uint32_t)m, (uint32_t)k, sorted_pos,
                                                                         seg_start, n_unique, out_rows);
@@ -550,7 +755,8 @@ int rm_segment_reduce(const float* grad, int64_t ld, int32_t m, int32_t k, int64
 static int emb_fm_bwd_impl(const float* dx, const float* x, int64_t ld, const float* sum, const float* g_fm,
                            const float* g_lin, int32_t m, int32_t k, int64_t N, const int32_t* sorted_pos,
                            const int32_t* seg_start, const int32_t* n_unique, float* out_rows, float* out_bias,
-                           float* out_lin, const rm::UpdateSink& sink, void* stream) {
+                           float* out_lin, const rm::UpdateSink& sink, void* workspace, size_t workspace_bytes,
+                           void* stream) {
   using namespace rm;
   RM_CHECK_ARG(sorted_pos && seg_start && n_unique, "null pointer");
   RM_CHECK_ARG(N >= 0 && m > 0 && k > 0 && ld >= (int64_t)m * k, "bad shape");
@@ -561,28 +767,33 @@ static int emb_fm_bwd_impl(const float* dx, const float* x, int64_t ld, const fl
                  "fused embedding backward needs k % 4 == 0, k <= 128 and 16-byte aligned rows");
   if (N == 0) return 0;
   const RowSrc<true> src{dx, x, sum, g_fm, g_lin, ld, (uint32_t)m, k};
-  return dispatch_segment_reduce(src, k, N, sorted_pos, seg_start, n_unique, out_rows, out_bias, out_lin, sink, 1,
+  LongWs lw;
+  const int rc = long_ws_from(workspace, workspace_bytes, N, k, "rm_emb_fm_bwd", &lw);
+  if (rc) return rc;
+  return dispatch_segment_reduce(src, k, N, sorted_pos, seg_start, n_unique, out_rows, out_bias, out_lin, sink, 1, lw,
                                  (cudaStream_t)stream);
 }
 
 int rm_emb_fm_bwd(const float* dx, const float* x, int64_t ld, const float* sum, const float* g_fm, const float* g_lin,
                   int32_t m, int32_t k, int64_t N, const int32_t* sorted_pos, const int32_t* seg_start,
-                  const int32_t* n_unique, float* out_rows, float* out_bias, float* out_lin, void* stream) {
+                  const int32_t* n_unique, float* out_rows, float* out_bias, float* out_lin, void* workspace,
+                  size_t workspace_bytes, void* stream) {
   return emb_fm_bwd_impl(dx, x, ld, sum, g_fm, g_lin, m, k, N, sorted_pos, seg_start, n_unique, out_rows, out_bias,
-                         out_lin, rm::UpdateSink{}, stream);
+                         out_lin, rm::UpdateSink{}, workspace, workspace_bytes, stream);
 }
 
 int rm_emb_fm_bwd_update(const float* dx, const float* x, int64_t ld, const float* sum, const float* g_fm,
                          const float* g_lin, int32_t m, int32_t k, int64_t N, const int32_t* sorted_pos,
                          const int32_t* seg_start, const int64_t* uniq_rows, const int32_t* n_unique, float* table,
-                         float* bias_table, float* lin_table, int32_t opt, float lr, float l2, void* stream) {
+                         float* bias_table, float* lin_table, int32_t opt, float lr, float l2, void* workspace,
+                         size_t workspace_bytes, void* stream) {
   using namespace rm;
   RM_CHECK_ARG(table && uniq_rows, "null pointer");
   UpdateSink sink{table, g_fm ? bias_table : nullptr, g_lin ? lin_table : nullptr, uniq_rows, OptParams{}};
   const int rc = make_params(opt, lr, l2, &sink.o);
   if (rc) return rc;
   return emb_fm_bwd_impl(dx, x, ld, sum, g_fm, g_lin, m, k, N, sorted_pos, seg_start, n_unique, nullptr, nullptr,
-                         nullptr, sink, stream);
+                         nullptr, sink, workspace, workspace_bytes, stream);
 }
 
 size_t rm_shard_plan_workspace_bytes(int64_t Ntot, int64_t N_cap) {
@@ -634,13 +845,16 @@ int rm_shard_plan(const int64_t* gids, int64_t Ntot, int32_t m, int32_t W, int32
   return 0;
 }
 
-static int segment_reduce_p2p_impl(const float* const* G, int32_t W, int64_t rows_per_rank, int32_t KP, int32_t k,
-                                   int64_t N_cap, const int32_t* sorted_gpos, const int32_t* seg_start,
+static int segment_reduce_p2p_impl(const float* const* G, const float* gscal, int32_t m, int32_t W,
+                                   int64_t rows_per_rank, int32_t KP, int32_t k, int64_t N_cap, const int32_t* sorted_gpos, const int32_t* seg_start,
                                    const int32_t* n_unique, float* out_rows, float* out_bias, float* out_lin,
-                                   const rm::UpdateSink& sink, void* stream) {
+                                   const rm::UpdateSink& sink, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
   using namespace rm;
   RM_CHECK_ARG(G && sorted_gpos && seg_start && n_unique, "null pointer");
-  RM_CHECK_ARG(W >= 1 && W <= RM_MAX_PEERS && rows_per_rank > 0 && k > 0 && KP >= k + 4 && N_cap >= 0, "bad shape");
+  RM_CHECK_ARG(W >= 1 && W <= RM_MAX_PEERS && rows_per_rank > 0 && k > 0 && N_cap >= 0, "bad shape");
+  RM_CHECK_ARG(gscal ? (KP >= k && m > 0 && rows_per_rank % m == 0) : KP >= k + 4,
+               "rows need their two k=1 columns (KP >= k + 4) unless the per-sample scalars are passed");
   RM_UNSUPPORTED(k % 4 == 0 && k <= 128 && KP % 4 == 0 && (!out_rows || aligned16(out_rows)) &&
                      (!sink.table || aligned16(sink.table)),
                  "peer segment reduce needs k % 4 == 0 and 16-byte aligned rows");
@@ -652,30 +866,37 @@ static int segment_reduce_p2p_impl(const float* const* G, int32_t W, int64_t row
     RM_CHECK_ARG(r >= W || (G[r] && aligned16(G[r])), "null / misaligned peer buffer");
   }
   src.rows_per_rank = (uint32_t)rows_per_rank;
+  src.gscal = gscal;
+  src.m = (uint32_t)(m > 0 ? m : 1);
   src.KP = KP;
   src.k = k;
+  LongWs lw;
+  const int rcw = long_ws_from(workspace, workspace_bytes, N_cap, k, "rm_segment_reduce_p2p", &lw);
+  if (rcw) return rcw;
   return dispatch_segment_reduce(src, k, N_cap, sorted_gpos, seg_start, n_unique, out_rows, out_bias, out_lin, sink, 1,
-                                 (cudaStream_t)stream);
+                                 lw, (cudaStream_t)stream);
 }
 
-int rm_segment_reduce_p2p(const float* const* G, int32_t W, int64_t rows_per_rank, int32_t KP, int32_t k,
-                          int64_t N_cap, const int32_t* sorted_gpos, const int32_t* seg_start,
-                          const int32_t* n_unique, float* out_rows, float* out_bias, float* out_lin, void* stream) {
-  return segment_reduce_p2p_impl(G, W, rows_per_rank, KP, k, N_cap, sorted_gpos, seg_start, n_unique, out_rows,
-                                 out_bias, out_lin, rm::UpdateSink{}, stream);
+int rm_segment_reduce_p2p(const float* const* G, const float* gscal, int32_t m, int32_t W, int64_t rows_per_rank,
+                          int32_t KP, int32_t k, int64_t N_cap, const int32_t* sorted_gpos, const int32_t* seg_start,
+                          const int32_t* n_unique, float* out_rows, float* out_bias, float* out_lin, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  return segment_reduce_p2p_impl(G, gscal, m, W, rows_per_rank, KP, k, N_cap, sorted_gpos, seg_start, n_unique,
+                                 out_rows, out_bias, out_lin, rm::UpdateSink{}, workspace, workspace_bytes, stream);
 }
 
-int rm_segment_reduce_p2p_update(const float* const* G, int32_t W, int64_t rows_per_rank, int32_t KP, int32_t k,
-                                 int64_t N_cap, const int32_t* sorted_gpos, const int32_t* seg_start,
+int rm_segment_reduce_p2p_update(const float* const* G, const float* gscal, int32_t m, int32_t W,
+                                 int64_t rows_per_rank, int32_t KP, int32_t k, int64_t N_cap, const int32_t* sorted_gpos, const int32_t* seg_start,
                                  const int64_t* uniq_rows, const int32_t* n_unique, float* table, float* bias_table,
-                                 float* lin_table, int32_t opt, float lr, float l2, void* stream) {
+                                 float* lin_table, int32_t opt, float lr, float l2, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
   using namespace rm;
   RM_CHECK_ARG(table && uniq_rows, "null pointer");
   UpdateSink sink{table, bias_table, lin_table, uniq_rows, OptParams{}};
   const int rc = make_params(opt, lr, l2, &sink.o);
   if (rc) return rc;
-  return segment_reduce_p2p_impl(G, W, rows_per_rank, KP, k, N_cap, sorted_gpos, seg_start, n_unique, nullptr, nullptr,
-                                 nullptr, sink, stream);
+  return segment_reduce_p2p_impl(G, gscal, m, W, rows_per_rank, KP, k, N_cap, sorted_gpos, seg_start, n_unique,
+                                 nullptr, nullptr, nullptr, sink, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

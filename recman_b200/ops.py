@@ -234,6 +234,12 @@ def segment_plan(ids, table_offsets, total_rows, side: bool = False) -> SegmentP
     return SegmentPlan(N, m, sorted_pos, seg_start, uniq_rows, n_unique, ws, ev)
 
 
+def _reduce_ws(plan: SegmentPlan, k: int):
+    """Workspace of the chunked long-segment path (hot rows under skewed ids)."""
+    n = _C.lib.rm_segment_reduce_workspace_bytes(max(plan.N, 1), k)
+    return torch.empty(n, dtype=torch.uint8, device=plan.sorted_pos.device), n
+
+
 def segment_reduce(grad, plan: SegmentPlan, k: int, ld: Optional[int] = None, out_rows=None):
     """grad rows addressed as grad[(p//m)*ld + (p%m)*k] -> summed rows [N, k] (first n_unique valid)."""
     _dev_check(grad)
@@ -245,9 +251,10 @@ def segment_reduce(grad, plan: SegmentPlan, k: int, ld: Optional[int] = None, ou
     if out_rows is None:
         out_rows = torch.empty(max(plan.N, 1), k, dtype=torch.float32, device=grad.device)
     plan.wait()
+    ws, wsn = _reduce_ws(plan, k)
     _C.call(
         "rm_segment_reduce", _p(grad), ld, plan.m, k, plan.N, _p(plan.sorted_pos), _p(plan.seg_start),
-        _p(plan.n_unique), _p(out_rows), _stream(),
+        _p(plan.n_unique), _p(out_rows), _p(ws), wsn, _stream(),
     )
     return out_rows
 
@@ -259,30 +266,34 @@ def emb_fm_bwd(dx, x, ld, S, g_fm, g_lin, plan: SegmentPlan, k, want_rows=True, 
     out_bias = torch.empty(n, dtype=torch.float32, device=dev) if want_bias else None
     out_lin = torch.empty(n, dtype=torch.float32, device=dev) if want_lin else None
     plan.wait()
+    ws, wsn = _reduce_ws(plan, k)
     _C.call(
         "rm_emb_fm_bwd", _p(dx), _p(x), ld, _p(S), _p(g_fm), _p(g_lin), plan.m, k, plan.N, _p(plan.sorted_pos),
-        _p(plan.seg_start), _p(plan.n_unique), _p(out_rows), _p(out_bias), _p(out_lin), _stream(),
+        _p(plan.seg_start), _p(plan.n_unique), _p(out_rows), _p(out_bias), _p(out_lin), _p(ws), wsn, _stream(),
     )
     return out_rows, out_bias, out_lin
 
 
 def segment_reduce_p2p_update(G_ptrs, rows_per_rank, KP, k, plan: SegmentPlan, table, bias_table, lin_table, opt, lr,
-                              l2=0.0):
+                              l2=0.0, gscal=None, m=1):
     plan.wait()
+    ws, wsn = _reduce_ws(plan, k)
     _C.call(
-        "rm_segment_reduce_p2p_update", _ptr_array(G_ptrs), len(G_ptrs), int(rows_per_rank), KP, k, plan.N,
+        "rm_segment_reduce_p2p_update", _ptr_array(G_ptrs), _p(gscal), int(m), len(G_ptrs), int(rows_per_rank), KP, k,
+        plan.N,
         _p(plan.sorted_pos), _p(plan.seg_start), _p(plan.uniq_rows), _p(plan.n_unique), _p(table), _p(bias_table),
-        _p(lin_table), opt, float(lr), float(l2), _stream(),
+        _p(lin_table), opt, float(lr), float(l2), _p(ws), wsn, _stream(),
     )
 
 
 def emb_fm_bwd_update(dx, x, ld, S, g_fm, g_lin, plan: SegmentPlan, k, table, bias_table, lin_table, opt, lr, l2=0.0):
     """rm_emb_fm_bwd + rm_sparse_opt_step in one pass: the tables are updated in place, nothing is returned."""
     plan.wait()
+    ws, wsn = _reduce_ws(plan, k)
     _C.call(
         "rm_emb_fm_bwd_update", _p(dx), _p(x), ld, _p(S), _p(g_fm), _p(g_lin), plan.m, k, plan.N, _p(plan.sorted_pos),
         _p(plan.seg_start), _p(plan.uniq_rows), _p(plan.n_unique), _p(table), _p(bias_table), _p(lin_table), opt,
-        float(lr), float(l2), _stream(),
+        float(lr), float(l2), _p(ws), wsn, _stream(),
     )
 
 
@@ -489,7 +500,8 @@ def unpack_rows(recv, pos, m, k, x, bias_out=None, lin_out=None):
 
 
 def pack_grad_rows(dx, x, ld, S, g_fm, g_lin, pos, m, k, KP, out=None, n=None):
-    """Gradient rows [n, KP] = [dx + g_fm*(S - x) | g_fm | g_lin | 0 | 0]; ``pos`` None keeps position order."""
+    """Gradient rows [n, KP] = [dx + g_fm*(S - x) | g_fm | g_lin | 0 | 0] (KP = k: no scalar columns); ``pos`` None
+    keeps position order."""
     if n is None:
         n = pos.numel()
     send = out if out is not None else torch.empty(n, KP, dtype=torch.float32, device=x.device)
@@ -558,15 +570,18 @@ def shard_plan(gids, W, rank, feat_sizes, local_offs, total_local, n_cap, status
     return plan
 
 
-def segment_reduce_p2p(G_ptrs, rows_per_rank, KP, k, plan: SegmentPlan, want_bias=True, want_lin=True):
+def segment_reduce_p2p(G_ptrs, rows_per_rank, KP, k, plan: SegmentPlan, want_bias=True, want_lin=True, gscal=None,
+                       m=1):
     dev = plan.sorted_pos.device
     n = max(plan.N, 1)
     out_rows = torch.empty(n, k, dtype=torch.float32, device=dev)
     out_bias = torch.empty(n, dtype=torch.float32, device=dev) if want_bias else None
     out_lin = torch.empty(n, dtype=torch.float32, device=dev) if want_lin else None
     plan.wait()
+    ws, wsn = _reduce_ws(plan, k)
     _C.call(
-        "rm_segment_reduce_p2p", _ptr_array(G_ptrs), len(G_ptrs), int(rows_per_rank), KP, k, plan.N,
-        _p(plan.sorted_pos), _p(plan.seg_start), _p(plan.n_unique), _p(out_rows), _p(out_bias), _p(out_lin), _stream(),
+        "rm_segment_reduce_p2p", _ptr_array(G_ptrs), _p(gscal), int(m), len(G_ptrs), int(rows_per_rank), KP, k, plan.N,
+        _p(plan.sorted_pos), _p(plan.seg_start), _p(plan.n_unique), _p(out_rows), _p(out_bias), _p(out_lin), _p(ws),
+        wsn, _stream(),
     )
     return out_rows, out_bias, out_lin

@@ -346,20 +346,27 @@ class P2PFrontEndFunction(Function):
         if sp is None:
             sp = ops.shard_plan(gids, plan.world, plan.rank, plan.feat_sizes_on(dev), plan.offsets_on(dev),
                                 plan.total_local, plan.capacity(b), ctx.status)
-        G = plan.grad_buffer(b * m, KP)
-        ops.pack_grad_rows(dx, x, ld, S, g_fm, g_lin, None, m, k, KP, out=G, n=b * m)
-        dist.all_reduce(plan.flag(dev), group=plan.group)  # every rank's G is complete
+        # gradient rows are exactly k floats (256-byte rows at k = 64: one NVLink request fewer per row than k+4); the two
+        # k=1 gradients are per-sample values and travel once, in the all-gather that also says "every G is complete"
+        G = plan.grad_buffer(b * m, k)
+        ops.pack_grad_rows(dx, x, ld, S, g_fm, g_lin, None, m, k, k, out=G, n=b * m)
+        zeros = None
+        if g_fm is None or g_lin is None:
+            zeros = torch.zeros(b, dtype=torch.float32, device=dev)
+        gs = torch.stack([g_fm if g_fm is not None else zeros, g_lin if g_lin is not None else zeros], dim=1)
+        gscal = torch.empty(plan.world * b, 2, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(gscal, gs.contiguous(), group=plan.group)
         want_bias = ctx.bias_table is not None and g_fm is not None
         want_lin = ctx.has_lin and ctx.W_lin is not None and g_lin is not None
         if ctx.has_lin_dense and ctx.W_lin is not None and g_lin is not None:
             ctx.W_lin.rm_dense_tail = (plan.total_local, dense.t() @ g_lin)
         if ctx.fused_opt is not None:
             kind, lr = ctx.fused_opt
-            ops.segment_reduce_p2p_update(plan.peer.ptrs_of(G), b * m, KP, k, sp, ctx.table.data,
+            ops.segment_reduce_p2p_update(plan.peer.ptrs_of(G), b * m, k, k, sp, ctx.table.data,
                                           ctx.bias_table.data if want_bias else None,
-                                          ctx.lin_table if want_lin else None, kind, lr)
+                                          ctx.lin_table if want_lin else None, kind, lr, gscal=gscal, m=m)
             return (None,) * 10
-        rows, ob, ol = ops.segment_reduce_p2p(plan.peer.ptrs_of(G), b * m, KP, k, sp, want_bias, want_lin)
+        rows, ob, ol = ops.segment_reduce_p2p(plan.peer.ptrs_of(G), b * m, k, k, sp, want_bias, want_lin, gscal=gscal, m=m)
         attach_sparse_grad(ctx.table, ops.SparseGrad(sp.uniq_rows, rows, sp.n_unique))
         if want_bias:
             attach_sparse_grad(ctx.bias_table, ops.SparseGrad(sp.uniq_rows, ob, sp.n_unique))

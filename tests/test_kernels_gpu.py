@@ -356,3 +356,50 @@ def test_narrow_linear_backward_kernels(B, d, N):
     dW = ops.linear_bwd_weight(x.cuda(), ld, d, gy.cuda())
     assert_close(dW, x[:, :d].double().t() @ gy.double(), rtol=1e-5, atol_scale=2e-6)
     assert torch.equal(dW, ops.linear_bwd_weight(x.cuda(), ld, d, gy.cuda()))  # run-to-run bit-identical
+
+
+@pytest.mark.parametrize("k", [16, 64])
+def test_hot_rows_take_the_chunked_long_segment_path(k):
+    """Skewed ids: a few rows collect hundreds to thousands of positions.  Long segments are summed chunk-wise (64
+    positions per row group, partials in chunk order) - same association as the oracle, so still bit-exact - and the
+    fused-update variant equals reduce + optimizer step."""
+    ops = _ops()
+    from recman_b200 import _C
+
+    rng = np.random.RandomState(5)
+    sizes = [1000, 50, 7]
+    m, B = len(sizes), 3000
+    offs = torch.tensor([0] + list(np.cumsum(sizes)), dtype=torch.int64)
+    ids = np.stack([(rng.zipf(1.3, size=B) - 1) % v for v in sizes], 1).astype(np.int64)
+    ids[:, 2] = 3  # one segment of 3000 positions = 94 chunks
+    g = torch.Generator().manual_seed(6)
+    grad = torch.randn(B, m, k, generator=g)
+    keys = oracle.global_rows(ids, offs.numpy()).reshape(-1)
+    uniq, sums, order, seg = oracle.segment_sum_sorted(keys, grad.reshape(-1, k).numpy())
+    assert int(np.diff(seg).max()) == B and (np.diff(seg) > oracle.segment.SEG_LONG).sum() >= 3
+    plan = ops.segment_plan(torch.from_numpy(ids).cuda(), offs.cuda(), int(offs[-1]))
+    n = plan.num_unique()
+    rows = ops.segment_reduce(grad.cuda(), plan, k)
+    assert np.array_equal(rows[:n].cpu().numpy(), sums)
+    assert torch.equal(rows[:n], ops.segment_reduce(grad.cuda(), plan, k)[:n])  # run-to-run identical
+    dense = oracle.dense_table_grad(keys, grad.reshape(-1, k).numpy(), int(offs[-1]))
+    assert_close(rows[:n], torch.from_numpy(dense[uniq]), rtol=1e-5, atol_scale=2e-6)
+    # fused FM backward + update on the same plan == unfused reduce followed by the optimizer kernels
+    ld = m * k
+    x = torch.randn(B, ld, generator=g).cuda()
+    dx = torch.randn(B, ld, generator=g).cuda()
+    S = x.view(B, m, k).sum(1).contiguous()
+    g_fm, g_lin = torch.randn(B, generator=g).cuda(), torch.randn(B, generator=g).cuda()
+    total = int(offs[-1])
+    tab = torch.randn(total, k, generator=g).cuda()
+    bt, lt = torch.randn(total, generator=g).cuda(), torch.randn(total, generator=g).cuda()
+    tab2, bt2, lt2 = tab.clone(), bt.clone(), lt.clone()
+    r, ob, ol = ops.emb_fm_bwd(dx, x, ld, S, g_fm, g_lin, plan, k, True, True, True)
+    exp_rows = (dx.view(B, m, k) + g_fm[:, None, None] * (S[:, None, :] - x.view(B, m, k))).reshape(-1, k)
+    dense2 = oracle.dense_table_grad(keys, exp_rows.cpu().numpy(), total)
+    assert_close(r[:n], torch.from_numpy(dense2[uniq]), rtol=1e-5, atol_scale=5e-6)
+    ops.sparse_opt_step(tab, ops.SparseGrad(plan.uniq_rows, r, plan.n_unique), _C.OPT_KINDS["adam"], 0.01)
+    ops.sparse_opt_step(bt, ops.SparseGrad(plan.uniq_rows, ob, plan.n_unique), _C.OPT_KINDS["adam"], 0.01)
+    ops.sparse_opt_step(lt, ops.SparseGrad(plan.uniq_rows, ol, plan.n_unique), _C.OPT_KINDS["adam"], 0.01)
+    ops.emb_fm_bwd_update(dx, x, ld, S, g_fm, g_lin, plan, k, tab2, bt2, lt2, _C.OPT_KINDS["adam"], 0.01)
+    assert torch.equal(tab, tab2) and torch.equal(bt, bt2) and torch.equal(lt, lt2)

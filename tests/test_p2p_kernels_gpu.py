@@ -130,3 +130,35 @@ def test_shard_plan_capacity_overflow_is_flagged():
     st.zero_()
     plan1 = ops.shard_plan(gids, W, 1, fs, lo, 15, 200, st)  # rank 1 owns nothing
     assert int(plan1.n_own.item()) == 0 and int(plan1.n_unique.item()) == 0 and int(st.item()) == 0
+
+
+@pytest.mark.parametrize("W", [2, 8])
+def test_peer_reduce_with_gathered_per_sample_scalars(W):
+    """k-wide gradient rows + all-gathered per-sample (g_bias, g_lin) == (k+4)-wide rows that carry them, bit for bit."""
+    from recman_b200 import ops
+
+    k, b = 16, 61
+    m = len(SIZES)
+    rng = np.random.RandomState(10 + W)
+    gids = np.stack([rng.randint(0, min(v, 30), size=W * b) for v in SIZES], 1).astype(np.int64)
+    gs = rng.randn(W * b, 2).astype(np.float32)  # per global sample
+    G20, Gk = [], []
+    for r in range(W):
+        rows = rng.randn(b * m, k + 4).astype(np.float32)
+        rows[:, k:] = 0
+        rows[:, k : k + 2] = np.repeat(gs[r * b : (r + 1) * b], m, axis=0)
+        G20.append(torch.from_numpy(rows).cuda())
+        Gk.append(torch.from_numpy(np.ascontiguousarray(rows[:, :k])).cuda())
+    local_sizes = [(v + W - 1) // W for v in SIZES]
+    loffs = np.concatenate([[0], np.cumsum(local_sizes)])
+    fs = torch.tensor(SIZES, dtype=torch.int64).cuda()
+    lo = torch.tensor(loffs[:-1], dtype=torch.int64).cuda()
+    gids_d = torch.from_numpy(gids).cuda()
+    gs_d = torch.from_numpy(gs).cuda()
+    for rank in (0, W - 1):
+        plan = ops.shard_plan(gids_d, W, rank, fs, lo, int(loffs[-1]), W * b * m, ops.new_status("cuda"))
+        nu = int(plan.n_unique.item())
+        a = ops.segment_reduce_p2p([g.data_ptr() for g in G20], b * m, k + 4, k, plan)
+        c = ops.segment_reduce_p2p([g.data_ptr() for g in Gk], b * m, k, k, plan, gscal=gs_d, m=m)
+        for u, v in zip(a, c):
+            assert torch.equal(u[:nu], v[:nu])
