@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--k", type=int, default=None)
     ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true", help="skip the torch-eager-CUDA comparison")
     ap.add_argument("--no-graph", action="store_true", help="do not CUDA-graph the step")
     ap.add_argument("--cin-precision", default="3xtf32")
     ap.add_argument("--cpu-batch", type=int, default=8192)
@@ -367,6 +368,12 @@ def run_ours(args):
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             cpu = cpu_baseline(args, w, steps=3, warmup=1)
+        lib = None
+        if not args.no_library_baseline and world == 1:
+            try:
+                lib = library_baseline(args, w, model, resident, B, m, k, rows, n_dense)
+            except Exception as exc:  # a reported comparison, never a reason to lose the bench line
+                lib = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
         out = {
             "metric": "CTR train samples/sec", "value": round(value, 1), "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
@@ -386,6 +393,7 @@ def run_ours(args):
             "roofline": roofline,
             "kernels": kernels,
             "cpu_baseline": cpu,
+            "library_baseline": lib,
             "wall_ms_per_step": round(wall_total / args.steps, 4),
         }
         print(json.dumps(out), flush=True)
@@ -398,6 +406,124 @@ def run_ours(args):
         # (destroy_process_group / graph destruction) wait on the peers: leave without it
         os._exit(0)
     return out
+
+
+# --------------------------------------------------------------------------------------- library bar (torch eager)
+def library_baseline(args, w, model, resident, B, m, k, rows, n_dense, steps=5, warmup=2):
+    """the same step written with stock PyTorch CUDA ops (F.embedding with sparse gradients, cuBLAS,
+    autograd, coalesce + index updates) on the same B200 and the SAME tables - "library kernels", the bar the
+    hand-written path has to beat.  Not the oracle (nothing from oracle/ is used) and not part of the product."""
+    import torch.nn.functional as F
+
+    dev = resident[0].sparse_ids.device
+    v = model.variables
+    T = v["feat_embed_table"].data.requires_grad_()
+    Bt = v["feat_bias_table"].data.view(-1, 1).requires_grad_() if "feat_bias_table" in v else None
+    total = m * rows
+    lw = v["linear_w"].data
+    Lt = lw[:total].view(-1, 1).requires_grad_()
+    offs = (torch.arange(m, device=dev, dtype=torch.int64) * rows)[None, :]
+    g = torch.Generator(device=dev).manual_seed(7)
+    d = m * k + n_dense
+    dims = [d] + list(w["deep"])
+    dense_p = []
+
+    def P(*shape, scale=0.05):
+        t = (torch.randn(*shape, device=dev, generator=g) * scale).requires_grad_()
+        dense_p.append(t)
+        return t
+
+    Ws = [P(dims[i], dims[i + 1]) for i in range(len(w["deep"]))]
+    bs = [P(dims[i + 1], scale=0.0) for i in range(len(w["deep"]))]
+    w_out, w0, lin_dense = P(dims[-1], 1), P(1, scale=0.0), P(max(n_dense, 1), scale=0.0)
+    act = torch.relu if w["model"] != "xDeepFM" else (lambda t: F.leaky_relu(t, 0.2))
+    if w["model"] == "DCN":
+        L = w["cross"]
+        cw, cb, co = P(L, d), P(L, d, scale=0.0), P(d, 1)
+    if w["model"] == "xDeepFM":
+        filt, fb, H, tot = [], [], m, 0
+        units = list(w["cin"])
+        for i, N in enumerate(units):
+            filt.append(P(m * H, N))
+            fb.append(P(N, scale=0.0))
+            keep = N if i == len(units) - 1 else N - N // 2
+            tot += keep
+            H = N // 2 if i < len(units) - 1 else N
+        cin_w = P(tot, 1)
+    lr = 1e-3
+    lr_t = lr * (1 - 0.999) ** 0.5 / (1 - 0.9)
+
+    def adam1(p, gr):  # fresh Adam, first step (the reference creates a new optimizer every batch)
+        return p - lr_t * (0.1 * gr) / ((0.001 * gr * gr).sqrt() + 1e-7)
+
+    def step(i):
+        inp = resident[i % len(resident)]
+        keys = inp.sparse_ids + offs
+        e = F.embedding(keys, T, sparse=True)
+        lin = F.embedding(keys, Lt, sparse=True).sum((1, 2))
+        dn = inp.dense
+        if n_dense:
+            lin = lin + dn @ lin_dense[:n_dense]
+        x = torch.cat([e.flatten(1), dn], 1) if n_dense else e.flatten(1)
+        h = x
+        for W_, b_ in zip(Ws, bs):
+            h = act(torch.addmm(b_, h, W_))
+        logit = lin + (h @ w_out).squeeze(1) + w0
+        if w["model"] == "DeepFM":
+            S = e.sum(1)
+            logit = logit + F.embedding(keys, Bt, sparse=True).sum((1, 2)) + 0.5 * ((S * S).sum(1) - (e * e).sum((1, 2)))
+        elif w["model"] == "DCN":
+            xl = x
+            for l in range(w["cross"]):
+                xl = x * (xl @ cw[l]).unsqueeze(1) + cb[l] + xl
+            logit = logit + (xl @ co).squeeze(1)
+        else:
+            x0, xk, outs = e, e, []
+            for i_, (Wf, bf) in enumerate(zip(filt, fb)):
+                z = torch.einsum("bpd,bqd->bdpq", x0, xk).flatten(2)           # [B, D, m*H]
+                f = act(z @ Wf + bf).transpose(1, 2)                            # [B, N, D]
+                N = f.shape[1]
+                if i_ < len(filt) - 1:
+                    xk, keep = f[:, : N // 2], f[:, N // 2 :]
+                else:
+                    keep = f
+                outs.append(keep.sum(2))
+            logit = logit + (torch.cat(outs, 1) @ cin_w).squeeze(1)
+        pred = torch.sigmoid(logit).clamp(1e-7, 1 - 1e-7)
+        y = inp["y"]
+        loss = -(y * torch.log(pred + 1e-7) + (1 - y) * torch.log(1 - pred + 1e-7)).mean()
+        loss.backward()
+        with torch.no_grad():
+            for t in (T, Bt, Lt):
+                if t is None or t.grad is None:
+                    continue
+                gsp = t.grad.coalesce()
+                idx = gsp.indices()[0]
+                t[idx] = adam1(t[idx], gsp.values())
+                t.grad = None
+            for t in dense_p:
+                if t.grad is not None:
+                    t.copy_(adam1(t, t.grad))
+                    t.grad = None
+        return loss
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    for t in (T, Bt, Lt):
+        if t is not None:
+            t.requires_grad_(False)
+    return {"value": round(B / (ms * 1e-3), 1), "unit": "samples/s", "ms_per_step": round(ms, 4),
+            "kind": "torch-eager-cuda", "steps": steps,
+            "what": "same step with stock PyTorch ops on the same GPU and tables: F.embedding(sparse=True), cuBLAS, "
+                    "autograd, sparse-grad coalesce + indexed first-step Adam (non-deterministic atomics allowed)"}
 
 
 # --------------------------------------------------------------------------------------- CPU oracle arm

@@ -113,7 +113,7 @@ class ShardPlan:
         self._offs_dev = {}
         self.peer: Optional[PeerMemory] = None  # set by enable_peer_memory(): tables live in cudaIpc-shared memory
         self._bufs = {}
-        self.slack = 0.25  # owner-side plan capacity, see capacity()
+        self.slack = 1.0  # owner-side plan capacity = 2x the uniform share (skewed ids load the owners of hot rows), see capacity()
 
     # ---- peer-memory mode -------------------------------------------------------------------------------
     def enable_peer_memory(self):
