@@ -24,73 +24,109 @@ __device__ __forceinline__ void cp_async_wait_group() {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// dx tile 128 rows x 128 columns per CTA, 8 x 8 outputs per thread, reduction over n < N from shared memory.
+// dx tile 128 rows x 128 columns per step, 8 x 8 outputs per thread, reduction over n < N from shared memory.
 // Columns d <= c < d_ld (the 16-byte row padding of the row buffer) come out as exact zeros (their W rows are zero).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int DX_BM = 128, DX_BN = 128, DX_LD = 132;  // smem row stride (floats): 16-byte aligned, conflict-free
 
+// A CTA keeps its g tile and walks DX_CT column tiles; the W^T slice of the next column tile is fetched into registers
+// while the current one is multiplied (the transposing shared-memory store cannot be done by cp.async).
+constexpr int DX_CT = 4;  // column tiles per CTA
+
 template <int NT>
-__global__ void __launch_bounds__(256) linear_dx_kernel(const float* __restrict__ g, int64_t B, int N,
-                                                        const float* __restrict__ W, int d, float* __restrict__ dx,
-                                                        int64_t d_ld) {
+__global__ void __launch_bounds__(256, 2) linear_dx_kernel(const float* __restrict__ g, int64_t B, int N,
+                                                           const float* __restrict__ W, int d, float* __restrict__ dx,
+                                                           int64_t d_ld) {
+  constexpr int LDV = (NT / 4) * 128 / 256;  // float4 loads per thread and tile
   extern __shared__ float smem_dx[];
-  float* Gs = smem_dx;               // [NT][DX_LD]: Gs[n][r] = g[r0 + r, n]
-  float* Ws = smem_dx + NT * DX_LD;  // [NT][DX_LD]: Ws[n][c] = W[c0 + c, n]
+  float* Gs = smem_dx;                // [NT][DX_LD]: Gs[n][r] = g[r0 + r, n]
+  float* Ws0 = smem_dx + NT * DX_LD;  // [2][NT][DX_LD]: Ws[n][c] = W[c0 + c, n]
   const int tid = threadIdx.x;
   const int64_t r0 = (int64_t)blockIdx.x * DX_BM;
-  const int c0 = blockIdx.y * DX_BN;
+  const int n_ct = (int)((d_ld + DX_BN - 1) / DX_BN);
+  const int ct_lo = blockIdx.y * DX_CT;
+  const int ct_hi = ct_lo + DX_CT < n_ct ? ct_lo + DX_CT : n_ct;
+  if (ct_lo >= ct_hi) return;
+
+  auto load_w = [&](int ct, float4 (&wv)[LDV]) {
 #pragma unroll
-  for (int i = 0; i < (NT / 4) * 128 / 256; ++i) {
-    const int idx = tid + i * 256;
-    const int r = idx & 127, n4 = idx >> 7;
-    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f), wv = gv;
-    if (4 * n4 < N) {
-      if (r0 + r < B) gv = ld4(g + (r0 + r) * N + 4 * n4);
-      if (c0 + r < d) wv = ld4(W + (int64_t)(c0 + r) * N + 4 * n4);
+    for (int i = 0; i < LDV; ++i) {
+      const int idx = tid + i * 256;
+      const int r = idx & 127, n4 = idx >> 7;
+      const int c = ct * DX_BN + r;
+      wv[i] = (4 * n4 < N && c < d) ? ld4(W + (int64_t)c * N + 4 * n4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    Gs[(4 * n4 + 0) * DX_LD + r] = gv.x; Gs[(4 * n4 + 1) * DX_LD + r] = gv.y;
-    Gs[(4 * n4 + 2) * DX_LD + r] = gv.z; Gs[(4 * n4 + 3) * DX_LD + r] = gv.w;
-    Ws[(4 * n4 + 0) * DX_LD + r] = wv.x; Ws[(4 * n4 + 1) * DX_LD + r] = wv.y;
-    Ws[(4 * n4 + 2) * DX_LD + r] = wv.z; Ws[(4 * n4 + 3) * DX_LD + r] = wv.w;
+  };
+  auto store_t = [&](float* dst, const float4 (&v)[LDV]) {  // transposed store: dst[n][r]
+#pragma unroll
+    for (int i = 0; i < LDV; ++i) {
+      const int idx = tid + i * 256;
+      const int r = idx & 127, n4 = idx >> 7;
+      dst[(4 * n4 + 0) * DX_LD + r] = v[i].x; dst[(4 * n4 + 1) * DX_LD + r] = v[i].y;
+      dst[(4 * n4 + 2) * DX_LD + r] = v[i].z; dst[(4 * n4 + 3) * DX_LD + r] = v[i].w;
+    }
+  };
+  {
+    float4 gv[LDV], wv[LDV];
+#pragma unroll
+    for (int i = 0; i < LDV; ++i) {
+      const int idx = tid + i * 256;
+      const int r = idx & 127, n4 = idx >> 7;
+      gv[i] = (4 * n4 < N && r0 + r < B) ? ld4(g + (r0 + r) * N + 4 * n4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    load_w(ct_lo, wv);
+    store_t(Gs, gv);
+    store_t(Ws0, wv);
   }
   __syncthreads();
   const int ty = tid >> 4, tx = tid & 15;
-  float acc[8][8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-#pragma unroll 4
-  for (int n = 0; n < N; ++n) {
-    const float4 a0 = ld4(Gs + n * DX_LD + ty * 8), a1 = ld4(Gs + n * DX_LD + ty * 8 + 4);
-    const float4 b0 = ld4(Ws + n * DX_LD + tx * 4), b1 = ld4(Ws + n * DX_LD + 64 + tx * 4);
-    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  for (int ct = ct_lo; ct < ct_hi; ++ct) {
+    const float* Ws = Ws0 + ((ct - ct_lo) & 1) * NT * DX_LD;
+    float4 wnext[LDV];
+    const bool more = ct + 1 < ct_hi;
+    if (more) load_w(ct + 1, wnext);
+    float acc[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-  }
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+    for (int n = 0; n < N; ++n) {
+      const float4 a0 = ld4(Gs + n * DX_LD + ty * 8), a1 = ld4(Gs + n * DX_LD + ty * 8 + 4);
+      const float4 b0 = ld4(Ws + n * DX_LD + tx * 4), b1 = ld4(Ws + n * DX_LD + 64 + tx * 4);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int64_t row = r0 + ty * 8 + i;
-    if (row < B) {
-      float* o = dx + row * d_ld;
-      const int ca = c0 + tx * 4, cb = c0 + 64 + tx * 4;
-      if (ca < d_ld) st4(o + ca, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
-      if (cb < d_ld) st4(o + cb, make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    const int c0 = ct * DX_BN;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t row = r0 + ty * 8 + i;
+      if (row < B) {
+        float* o = dx + row * d_ld;
+        const int ca = c0 + tx * 4, cb = c0 + 64 + tx * 4;
+        if (ca < d_ld) st4(o + ca, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+        if (cb < d_ld) st4(o + cb, make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
+      }
+    }
+    if (more) {
+      store_t(Ws0 + (((ct - ct_lo) & 1) ^ 1) * NT * DX_LD, wnext);
+      __syncthreads();
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // dW: CTA (feature tile of 128, batch slab) -> partial[slab][f][n]; chunks of 32 samples double-buffered with cp.async.
-// Thread: 4 features x (NT / 8) outputs.  The slabs are summed in slab order by linear_dw_final_kernel.
+// 128 threads, thread: 8 features x (NT / 8) outputs.  The slabs are summed in slab order by linear_dw_final_kernel.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int DW_BF = 128, DW_BK = 32;
 
 template <int NT>
-__global__ void __launch_bounds__(256) linear_dw_kernel(const float* __restrict__ x, int64_t ld,
+__global__ void __launch_bounds__(128) linear_dw_kernel(const float* __restrict__ x, int64_t ld,
                                                         const float* __restrict__ g, int64_t B, int K, int N,
                                                         int64_t slab_rows, float* __restrict__ partial, int Kpad) {
   constexpr int NV = NT / 32;  // float4 output groups per thread along n
@@ -108,15 +144,15 @@ __global__ void __launch_bounds__(256) linear_dw_kernel(const float* __restrict_
     const int buf = ch & 1;
     const int64_t b0 = b_lo + (int64_t)ch * DW_BK;
 #pragma unroll
-    for (int i = 0; i < DW_BK * DW_BF / 4 / 256; ++i) {  // 4 float4 of the x chunk per thread
-      const int idx = tid + i * 256;
+    for (int i = 0; i < DW_BK * DW_BF / 4 / 128; ++i) {  // 8 float4 of the x chunk per thread
+      const int idx = tid + i * 128;
       const int r = idx >> 5, c4 = idx & 31;
       const int64_t b = b0 + r;
       const int f = f0 + 4 * c4;
       const bool ok = b < b_hi && f < ld;  // ld % 4 == 0: a float4 never straddles the row end
       cp_async16_zfill(xs_u32 + (uint32_t)((buf * DW_BK + r) * DW_BF + 4 * c4) * 4u, ok ? x + b * ld + f : x, ok);
     }
-    for (int idx = tid; idx < DW_BK * NT / 4; idx += 256) {
+    for (int idx = tid; idx < DW_BK * NT / 4; idx += 128) {
       const int r = idx / (NT / 4), c4 = idx - r * (NT / 4);
       const int64_t b = b0 + r;
       const bool ok = b < b_hi && 4 * c4 < N;
@@ -125,10 +161,10 @@ __global__ void __launch_bounds__(256) linear_dw_kernel(const float* __restrict_
     cp_async_commit_group();
   };
 
-  const int tf = tid >> 3, tn = tid & 7;  // features tf*4 .. +3, outputs tn*4 .. +3 (+32 for NT = 64)
-  float acc[4][4 * NV];
+  const int tf = tid >> 3, tn = tid & 7;  // features tf*8 .. +7, outputs tn*4 .. +3 (+32 for NT = 64)
+  float acc[8][4 * NV];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4 * NV; ++j) acc[i][j] = 0.f;
   if (n_chunks > 0) issue(0);
@@ -137,27 +173,27 @@ __global__ void __launch_bounds__(256) linear_dw_kernel(const float* __restrict_
     else cp_async_commit_group();
     cp_async_wait_group<1>();
     __syncthreads();
-    const float* xb = Xs + (ch & 1) * DW_BK * DW_BF + tf * 4;
+    const float* xb = Xs + (ch & 1) * DW_BK * DW_BF + tf * 8;
     const float* gb = Gs + (ch & 1) * DW_BK * NT + tn * 4;
-#pragma unroll 8
+#pragma unroll 4
     for (int r = 0; r < DW_BK; ++r) {
-      const float4 xv = ld4(xb + r * DW_BF);
-      const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+      const float4 x0 = ld4(xb + r * DW_BF), x1 = ld4(xb + r * DW_BF + 4);
+      const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         const float4 gv = ld4(gb + r * NT + 32 * v);
         const float ga[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[i][4 * v + j] = fmaf(xa[i], ga[j], acc[i][4 * v + j]);
       }
     }
     __syncthreads();  // the buffer is refilled by the next iteration's issue
   }
-  float* out = partial + ((int64_t)blockIdx.y * Kpad + f0 + tf * 4) * NT;
+  float* out = partial + ((int64_t)blockIdx.y * Kpad + f0 + tf * 8) * NT;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int v = 0; v < NV; ++v)
       st4(out + i * NT + 32 * v + tn * 4,
@@ -187,7 +223,7 @@ static DwLayout dw_layout(int64_t B, int K, int N) {
   L.NT = N <= 32 ? 32 : 64;
   L.n_ftiles = (int)ceil_div(K, DW_BF);
   L.Kpad = L.n_ftiles * DW_BF;
-  int64_t slabs = (4 * RM_NUM_SMS) / L.n_ftiles;  // about four CTAs per SM in one wave
+  int64_t slabs = (5 * RM_NUM_SMS) / L.n_ftiles;  // about five 128-thread CTAs per SM (40 KB smem each) in one wave
   const int64_t max_slabs = ceil_div(B > 0 ? B : 1, 256);
   if (slabs > max_slabs) slabs = max_slabs;
   if (slabs < 1) slabs = 1;
@@ -210,12 +246,13 @@ int rm_linear_bwd_input(const float* g, int64_t B, int32_t N, const float* W, in
   RM_UNSUPPORTED(N <= 64 && N % 4 == 0 && d_ld % 4 == 0 && aligned16(g) && aligned16(W) && aligned16(dx),
                  "narrow-layer input gradient needs N <= 64, N % 4 == 0 and 16-byte aligned rows");
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((unsigned)ceil_div(B, DX_BM), (unsigned)ceil_div(d_ld, DX_BN));
+  dim3 grid((unsigned)ceil_div(B, DX_BM), (unsigned)ceil_div(ceil_div(d_ld, DX_BN), DX_CT));
   if (N <= 32) {
-    const size_t smem = (size_t)2 * 32 * DX_LD * sizeof(float);
+    const size_t smem = (size_t)3 * 32 * DX_LD * sizeof(float);
+    RM_CUDA(cudaFuncSetAttribute(linear_dx_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     linear_dx_kernel<32><<<grid, 256, smem, st>>>(g, B, N, W, d, dx, d_ld);
   } else {
-    const size_t smem = (size_t)2 * 64 * DX_LD * sizeof(float);
+    const size_t smem = (size_t)3 * 64 * DX_LD * sizeof(float);
     RM_CUDA(cudaFuncSetAttribute(linear_dx_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     linear_dx_kernel<64><<<grid, 256, smem, st>>>(g, B, N, W, d, dx, d_ld);
   }
@@ -250,10 +287,10 @@ int rm_linear_bwd_weight(const float* x, int64_t ld, const float* g, int64_t B, 
   dim3 grid((unsigned)L.n_ftiles, (unsigned)L.slabs);
   const size_t smem = (size_t)2 * DW_BK * (DW_BF + L.NT) * sizeof(float);
   if (L.NT == 32) {
-    linear_dw_kernel<32><<<grid, 256, smem, st>>>(x, ld, g, B, K, N, L.slab_rows, partial, L.Kpad);
+    linear_dw_kernel<32><<<grid, 128, smem, st>>>(x, ld, g, B, K, N, L.slab_rows, partial, L.Kpad);
   } else {
     RM_CUDA(cudaFuncSetAttribute(linear_dw_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    linear_dw_kernel<64><<<grid, 256, smem, st>>>(x, ld, g, B, K, N, L.slab_rows, partial, L.Kpad);
+    linear_dw_kernel<64><<<grid, 128, smem, st>>>(x, ld, g, B, K, N, L.slab_rows, partial, L.Kpad);
   }
   RM_LAUNCH_CHECK();
   linear_dw_final_kernel<<<grid_for((int64_t)K * N, 256, 8), 256, 0, st>>>(partial, L.slabs, L.Kpad, L.NT, K, N, dW);

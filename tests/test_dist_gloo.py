@@ -108,3 +108,23 @@ def test_shard_plan_layout():
     assert p.local_rows_of(0).tolist() == [1, 5, 9] and p.local_rows_of(1).tolist() == [1]
     dest, key = p.route(torch.tensor([[9, 2, 7], [0, 0, 0]]))
     assert dest.tolist() == [1, 2, 3, 0, 0, 0] and key.tolist() == [2, 3, 5, 0, 3, 4]
+
+
+def test_shard_plan_capacity_covers_skewed_and_tiny_tables():
+    """Owner-side plan capacity: tables with fewer rows than ranks load the low ranks, Zipf ids load the owners of the
+    hot rows (id 0 of every table lives on rank 0) - the default capacity has to hold both."""
+    from recman_b200.th.dist import ShardPlan
+
+    W, b = 8, 300
+    sizes = [50, 7, 1000, 3, 200, 31, 2, 90, 1]
+    plan = ShardPlan(sizes, W, 0)
+    rng = np.random.RandomState(0)
+    ids = np.stack([rng.randint(0, v, size=W * b) for v in sizes], 1)
+    owned = np.bincount((ids % W).reshape(-1), minlength=W)
+    assert owned.max() <= plan.capacity(b) <= W * b * len(sizes)
+    # Criteo-shaped, Zipf(1.05): rank 0 owns ~1.3x the uniform share at W = 8
+    m, rows, b = 26, 10_000_000, 8192
+    plan = ShardPlan([rows] * m, W, 0)
+    z = (np.random.RandomState(1).zipf(1.05, size=(W * b, m)) - 1) % rows
+    owned = np.bincount((z % W).reshape(-1), minlength=W)
+    assert owned.max() > 1.2 * b * m and owned.max() <= plan.capacity(b)
