@@ -264,6 +264,13 @@ int rm_pack_grad_rows(const float* dx, const float* x, int64_t ld, const float* 
  * ------------------------------------------------------------------------- */
 int rm_linear_bwd_input(const float* g, int64_t B, int32_t N, const float* W, int32_t d, float* dx, int64_t d_ld,
                         void* stream);
+/* rm_linear_bwd_input with DeepFM's FM backward (A5b) fused into the epilogue: the first m*k input columns are the
+ * embedding block of the row buffer x[B, x_ld], and
+ *   out[b, f*k + j] = sum_n g[b,n] * W[f*k + j, n] + g_fm[b] * (sum[b, j] - x[b*x_ld + f*k + j])
+ * is the complete gradient of embedding row (b, f): out [B, m*k] is exactly the [B*m, k] gradient-row buffer that
+ * rm_segment_reduce_p2p[_update] (W = 1: this rank only) consumes - no separate dx pass, no pack pass. */
+int rm_linear_bwd_input_fm(const float* g, int64_t B, int32_t N, const float* W, int32_t m, int32_t k, const float* x,
+                           int64_t x_ld, const float* sum, const float* g_fm, float* out, void* stream);
 size_t rm_linear_bwd_weight_workspace_bytes(int64_t B, int32_t K, int32_t N);
 int rm_linear_bwd_weight(const float* x, int64_t ld, const float* g, int64_t B, int32_t K, int32_t N, float* dW,
                          void* workspace, size_t workspace_bytes, void* stream);

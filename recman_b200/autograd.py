@@ -227,6 +227,40 @@ class CINLayerFunction(Function):
 # --------------------------------------------------------------------------- #
 # fused DeepFM / DCN / xDeepFM front end (K1 + K3 + first-order, one launch)
 # --------------------------------------------------------------------------- #
+class FmBack:
+    """Side channel between DeepFM's front end and its first (narrow) MLP layer: with both at hand, the layer's
+    input-gradient kernel adds the FM backward term in its epilogue and writes the complete embedding-row gradients
+    G [B*m, k] directly (rm_linear_bwd_input_fm) - the front end's backward then only reduces G.  ``g_fm`` arrives through
+    a tensor hook on the FM logit, which autograd fires before it walks back into the MLP; when it has not (other graph
+    shapes), both sides fall back to their separate kernels."""
+
+    def __init__(self):
+        # no reference to the row buffer itself: it is an output of the front-end Function whose ctx holds this object,
+        # and such a cycle would leave the step's tensors to the garbage collector (fatal inside CUDA-graph capture)
+        self.x_ptr = 0
+        self.S = self.g_fm = self.G = None
+        self.m = self.k = 0
+        self.alloc = None  # () -> G buffer [B*m, k] (peer-shared memory when the tables are row-sharded)
+
+    def on_g_fm(self, g):
+        self.g_fm = g.reshape(-1).contiguous()
+
+
+class GradTap(Function):
+    """Identity on the final logit whose backward hands d(loss)/d(logit) to an ``FmBack`` before autograd walks into
+    the MLP (a plain node instead of a tensor hook: hooks break CUDA-graph capture of the step)."""
+
+    @staticmethod
+    def forward(ctx, logit, fm_back):
+        ctx.fm_back = fm_back
+        return logit.view_as(logit)
+
+    @staticmethod
+    def backward(ctx, g):
+        ctx.fm_back.on_g_fm(g)
+        return g, None
+
+
 class FrontEndFunction(Function):
     """ids -> (xbuf [B, ld] = [embeds | dense | 0-pad], fm [B,1], lin [B,1]).
 
@@ -240,8 +274,16 @@ class FrontEndFunction(Function):
 
     @staticmethod
     def forward(ctx, table, bias_table, W_lin, lin_table, lin_dense, offsets, total_rows, status, ids, dense,
-                fused_opt=None):
+                fused_opt=None, fm_back=None):
         x, fm, lin, S = ops.gather_fm_fwd(table, bias_table, lin_table, offsets, ids, dense, lin_dense, status=status)
+        ctx.fm_back = fm_back
+        if fm_back is not None:
+            B_, m_ = ids.shape
+            k_ = table.shape[1]
+            fm_back.x_ptr, fm_back.S, fm_back.m, fm_back.k = x.data_ptr(), S, m_, k_
+            fm_back.g_fm = fm_back.G = None
+            dev_ = x.device
+            fm_back.alloc = lambda: torch.empty(B_ * m_, k_, dtype=torch.float32, device=dev_)
         ctx.table, ctx.bias_table, ctx.W_lin = table, bias_table, W_lin
         ctx.has_lin = lin_table is not None
         ctx.n_lin_dense = 0 if lin_dense is None else lin_dense.numel()
@@ -268,6 +310,29 @@ class FrontEndFunction(Function):
         g_lin = None if dlin is None else dlin.reshape(-1).contiguous()
         want_bias = ctx.bias_table is not None and g_fm is not None
         want_lin = ctx.has_lin and g_lin is not None
+        fb = ctx.fm_back
+        if fb is not None and fb.G is not None:
+            # the first MLP layer already wrote the complete row gradients (dx + FM backward): reduce them
+            G, fb.G = fb.G, None
+            B_, m_ = ids.shape
+            zeros = torch.zeros(B_, dtype=torch.float32, device=x.device) if (g_fm is None or g_lin is None) else None
+            gscal = torch.stack([g_fm if g_fm is not None else zeros, g_lin if g_lin is not None else zeros], 1).contiguous()
+            if want_lin and ctx.W_lin is not None and ctx.n_lin_dense and dense is not None:
+                ctx.W_lin.rm_dense_tail = (ctx.total_rows, dense.t() @ g_lin)
+            if ctx.fused_opt is not None:
+                kind, lr = ctx.fused_opt
+                ops.segment_reduce_p2p_update([G.data_ptr()], B_ * m_, k, k, plan, ctx.table.data,
+                                              ctx.bias_table.data if want_bias else None,
+                                              ctx.lin_table if want_lin else None, kind, lr, gscal=gscal, m=m_)
+                return (None,) * 12
+            rows, ob, ol = ops.segment_reduce_p2p([G.data_ptr()], B_ * m_, k, k, plan, want_bias, want_lin, gscal=gscal,
+                                                  m=m_)
+            attach_sparse_grad(ctx.table, ops.SparseGrad(plan.uniq_rows, rows, plan.n_unique))
+            if want_bias:
+                attach_sparse_grad(ctx.bias_table, ops.SparseGrad(plan.uniq_rows, ob, plan.n_unique))
+            if want_lin and ctx.W_lin is not None:
+                attach_sparse_grad(ctx.W_lin, ops.SparseGrad(plan.uniq_rows, ol, plan.n_unique))
+            return (None,) * 12
         if ctx.fused_opt is not None:
             kind, lr = ctx.fused_opt
             ops.emb_fm_bwd_update(dx, x, ld, S, g_fm, g_lin if want_lin else None, plan, k, ctx.table.data,
@@ -275,7 +340,7 @@ class FrontEndFunction(Function):
                                   ctx.lin_table if want_lin else None, kind, lr)
             if want_lin and ctx.W_lin is not None and ctx.n_lin_dense and dense is not None:
                 ctx.W_lin.rm_dense_tail = (ctx.total_rows, dense.t() @ g_lin)
-            return (None,) * 11
+            return (None,) * 12
         rows, ob, ol = ops.emb_fm_bwd(dx, x, ld, S, g_fm, g_lin if want_lin else None, plan, k, True, want_bias,
                                       want_lin)
         attach_sparse_grad(ctx.table, ops.SparseGrad(plan.uniq_rows, rows, plan.n_unique))
@@ -285,17 +350,18 @@ class FrontEndFunction(Function):
             attach_sparse_grad(ctx.W_lin, ops.SparseGrad(plan.uniq_rows, ol, plan.n_unique))
             if ctx.n_lin_dense and dense is not None:
                 ctx.W_lin.rm_dense_tail = (ctx.total_rows, dense.t() @ g_lin)
-        return (None,) * 11
+        return (None,) * 12
 
 
 class FirstLinearFunction(Function):
     """y = xbuf[:, :d] @ W + b with the input gradient written straight into a padded [B, ld] buffer."""
 
     @staticmethod
-    def forward(ctx, xbuf, W, b, d):
+    def forward(ctx, xbuf, W, b, d, fm_back=None):
         x = xbuf[:, :d]
         ctx.save_for_backward(xbuf, W)
         ctx.d = d
+        ctx.fm_back = fm_back
         return torch.addmm(b, x, W)
 
     @staticmethod
@@ -308,14 +374,22 @@ class FirstLinearFunction(Function):
         if ops.narrow_linear_ok(g.shape[1]) and xbuf.is_contiguous() and W.is_contiguous():
             # narrow first layer (DeepFM default 32 units): the batch is the only large dimension of both products
             dW = ops.linear_bwd_weight(xbuf, ld, d, g)
+            fb = ctx.fm_back
+            if (fb is not None and fb.g_fm is not None and fb.x_ptr == xbuf.data_ptr() and fb.k % 4 == 0
+                    and fb.g_fm.shape[0] == xbuf.shape[0]):
+                # DeepFM: FM backward fused into the epilogue -> complete embedding-row gradients, no dx pass at all
+                G = fb.alloc()
+                ops.linear_bwd_input_fm(g, W, fb.m, fb.k, xbuf, fb.S, fb.g_fm, out=G)
+                fb.G, fb.g_fm = G, None
+                return None, dW, db, None, None
             dxbuf = ops.linear_bwd_input(g, W, d_ld=ld)
-            return dxbuf, dW, db, None
+            return dxbuf, dW, db, None, None
         dW = xbuf[:, :d].t() @ g
         dxbuf = torch.empty_like(xbuf)
         torch.mm(g, W.t(), out=dxbuf[:, :d])
         if xbuf.shape[1] > d:
             dxbuf[:, d:].zero_()
-        return dxbuf, dW, db, None
+        return dxbuf, dW, db, None, None
 
 
 class NarrowLinearFunction(Function):

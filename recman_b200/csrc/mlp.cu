@@ -18,6 +18,7 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* 
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -36,7 +37,9 @@ constexpr int DX_CT = 4;  // column tiles per CTA
 template <int NT>
 __global__ void __launch_bounds__(256, 2) linear_dx_kernel(const float* __restrict__ g, int64_t B, int N,
                                                            const float* __restrict__ W, int d, float* __restrict__ dx,
-                                                           int64_t d_ld) {
+                                                           int64_t d_ld, const float* __restrict__ fx, int64_t fx_ld,
+                                                           const float* __restrict__ fS, const float* __restrict__ fg,
+                                                           int fk) {
   constexpr int LDV = (NT / 4) * 128 / 256;  // float4 loads per thread and tile
   extern __shared__ float smem_dx[];
   float* Gs = smem_dx;                // [NT][DX_LD]: Gs[n][r] = g[r0 + r, n]
@@ -85,6 +88,17 @@ __global__ void __launch_bounds__(256, 2) linear_dx_kernel(const float* __restri
     float4 wnext[LDV];
     const bool more = ct + 1 < ct_hi;
     if (more) load_w(ct + 1, wnext);
+    if (fx) {  // the epilogue's x values: pull them into L1 while the products are formed (no registers held)
+      const int c0p = ct * DX_BN;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t row = r0 + ty * 8 + i;
+        if (row < B) {
+          if (c0p + tx * 4 < d) prefetch_l1(fx + row * fx_ld + c0p + tx * 4);
+          if (c0p + 64 + tx * 4 < d) prefetch_l1(fx + row * fx_ld + c0p + 64 + tx * 4);
+        }
+      }
+    }
     float acc[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -108,8 +122,21 @@ __global__ void __launch_bounds__(256, 2) linear_dx_kernel(const float* __restri
       if (row < B) {
         float* o = dx + row * d_ld;
         const int ca = c0 + tx * 4, cb = c0 + 64 + tx * 4;
-        if (ca < d_ld) st4(o + ca, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
-        if (cb < d_ld) st4(o + cb, make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
+        float4 va = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        float4 vb = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+        if (fx) {  // FM backward fused in: out = dx + g_fm[row] * (S[row, c % k] - x[row, c])  (layers.py:457-478)
+          const float gf = fg[row];
+          if (ca < d) {
+            const float4 xv = ld4(fx + row * fx_ld + ca), sv = ld4(fS + row * fk + (ca % fk));
+            va.x += gf * (sv.x - xv.x); va.y += gf * (sv.y - xv.y); va.z += gf * (sv.z - xv.z); va.w += gf * (sv.w - xv.w);
+          }
+          if (cb < d) {
+            const float4 xv = ld4(fx + row * fx_ld + cb), sv = ld4(fS + row * fk + (cb % fk));
+            vb.x += gf * (sv.x - xv.x); vb.y += gf * (sv.y - xv.y); vb.z += gf * (sv.z - xv.z); vb.w += gf * (sv.w - xv.w);
+          }
+        }
+        if (ca < d_ld) st4(o + ca, va);
+        if (cb < d_ld) st4(o + cb, vb);
       }
     }
     if (more) {
@@ -237,6 +264,25 @@ static DwLayout dw_layout(int64_t B, int K, int N) {
 
 extern "C" {
 
+static int linear_dx_launch(const float* g, int64_t B, int32_t N, const float* W, int32_t d, float* dx, int64_t d_ld,
+                            const float* fx, int64_t fx_ld, const float* fS, const float* fg, int32_t fk,
+                            void* stream) {
+  using namespace rm;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)ceil_div(B, DX_BM), (unsigned)ceil_div(ceil_div(d_ld, DX_BN), DX_CT));
+  if (N <= 32) {
+    const size_t smem = (size_t)3 * 32 * DX_LD * sizeof(float);
+    RM_CUDA(cudaFuncSetAttribute(linear_dx_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    linear_dx_kernel<32><<<grid, 256, smem, st>>>(g, B, N, W, d, dx, d_ld, fx, fx_ld, fS, fg, fk);
+  } else {
+    const size_t smem = (size_t)3 * 64 * DX_LD * sizeof(float);
+    RM_CUDA(cudaFuncSetAttribute(linear_dx_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    linear_dx_kernel<64><<<grid, 256, smem, st>>>(g, B, N, W, d, dx, d_ld, fx, fx_ld, fS, fg, fk);
+  }
+  RM_LAUNCH_CHECK();
+  return 0;
+}
+
 int rm_linear_bwd_input(const float* g, int64_t B, int32_t N, const float* W, int32_t d, float* dx, int64_t d_ld,
                         void* stream) {
   using namespace rm;
@@ -245,19 +291,20 @@ int rm_linear_bwd_input(const float* g, int64_t B, int32_t N, const float* W, in
   RM_CHECK_ARG(g && W && dx, "null pointer");
   RM_UNSUPPORTED(N <= 64 && N % 4 == 0 && d_ld % 4 == 0 && aligned16(g) && aligned16(W) && aligned16(dx),
                  "narrow-layer input gradient needs N <= 64, N % 4 == 0 and 16-byte aligned rows");
-  cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((unsigned)ceil_div(B, DX_BM), (unsigned)ceil_div(ceil_div(d_ld, DX_BN), DX_CT));
-  if (N <= 32) {
-    const size_t smem = (size_t)3 * 32 * DX_LD * sizeof(float);
-    RM_CUDA(cudaFuncSetAttribute(linear_dx_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    linear_dx_kernel<32><<<grid, 256, smem, st>>>(g, B, N, W, d, dx, d_ld);
-  } else {
-    const size_t smem = (size_t)3 * 64 * DX_LD * sizeof(float);
-    RM_CUDA(cudaFuncSetAttribute(linear_dx_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    linear_dx_kernel<64><<<grid, 256, smem, st>>>(g, B, N, W, d, dx, d_ld);
-  }
-  RM_LAUNCH_CHECK();
-  return 0;
+  return linear_dx_launch(g, B, N, W, d, dx, d_ld, nullptr, 0, nullptr, nullptr, 4, stream);
+}
+
+int rm_linear_bwd_input_fm(const float* g, int64_t B, int32_t N, const float* W, int32_t m, int32_t k, const float* x,
+                           int64_t x_ld, const float* sum, const float* g_fm, float* out, void* stream) {
+  using namespace rm;
+  RM_CHECK_ARG(B >= 0 && N > 0 && m > 0 && k > 0 && x_ld >= (int64_t)m * k, "bad shape");
+  if (B == 0) return 0;
+  RM_CHECK_ARG(g && W && x && sum && g_fm && out, "null pointer");
+  RM_UNSUPPORTED(N <= 64 && N % 4 == 0 && k % 4 == 0 && x_ld % 4 == 0 && aligned16(g) && aligned16(W) &&
+                     aligned16(x) && aligned16(sum) && aligned16(out),
+                 "fused FM backward needs N <= 64, N % 4 == 0, k % 4 == 0 and 16-byte aligned rows");
+  const int32_t d = m * k;
+  return linear_dx_launch(g, B, N, W, d, out, d, x, x_ld, sum, g_fm, k, stream);
 }
 
 size_t rm_linear_bwd_weight_workspace_bytes(int64_t B, int32_t K, int32_t N) {

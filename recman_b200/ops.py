@@ -460,6 +460,20 @@ def linear_bwd_input(g, W, d_ld: Optional[int] = None, out=None):
     return out
 
 
+def linear_bwd_input_fm(g, W, m: int, k: int, x, S, g_fm, out=None):
+    """G [B, m*k] = g @ W[:m*k]^T + g_fm * (S - x): the complete embedding-row gradients of DeepFM (MLP input gradient +
+    FM backward) in one pass; ``x`` is the row buffer [B, ld], ``S`` [B, k] the field sums, ``g_fm`` [B]."""
+    _dev_check(g)
+    B, N = g.shape
+    assert W.shape[0] >= m * k and W.shape[1] == N and g.is_contiguous() and W.is_contiguous()
+    assert x.is_contiguous() and S.is_contiguous() and g_fm.is_contiguous() and x.shape[0] == B
+    if out is None:
+        out = torch.empty(B, m * k, dtype=torch.float32, device=g.device)
+    assert out.is_contiguous() and out.numel() == B * m * k
+    _C.call("rm_linear_bwd_input_fm", _p(g), B, N, _p(W), m, k, _p(x), x.shape[1], _p(S), _p(g_fm), _p(out), _stream())
+    return out
+
+
 def linear_bwd_weight(x, ld: int, K: int, g):
     """dW [K, N] = x[:, :K]^T @ g, x rows ld floats apart (ld % 4 == 0), deterministic slabbed batch reduction."""
     _dev_check(g)

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import torch
 
+from ..autograd import GradTap
 from .DeepModel import DeepModel, create_loss
 from .input import DataInputs, FeatureDictionary
 from .layers import DNN, DNNCombiner, FMLayer, LinearCombiner, LinearLayer, PredictionLayer, relu
@@ -92,6 +93,11 @@ class DeepFM(DeepModel):
                            hp["deep_activation"], hp["deep_l2_reg"])
             self.dnn.training = training
             final_logit = final_logit + self.dnn(dnn_input)
+        fm_back = getattr(dnn_input, "fm_back", None) if self.use_deep else None
+        if fm_back is not None and final_logit.requires_grad:
+            # d(loss)/d(fm_logit) == d(loss)/d(final_logit) (plain sum); a tap on the final logit runs at the very start of
+            # the backward pass, i.e. before autograd walks into the MLP, whose first layer then fuses the FM backward
+            final_logit = GradTap.apply(final_logit, fm_back)
         self.final_logit = final_logit.detach()  # detached: keeping the graph alive would pin its grad accumulators
         return PredictionLayer(self.variables, self.task, use_bias=False)(final_logit)
 

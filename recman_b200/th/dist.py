@@ -217,7 +217,7 @@ class ShardedFrontEndFunction(Function):
 
     @staticmethod
     def forward(ctx, table, bias_table, W_lin, lin_table, lin_dense, plan: ShardPlan, status, ids, dense,
-                fused_opt=None):
+                fused_opt=None, fm_back=None):
         from .. import ops
 
         b, m = ids.shape
@@ -288,7 +288,7 @@ class ShardedFrontEndFunction(Function):
                 attach_sparse_grad(ctx.W_lin, ops.SparseGrad(sp.uniq_rows, rows[:, k + 1].contiguous(), sp.n_unique))
         if ctx.has_lin_dense and ctx.W_lin is not None and g_lin is not None:
             ctx.W_lin.rm_dense_tail = (plan.total_local, dense.t() @ g_lin)  # replicated: all-reduced by the optimizer
-        return (None,) * 10
+        return (None,) * 11
 
 
 class P2PFrontEndFunction(Function):
@@ -296,13 +296,14 @@ class P2PFrontEndFunction(Function):
 
     @staticmethod
     def forward(ctx, table, bias_table, W_lin, lin_table, lin_dense, plan: ShardPlan, status, ids, dense,
-                fused_opt=None):
+                fused_opt=None, fm_back=None):
         from .. import ops
 
         b, m = ids.shape
         k = table.shape[1]
         W, dev, peer = plan.world, table.device, plan.peer
         ctx.fused_opt, ctx.lin_table = fused_opt, lin_table
+        ctx.fm_back = fm_back
         ids = ids.contiguous()
         gids = torch.empty(W * b, m, dtype=torch.int64, device=dev)
         # every rank has finished the previous step's table update once this returns (it is also the barrier that
@@ -322,6 +323,10 @@ class P2PFrontEndFunction(Function):
         ctx.table, ctx.bias_table, ctx.W_lin = table, bias_table, W_lin
         ctx.has_lin = lin_table is not None
         ctx.has_lin_dense = lin_dense is not None and dense is not None and dense.shape[1] > 0
+        if fm_back is not None:
+            fm_back.x_ptr, fm_back.S, fm_back.m, fm_back.k = x.data_ptr(), S, m, k
+            fm_back.g_fm = fm_back.G = None
+            fm_back.alloc = lambda: plan.grad_buffer(b * m, k)
         ctx.save_for_backward(x, S, dense, gids)
         ctx.b, ctx.m, ctx.k = b, m, k
         ctx.set_materialize_grads(False)
@@ -348,8 +353,12 @@ class P2PFrontEndFunction(Function):
                                 plan.total_local, plan.capacity(b), ctx.status)
         # gradient rows are exactly k floats (256-byte rows at k = 64: one NVLink request fewer per row than k+4); the two
         # k=1 gradients are per-sample values and travel once, in the all-gather that also says "every G is complete"
-        G = plan.grad_buffer(b * m, k)
-        ops.pack_grad_rows(dx, x, ld, S, g_fm, g_lin, None, m, k, k, out=G, n=b * m)
+        fb = ctx.fm_back
+        if fb is not None and fb.G is not None:
+            G, fb.G = fb.G, None  # the first MLP layer already wrote dx + FM backward into this rank's peer-shared buffer
+        else:
+            G = plan.grad_buffer(b * m, k)
+            ops.pack_grad_rows(dx, x, ld, S, g_fm, g_lin, None, m, k, k, out=G, n=b * m)
         zeros = None
         if g_fm is None or g_lin is None:
             zeros = torch.zeros(b, dtype=torch.float32, device=dev)
@@ -365,14 +374,14 @@ class P2PFrontEndFunction(Function):
             ops.segment_reduce_p2p_update(plan.peer.ptrs_of(G), b * m, k, k, sp, ctx.table.data,
                                           ctx.bias_table.data if want_bias else None,
                                           ctx.lin_table if want_lin else None, kind, lr, gscal=gscal, m=m)
-            return (None,) * 10
+            return (None,) * 11
         rows, ob, ol = ops.segment_reduce_p2p(plan.peer.ptrs_of(G), b * m, k, k, sp, want_bias, want_lin, gscal=gscal, m=m)
         attach_sparse_grad(ctx.table, ops.SparseGrad(sp.uniq_rows, rows, sp.n_unique))
         if want_bias:
             attach_sparse_grad(ctx.bias_table, ops.SparseGrad(sp.uniq_rows, ob, sp.n_unique))
         if want_lin:
             attach_sparse_grad(ctx.W_lin, ops.SparseGrad(sp.uniq_rows, ol, sp.n_unique))
-        return (None,) * 10
+        return (None,) * 11
 
 
 def allreduce_dense(grads: List[torch.Tensor], group=None) -> None:

@@ -531,7 +531,7 @@ class DNN:
         for i in range(len(self.hidden_units)):
             W, b = v[f"{p}dnn_layer_{i}_weights"], v[f"{p}dnn_layer_{i}_bias"]
             if i == 0 and padded:
-                y = FirstLinearFunction.apply(y.buf, W, b, y.d)
+                y = FirstLinearFunction.apply(y.buf, W, b, y.d, getattr(y, "fm_back", None))
             elif ops.narrow_linear_ok(W.shape[1]) and y.shape[1] % 4 == 0:
                 # narrow hidden layer: batch-reduced backward kernels (csrc/mlp.cu)
                 y = NarrowLinearFunction.apply(y.contiguous(), W, b)

@@ -181,3 +181,33 @@ def test_fused_sparse_update_is_bit_identical(model_name, opt):
     assert set(a.variables) == set(b.variables)
     for name in a.variables:
         assert torch.equal(a.variables[name].data, b.variables[name].data), name
+
+
+def test_deepfm_fm_backward_fused_into_first_layer_matches_separate_kernels():
+    """DeepFM with a narrow first layer, opt-in hparams["fuse_fm_backward"]: the FM backward rides in the MLP
+    input-gradient epilogue (rm_linear_bwd_input_fm -> row gradients -> reduce).  Same gradients as the separate
+    dx / fused-reduce kernels, and the path is actually taken."""
+    import torch
+
+    from recman_b200 import ops
+    from recman_b200.th import DeepFM
+
+    fd = pu.make_feat_dict([50, 7, 1000, 3, 200, 31], n_dense=5)
+    X, y = pu.synth_batch(fd, 700, seed=3)
+    grads = {}
+    for fuse in (True, False):
+        model = DeepFM(fd, embedding_size=16, deep_hidden_units=(32, 32), deep_dropout=(1, 1, 1), batch_size=700)
+        model.hparams["fuse_fm_backward"] = fuse
+        calls = []
+        orig = ops.linear_bwd_input_fm
+        ops.linear_bwd_input_fm = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+        try:
+            report = pu.compare(model, X, y)
+        finally:
+            ops.linear_bwd_input_fm = orig
+        assert bool(calls) == fuse
+        assert max(report.values()) < 1e-4
+        _, _, g = pu.run_model_step(model, X, y)
+        grads[fuse] = g
+    for name in grads[True]:
+        torch.testing.assert_close(grads[True][name], grads[False][name], rtol=1e-5, atol=1e-7)
