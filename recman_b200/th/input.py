@@ -379,3 +379,43 @@ class DataInputs(dict):
 
     def multi_val_csv_inputs(self, feat_dict):
         return [self[f.name] for f in feat_dict.multi_val_csv_feats]
+
+
+class HostPrefetcher:
+    """Double-buffered host->device input pipeline: while step i runs, the pinned host buffers of step
+    i+1 are already on their way over PCIe on a copy stream, so the GPU is not input-starved.
+
+    ``source(i)`` returns the pinned host tensors ``(sparse_ids int64 [B,m], dense float32 [B,n] | None, y float32 [B])``
+    of step i.  ``get(i)`` returns the device ``DataInputs`` of step i (copied on the copy stream, the current stream
+    waits for the copy) and starts the copy of step i+1.  Every step's copy happens, one step early.
+    """
+
+    def __init__(self, feat_dict: "FeatureDictionary", source, device=None):
+        self.feat_dict = feat_dict
+        self.source = source
+        self.device = torch.device(device if device is not None else "cuda")
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._pending = None  # (step index, device tensors, copy-done event)
+        self.h2d_bytes = 0
+
+    def _stage(self, i):
+        host = self.source(i)
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.stream):
+            dev = tuple(None if t is None else t.to(self.device, non_blocking=True) for t in host)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        for t in dev:
+            if t is not None:
+                t.record_stream(cur)  # allocated on the copy stream, consumed on the compute stream
+                self.h2d_bytes += t.numel() * t.element_size()
+        return i, dev, ev
+
+    def get(self, i) -> "DataInputs":
+        if self._pending is None or self._pending[0] != i:
+            self._pending = self._stage(i)
+        _, (ids, dense, y), ev = self._pending
+        self._pending = self._stage(i + 1)
+        torch.cuda.current_stream(self.device).wait_event(ev)
+        return DataInputs.from_tensors(self.feat_dict, ids, dense, y)
+

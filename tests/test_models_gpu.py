@@ -211,3 +211,30 @@ def test_deepfm_fm_backward_fused_into_first_layer_matches_separate_kernels():
         grads[fuse] = g
     for name in grads[True]:
         torch.testing.assert_close(grads[True][name], grads[False][name], rtol=1e-5, atol=1e-7)
+
+
+def test_host_prefetcher_delivers_every_batch_in_order():
+    """Double-buffered H2D (N2): get(i) returns batch i on the device while batch i+1 is already being copied."""
+    from recman_b200.th.input import HostPrefetcher
+
+    fd = pu.make_feat_dict([50, 7, 1000], n_dense=2)
+    g = torch.Generator().manual_seed(0)
+    host = []
+    for i in range(5):
+        ids = torch.randint(0, 7, (64, 3), generator=g).pin_memory()
+        dense = torch.randn(64, 2, generator=g).pin_memory()
+        y = torch.rand(64, generator=g).pin_memory()
+        host.append((ids, dense, y))
+    pf = HostPrefetcher(fd, lambda i: host[i % 5], "cuda")
+    for i in list(range(7)) + [3, 4]:  # sequential use, then a jump (re-stages)
+        inp = pf.get(i)
+        a, b, c = host[i % 5]
+        torch.cuda.synchronize()
+        assert torch.equal(inp.sparse_ids.cpu(), a) and torch.equal(inp.dense.cpu(), b) and torch.equal(inp["y"].cpu(), c)
+        assert pf._pending[0] == i + 1
+    assert pf.h2d_bytes > 0
+    # no dense features
+    fd2 = pu.make_feat_dict([50, 7, 1000], n_dense=0)
+    pf2 = HostPrefetcher(fd2, lambda i: (host[i % 5][0], None, host[i % 5][2]), "cuda")
+    inp = pf2.get(0)
+    assert inp.dense is None and torch.equal(inp.sparse_ids.cpu(), host[0][0])
