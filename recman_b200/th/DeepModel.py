@@ -392,6 +392,58 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
             p.grad = None
         ops.dense_opt_step_multi(dense_pairs, kind, lr, 0.0)
 
+    # ------------------------------------------------------------------ N2: encode once, prefetch batches
+    def _encode_once(self, X, y):
+        """Whole training frame -> pinned host arrays (ids int64 [n, m], dense float32 [n, nd] | None, y float32 [n]).
+
+        The reference re-encodes every mini-batch with pandas / LabelEncoder (inputs.py:128-139, DeepModel.py:188); the
+        encoders are row-wise, so encoding the frame once and slicing gives the same batches.  Only for models whose
+        features are one-hot sparse + dense (multi-valued CSV fields keep the per-batch path); returns None otherwise."""
+        fd = self.feat_dict
+        if fd.multi_val_csv_feats or not fd.sparse_feats or self.device.type != "cuda":
+            return None
+        from .input import _column
+
+        ids = np.concatenate([f(_column(X, f.name)) for f in fd.sparse_feats], axis=1).astype(np.int64)
+        dense = None
+        if fd.dense_feats:
+            dense = np.concatenate([f(_column(X, f.name)) for f in fd.dense_feats], axis=1).astype(np.float32)
+        yv = np.asarray(y, dtype=np.float32).reshape(-1)
+        pin = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return pin(ids), pin(dense), pin(yv)
+
+    @staticmethod
+    def _permute_encoded(enc, perm):
+        idx = torch.from_numpy(np.asarray(perm, dtype=np.int64))
+        out = []
+        for t in enc:
+            if t is None:
+                out.append(None)
+            else:
+                buf = torch.empty_like(t).pin_memory()
+                torch.index_select(t, 0, idx, out=buf)
+                out.append(buf)
+        return tuple(out)
+
+    def _fit_epoch_prefetched(self, enc, total_batch, show_every):
+        from .input import HostPrefetcher
+
+        ids, dense, y = enc
+        n, bs = y.shape[0], self.batch_size
+
+        def source(i):
+            lo, hi = min(i * bs, n), min((i + 1) * bs, n)
+            return ids[lo:hi], (None if dense is None else dense[lo:hi]), y[lo:hi]
+
+        pf = HostPrefetcher(self.feat_dict, source, self.device)
+        for i in range(total_batch):
+            if min(i * bs, n) == min((i + 1) * bs, n):
+                continue  # the reference's empty trailing batch
+            self.fit_on_batch(pf.get(i), None)
+            if i % show_every == 0:
+                log.info(f"Fit: {(i + 1)}/{total_batch} has been completed")
+        torch.cuda.synchronize(self.device)  # the pinned epoch buffers are about to be replaced
+
     def _eval_at_epoch(self, X_train, y_train, X_valid=None, y_valid=None, start_time=None, epoch=0,
                        batch_number_to_show_progress=50):
         start_time = time() if start_time is None else start_time
@@ -411,19 +463,24 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
         y_train = np.asarray(y_train)
         eval_results = self._eval_at_epoch(X_train, y_train, X_valid, y_valid, time())
         self.history = [eval_results]
+        enc = self._encode_once(X_train, y_train)  # one-hot + dense models: encode once, then pinned slices + prefetch
         for epoch in range(1, self.epoch + 1):
             t0 = time()
             seed = np.random.randint(1, 2019) if random_seed_for_mini_batch else self.random_seed
             perm = _shuffle(len(y_train), seed)
             X_train, y_train = _take(X_train, perm), y_train[perm]
             total_batch = len(y_train) // self.batch_size + 1
-            for i in range(total_batch):
-                Xi_batch, y_batch = self.get_batch(X_train, y_train, self.batch_size, i)
-                if len(y_batch) == 0:
-                    continue
-                self.fit_on_batch(Xi_batch, y_batch)
-                if i % batch_number_to_show_progress == 0:
-                    log.info(f"Fit: {(i + 1)}/{total_batch} has been completed")
+            if enc is not None:
+                enc = self._permute_encoded(enc, perm)
+                self._fit_epoch_prefetched(enc, total_batch, batch_number_to_show_progress)
+            else:
+                for i in range(total_batch):
+                    Xi_batch, y_batch = self.get_batch(X_train, y_train, self.batch_size, i)
+                    if len(y_batch) == 0:
+                        continue
+                    self.fit_on_batch(Xi_batch, y_batch)
+                    if i % batch_number_to_show_progress == 0:
+                        log.info(f"Fit: {(i + 1)}/{total_batch} has been completed")
             log.info(f"Fit: {total_batch}/{total_batch} has been completed [{time() - t0:.1f} s]")
             eval_results = self._eval_at_epoch(X_train, y_train, X_valid, y_valid, time(), epoch,
                                                batch_number_to_show_progress)

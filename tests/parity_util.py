@@ -128,7 +128,7 @@ def oracle_loss(model, X, y, dtype=torch.float64):
     dense = None
     if fd.dense_feats:
         dense = torch.stack([torch.from_numpy(np.asarray(X[f.name], dtype=np.float32)).to(dtype) for f in fd.dense_feats], 1)
-    yt = torch.from_numpy(np.asarray(y, dtype=np.float32)).to(dtype)
+    yt = torch.from_numpy(np.array(y, dtype=np.float32)).to(dtype)  # np.array: a writable copy
     emb_l2 = hp.get("embedding_l2_reg", 0.0) * sum(oracle.l2_loss(t) for t in tabs) if layer.l2_reg else 0.0
     if isinstance(model, DeepFM):
         lin = _oracle_linear(fd, model.linear, st, X, dtype)

@@ -238,3 +238,26 @@ def test_host_prefetcher_delivers_every_batch_in_order():
     pf2 = HostPrefetcher(fd2, lambda i: (host[i % 5][0], None, host[i % 5][2]), "cuda")
     inp = pf2.get(0)
     assert inp.dense is None and torch.equal(inp.sparse_ids.cpu(), host[0][0])
+
+
+def test_fit_encode_once_prefetch_path_equals_per_batch_path():
+    """fit(): encoding the frame once + pinned slices + HostPrefetcher (N2) trains exactly like re-encoding every batch."""
+    from recman_b200.th import DeepFM
+    from recman_b200.th.DeepModel import DeepModel
+
+    fd = pu.make_feat_dict([50, 7, 1000, 3], n_dense=3)
+    X, y = pu.synth_batch(fd, 1000, seed=11)  # 1000 = 3 full batches of 300 + a ragged one
+    kw = dict(embedding_size=8, deep_hidden_units=(32, 32), deep_dropout=(1, 1, 1), batch_size=300, epoch=2,
+              learning_rate=0.01, embedding_l2_reg=0.0, linear_l2_reg=0.0)
+    fast = DeepFM(fd, **kw)
+    fast.fit(X, y, random_seed_for_mini_batch=False)
+    slow = DeepFM(fd, **kw)
+    orig = DeepModel._encode_once
+    DeepModel._encode_once = lambda self, X_, y_: None
+    try:
+        slow.fit(X, y, random_seed_for_mini_batch=False)
+    finally:
+        DeepModel._encode_once = orig
+    assert fast.samples_seen == slow.samples_seen == 2000
+    for name, p in fast.variables.items():
+        assert torch.equal(p.data, slow.variables[name].data), name
