@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RM_ABI_VERSION 1
+#define RM_ABI_VERSION 2 /* 2: workspaces on the segmented reduces, gathered k=1 gradients, narrow-layer kernels */
 
 #define RM_E_INVALID (-1)     /* bad argument (null pointer, negative size, ...) */
 #define RM_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
