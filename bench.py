@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=None, help="rows per table (override)")
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (override)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): the workload's batch per GPU; strong: the workload's batch is the GLOBAL batch")
     ap.add_argument("--k", type=int, default=None)
     ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -146,6 +148,8 @@ def build_model(w, args, world, rank):
     for j in range(w["n_dense"]):
         fd[f"I{j}"] = DenseFeat(f"I{j}", scaler=False)
     B = args.batch or w["batch"]
+    if args.scaling == "strong":  # fixed global batch, split evenly over the ranks
+        B = max(1, B // world)
     common = dict(embedding_size=k, embedding_l2_reg=0.0, linear_l2_reg=0.0, batch_size=B, learning_rate=1e-3,
                   optimizer="adam")
     if w["model"] == "DeepFM":
@@ -395,7 +399,7 @@ def run_ours(args):
         out = {
             "metric": "CTR train samples/sec", "value": round(value, 1), "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["desc"], "model": w["model"], "fields": m, "rows_per_table": rows, "k": k,
                        "n_dense": n_dense, "batch_per_gpu": B, "global_batch": B * world, "ids": args.ids,
                        "optimizer": "adam (fresh per batch, as the reference)", "l2_flush":
