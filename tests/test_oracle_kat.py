@@ -239,3 +239,34 @@ def test_fresh_adam_first_step_is_sign_like():
     new = oracle.fresh_optimizer_step(p, g, "adam", 0.01)
     assert abs(new[0].item() + 0.01) < 1e-6 and abs(new[1].item() - 0.01) < 1e-6 and new[2].item() == 0.0
     assert torch.equal(oracle.fresh_optimizer_step(p, g, "gd", 0.1), -0.1 * g)
+
+
+def test_segment_sum_sorted_long_segments_are_chunked():
+    """Hot rows: a segment longer than SEG_LONG positions is summed chunk-wise (SEG_CHUNK positions sequentially per
+    partial, partials in chunk order) - the association the CUDA kernels commit to.  Short segments stay sequential."""
+    from oracle.segment import SEG_CHUNK, SEG_LONG
+
+    rng = np.random.RandomState(0)
+    n_long = 3 * SEG_CHUNK + 5
+    keys = np.concatenate([np.full(n_long, 7), np.full(SEG_LONG, 3), [9]]).astype(np.int64)
+    perm = rng.permutation(len(keys))
+    keys = keys[perm]
+    g = (rng.randn(len(keys), 2) * 1e3).astype(np.float32)
+    uniq, sums, order, seg = oracle.segment_sum_sorted(keys, g)
+    assert uniq.tolist() == [3, 7, 9] and np.diff(seg).tolist() == [SEG_LONG, n_long, 1]
+    gs = g[order]
+    seq = np.zeros(2, np.float32)
+    for row in gs[seg[0]:seg[1]]:
+        seq = (seq + row).astype(np.float32)
+    assert np.array_equal(sums[0], seq)  # exactly SEG_LONG positions: still the plain sequential sum
+    total = np.zeros(2, np.float32)
+    for c0 in range(int(seg[1]), int(seg[2]), SEG_CHUNK):
+        part = np.zeros(2, np.float32)
+        for row in gs[c0:min(c0 + SEG_CHUNK, int(seg[2]))]:
+            part = (part + row).astype(np.float32)
+        total = (total + part).astype(np.float32)
+    assert np.array_equal(sums[1], total)
+    _, plain, _, _ = oracle.segment_sum_sorted(keys, g, chunked=False)
+    np.testing.assert_allclose(sums, plain, rtol=1e-5, atol=1e-2)
+    dense = oracle.dense_table_grad(keys, g, 10)
+    np.testing.assert_allclose(sums, dense[uniq], rtol=1e-5, atol=1e-2)
