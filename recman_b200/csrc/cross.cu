@@ -227,7 +227,7 @@ struct CrossWs {
 static CrossWs cross_layout(int64_t B, int d, int L, void* base) {
   CrossWs w;
   const int L1 = L + 1;
-  int64_t nblk = ceil_div(B, 64);  // >= 64 samples per chunk: the ordered final sums stay short
+  int64_t nblk = ceil_div(B, 16);  // small chunks: the chunk kernel is a serial walk per column, the final pass is parallel
   if (nblk > 2 * RM_NUM_SMS) nblk = 2 * RM_NUM_SMS;
   if (nblk < 1) nblk = 1;
   w.chunk = ceil_div(B, nblk);
