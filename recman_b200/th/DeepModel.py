@@ -209,15 +209,35 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
         dummy_y = np.ones(n, dtype=np.float32)
         outs = []
         total_batch = n // self.batch_size + 1
+        enc = self._encode_once(X, dummy_y) if n > 0 else None  # one-hot + dense: encode once, prefetch pinned slices
         with torch.no_grad():
-            for batch_index in range(total_batch):
-                x_batch, y_batch = self.get_batch(X, dummy_y, self.batch_size, batch_index)
-                if len(y_batch) == 0:  # the reference feeds this empty batch to TF; nothing to compute
-                    continue
-                inputs = DataInputs(self.device).load(self.feat_dict, x_batch, y_batch)
-                outs.append(self._out(inputs, training=training).reshape(-1))
-                if batch_index % batch_number_to_show_progress == 0:
-                    log.info(f"Predict: {(batch_index + 1)}/{total_batch} has been completed")
+            if enc is not None:
+                from .input import HostPrefetcher
+
+                ids, dense, yy = enc
+                bs = self.batch_size
+
+                def source(i):
+                    lo, hi = min(i * bs, n), min((i + 1) * bs, n)
+                    return ids[lo:hi], (None if dense is None else dense[lo:hi]), yy[lo:hi]
+
+                pf = HostPrefetcher(self.feat_dict, source, self.device)
+                for batch_index in range(total_batch):
+                    if min(batch_index * bs, n) == min((batch_index + 1) * bs, n):
+                        continue
+                    outs.append(self._out(pf.get(batch_index), training=training).reshape(-1))
+                    if batch_index % batch_number_to_show_progress == 0:
+                        log.info(f"Predict: {(batch_index + 1)}/{total_batch} has been completed")
+                torch.cuda.synchronize(self.device)
+            else:
+                for batch_index in range(total_batch):
+                    x_batch, y_batch = self.get_batch(X, dummy_y, self.batch_size, batch_index)
+                    if len(y_batch) == 0:  # the reference feeds this empty batch to TF; nothing to compute
+                        continue
+                    inputs = DataInputs(self.device).load(self.feat_dict, x_batch, y_batch)
+                    outs.append(self._out(inputs, training=training).reshape(-1))
+                    if batch_index % batch_number_to_show_progress == 0:
+                        log.info(f"Predict: {(batch_index + 1)}/{total_batch} has been completed")
         log.info(f"Predict: {total_batch}/{total_batch} has been completed")
         if not outs:
             return np.zeros((0,), dtype=np.float32)

@@ -116,6 +116,15 @@ def test_predict_and_evaluate_batches():
     p2 = model.predict({k: v[:128] for k, v in X.items()})  # 128 % 64 == 0: the reference's empty trailing batch
     assert p2.shape == (128,)
     np.testing.assert_array_equal(p[:128], p2)
+    # the encode-once + prefetch path (N2) returns what per-batch encoding returns
+    from recman_b200.th.DeepModel import DeepModel
+
+    orig = DeepModel._encode_once
+    DeepModel._encode_once = lambda self, X_, y_: None
+    try:
+        np.testing.assert_array_equal(model.predict(X), p)
+    finally:
+        DeepModel._encode_once = orig
     model.fit(X, y, random_seed_for_mini_batch=False)
     res = model.evaluate(X, y)
     assert len(res) == 2 and all(np.isfinite(r) for r in res)
