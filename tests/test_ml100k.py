@@ -149,3 +149,30 @@ def test_c1_fit_on_ml100k_sample_learns():
     assert np.isfinite(vll) and vauc > 0.5
     pred = model.predict(valid)
     assert pred.shape[0] == len(valid) and float(pred.min()) >= 0.0 and float(pred.max()) <= 1.0
+
+
+@pytest.mark.gpu
+def test_xdeepfm_sweep_with_best_model_finder_on_ml100k_sample(tmp_path):
+    """The reference's xDeepFM example workflow (examples/xDeepFM_ml.py): grid search over the learning rate, best model
+    kept (and saved) by the epoch callback, restored into a fresh model."""
+    import torch
+
+    from recman_b200.examples.xDeepFM_ml import sweep
+    from recman_b200.th import xDeepFM
+
+    df, domains = _sample()
+    train, valid, test = df.iloc[:2000], df.iloc[2000:2600], df.iloc[2600:]
+    finder, fd = sweep(train, valid, test, domains, learning_rates=(0.01, 0.002), epoch=1, batch_size=128,
+                       save_model=True, out_dir=str(tmp_path))
+    best = finder.best_model
+    assert best is not None and best.hparams["learning_rate"] in (0.01, 0.002)
+    train_res, valid_res = finder.best_eval_results
+    assert finder.best_score == float(valid_res[0]) and np.isfinite(finder.best_score)
+    assert (tmp_path / "ckpt_model.pt").exists() and (tmp_path / "hparams").exists() and (tmp_path / "feat_dict").exists()
+    pred = best.predict(test)
+    assert pred.shape == (len(test),) and np.all((pred > 0) & (pred < 1))
+    # restore the saved variables into a fresh model: same predictions
+    fresh = xDeepFM(fd, dict(best.hparams), batch_size=128)
+    fresh.predict(test.iloc[:4])  # creates the variables
+    fresh.restore(str(tmp_path / "ckpt_model.pt"))
+    np.testing.assert_allclose(fresh.predict(test), pred, rtol=1e-5, atol=1e-6)
