@@ -176,3 +176,18 @@ def test_xdeepfm_sweep_with_best_model_finder_on_ml100k_sample(tmp_path):
     fresh.predict(test.iloc[:4])  # creates the variables
     fresh.restore(str(tmp_path / "ckpt_model.pt"))
     np.testing.assert_allclose(fresh.predict(test), pred, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_dcn_example_on_ml100k_sample():
+    """recman/examples/DCN_ml.py on the sample: DCN with the multi-valued genres field (sqrtn-pooled lookup) trains."""
+    from recman_b200.examples.DCN_ml import train
+
+    df, domains = _sample()
+    model, _ = train(df.iloc[:2400], df.iloc[2400:2700], df.iloc[2700:], domains, epoch=3, batch_size=128,
+                     learning_rate=0.01)
+    (ll0, auc0), _ = model.history[0]
+    (ll1, auc1), (vll, vauc) = model.history[-1]
+    assert ll1 < ll0 and auc1 > auc0 and np.isfinite(vll) and 0.0 <= vauc <= 1.0
+    pred = model.predict(df.iloc[2700:])
+    assert pred.shape == (300,) and np.all((pred >= 0) & (pred <= 1))
