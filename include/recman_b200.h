@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RM_ABI_VERSION 2 /* 2: workspaces on the segmented reduces, gathered k=1 gradients, narrow-layer kernels */
+#define RM_ABI_VERSION 3 /* 3: fused DeepFM tower entry points (rm_tower_*) */
 
 #define RM_E_INVALID (-1)     /* bad argument (null pointer, negative size, ...) */
 #define RM_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
@@ -44,6 +44,7 @@ extern "C" {
 #define RM_OPT_ADAM 0
 #define RM_OPT_ADAGRAD 1
 #define RM_OPT_GD 2
+#define RM_OPT_NONE (-1) /* rm_tower_bwd_update only: compute gradients, leave the tables untouched */
 
 /* activation kinds for rm_cin_* : hparams/xDeepFM.py:29,33 (tf.nn.leaky_relu, alpha 0.2) */
 #define RM_ACT_IDENTITY 0
@@ -225,6 +226,10 @@ size_t rm_cin_layer_bwd_workspace_bytes(int64_t B, int32_t m, int32_t H, int32_t
 int rm_sparse_opt_step(float* table, int32_t k, const int64_t* uniq_rows, const float* rows,
                        const int32_t* n_unique, int64_t max_rows, int32_t opt, float lr, float l2,
                        void* stream);
+/* The same with rows `row_stride` floats apart (the k = 1 tables interleaved as [rows, 2], see rm_tower_fwd). */
+int rm_sparse_opt_step_strided(float* table, int32_t k, int64_t row_stride, const int64_t* uniq_rows,
+                               const float* rows, const int32_t* n_unique, int64_t max_rows, int32_t opt,
+                               float lr, float l2, void* stream);
 int rm_dense_opt_step(float* p, const float* g, int64_t n, int32_t opt, float lr, float l2,
                       void* stream);
 /* The same update for `count` tensors in one launch (per 96 tensors): ps / gs / ns are HOST arrays of device
@@ -335,6 +340,54 @@ int rm_segment_reduce_p2p_update(const float* const* G, const float* gscal, int3
                                  const int32_t* n_unique, float* table, float* bias_table,
                                  float* lin_table, int32_t opt, float lr, float l2, void* workspace,
                                  size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * T   fused DeepFM "tower": front end + first DNN layer on tcgen05 (forward), and the
+ *     whole sparse backward + optimizer in one sorted pass (backward).
+ * replaces, forward : FeatEmbeddingLayer.__call__ layers.py:238-261 (gather), FMLayer
+ *     layers.py:457-478, LinearLayer layers.py:330-347 and the first matmul + bias_add of
+ *     DNN.__call__ layers.py:589-609, composed as in tf/core/DeepFM.py:107-163;
+ * replaces, backward: TF autodiff of the same ops (IndexedSlices gradient of
+ *     tf.nn.embedding_lookup with duplicate rows summed) + the per-batch optimizer of
+ *     xDeepFM.py:116-126.
+ * The two k=1 tables (embedding bias layers.py:124-128, first-order weight :418-439) are ONE
+ * interleaved [rows, 2] array `scal` = (bias, weight): one 8-byte lookup per id.
+ * Forward: y1[b, :] = [embeds | dense] @ W1 + b1 (pre-activation, 3xTF32 on the tensor
+ * core, fp32 result), fm_out / lin_out / sum_out as rm_gather_fm_fwd; the row buffer x is
+ * optional (NULL: never written).  k in {32, 64}, N1 <= 64.
+ * Backward: rm_tower_plan sorts (row, position) and cuts work units; rm_tower_bwd_update
+ * then gathers each touched row once, forms g1 @ W1_f^T + g_fm * (S - row) per position
+ * on the tensor core, sums positions of the same row in ascending position order
+ * (deterministic), applies the stateless first-step optimizer in place and accumulates
+ * dW1[:m*k] = x^T @ g1.  k = 64, N1 = 32.  out_rows / out_scal (nullable): summed
+ * gradient row / (bias, weight) gradient written at the sorted position that closes its
+ * segment (tests); opt == RM_OPT_NONE skips the update.
+ * ------------------------------------------------------------------------- */
+int rm_tower_supported(int32_t m, int32_t k, int32_t n_dense, int32_t N1);
+size_t rm_tower_fwd_workspace_bytes(int32_t m, int32_t k, int32_t N1);
+int rm_tower_fwd(const float* table, const float* scal, const int64_t* table_offsets,
+                 const int64_t* ids, const float* dense, const float* lin_dense,
+                 int32_t lin_dense_stride, int32_t n_dense, const float* W1, const float* b1,
+                 int32_t N1, int64_t B, int32_t m, int32_t k, float* x, int64_t ld, float* y1,
+                 float* fm_out, float* lin_out, float* sum_out, int32_t* status, void* workspace,
+                 size_t workspace_bytes, void* stream);
+int32_t rm_tower_units_per_field(int64_t B, int32_t unit);
+size_t rm_tower_plan_workspace_bytes(int64_t N);
+int rm_tower_plan(const int64_t* ids, const int64_t* table_offsets, int64_t B, int32_t m,
+                  int64_t total_rows, int32_t unit, void* workspace, size_t workspace_bytes,
+                  uint32_t* sorted_keys, int32_t* sorted_pos, int32_t* field_bounds,
+                  int32_t* unit_bounds, int32_t* status, void* stream);
+size_t rm_tower_bwd_workspace_bytes(int64_t B, int32_t m, int32_t unit);
+int rm_tower_bwd_update(float* table, float* scal, const uint32_t* sorted_keys,
+                        const int32_t* sorted_pos, const int32_t* unit_bounds, const float* g1,
+                        const float* S, const float* g_fm, const float* g_lin, const float* W1,
+                        int64_t B, int32_t m, int32_t k, int32_t N1, int32_t unit, int32_t opt,
+                        float lr, float l2, float* dW1, float* out_rows, float* out_scal,
+                        int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+/* Test-only: D[128,32] = At^T @ Bt (At [K,128], Bt [K,32]) through the MN-major SWIZZLE_128B
+ * operand layout of the tower backward's weight-gradient GEMM (variant 0 = the layout used). */
+int rm_umma_probe(const float* At, const float* Bt, int32_t K, int32_t variant, float* D,
+                  int32_t* status, void* stream);
 
 #ifdef __cplusplus
 }

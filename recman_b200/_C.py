@@ -92,12 +92,28 @@ _SIGS = {
         ctypes.c_int,
         [P, P, c_int32, c_int32, c_int64, c_int32, c_int32, c_int64, P, P, P, P, P, P, P, c_int32, c_float, c_float, P, c_size_t, P]),
     "rm_sparse_opt_step": (ctypes.c_int, [P, c_int32, P, P, P, c_int64, c_int32, c_float, c_float, P]),
+    "rm_sparse_opt_step_strided": (ctypes.c_int, [P, c_int32, c_int64, P, P, P, c_int64, c_int32, c_float, c_float, P]),
     "rm_dense_opt_step": (ctypes.c_int, [P, P, c_int64, c_int32, c_float, c_float, P]),
     "rm_linear_bwd_input": (ctypes.c_int, [P, c_int64, c_int32, P, c_int32, P, c_int64, P]),
     "rm_linear_bwd_input_fm": (ctypes.c_int, [P, c_int64, c_int32, P, c_int32, c_int32, P, c_int64, P, P, P, P]),
     "rm_linear_bwd_weight_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "rm_linear_bwd_weight": (ctypes.c_int, [P, c_int64, P, c_int64, c_int32, c_int32, P, P, c_size_t, P]),
     "rm_dense_opt_step_multi": (ctypes.c_int, [P, P, P, c_int32, c_int32, c_float, c_float, P]),
+    "rm_tower_supported": (ctypes.c_int, [c_int32, c_int32, c_int32, c_int32]),
+    "rm_tower_fwd_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "rm_tower_fwd": (
+        ctypes.c_int,
+        [P, P, P, P, P, P, c_int32, c_int32, P, P, c_int32, c_int64, c_int32, c_int32, P, c_int64, P, P, P, P, P, P,
+         c_size_t, P]),
+    "rm_tower_units_per_field": (c_int32, [c_int64, c_int32]),
+    "rm_tower_plan_workspace_bytes": (c_size_t, [c_int64]),
+    "rm_tower_plan": (ctypes.c_int, [P, P, c_int64, c_int32, c_int64, c_int32, P, c_size_t, P, P, P, P, P, P]),
+    "rm_tower_bwd_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
+    "rm_tower_bwd_update": (
+        ctypes.c_int,
+        [P, P, P, P, P, P, P, P, P, P, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_float, P, P, P,
+         P, P, c_size_t, P]),
+    "rm_umma_probe": (ctypes.c_int, [P, P, c_int32, c_int32, P, P, P]),
 }
 
 EXPORTS = tuple(_SIGS)

@@ -413,3 +413,81 @@ class NarrowLinearFunction(Function):
             dW = x.t() @ g
             dx = g @ W.t() if ctx.needs_input_grad[0] else None
         return dx, dW, db
+
+
+# --------------------------------------------------------------------------- #
+# fused DeepFM tower: front end + first DNN layer on tcgen05, sorted fused backward + update
+# --------------------------------------------------------------------------- #
+class TowerFunction(Function):
+    """ids -> (y1 [B, N1] = [embeds | dense] @ W1 + b1, fm [B,1], lin [B,1]) in one kernel (rm_tower_fwd).
+
+    ``scal`` is the interleaved k=1 storage [rows + n_dense, 2] = (embedding bias, first-order weight); ``bias_param`` /
+    ``W_lin`` are the parameters that view its two columns (sparse gradients are attached to them).
+    Backward, two modes:
+      * ``fused_opt`` given and (k, N1) = (64, 32): rm_tower_bwd_update - the table rows are updated in place inside
+        the backward kernel, dx / the row buffer / the summed gradients never exist in HBM;
+      * otherwise: the forward also wrote the row buffer and the backward runs the separate kernels
+        (rm_linear_bwd_*, rm_emb_fm_bwd) and attaches ``ops.SparseGrad`` s.
+    """
+
+    @staticmethod
+    def forward(ctx, table, scal, scal_fwd, bias_param, W_lin, W1, b1, offsets, total_rows, status, ids, dense,
+                fused_opt):
+        k = table.shape[1]
+        N1 = W1.shape[1]
+        n_dense = 0 if dense is None else dense.shape[1]
+        need_grad = any(ctx.needs_input_grad)
+        use_bk = need_grad and fused_opt is not None and ops.tower_bwd_supported(k, N1)
+        lin_dense = scal_fwd[total_rows:, 1] if n_dense else None
+        y1, fm, lin, S, x = ops.tower_fwd(table, scal_fwd[:total_rows], offsets, ids, dense, lin_dense, W1, b1,
+                                          want_x=need_grad and not use_bk, status=status)
+        ctx.use_bk, ctx.fused_opt = use_bk, fused_opt
+        ctx.table, ctx.scal, ctx.bias_param, ctx.W_lin = table, scal, bias_param, W_lin
+        ctx.total_rows, ctx.n_dense, ctx.status = total_rows, n_dense, status
+        ctx.plan = None
+        if need_grad:  # the plans need the ids only: built on the side stream, under the forward
+            ctx.plan = (ops.tower_plan(ids, offsets, total_rows, status=status, side=True) if use_bk
+                        else ops.segment_plan(ids, offsets, total_rows, side=True))
+        ctx.save_for_backward(x, S, ids, dense, W1)
+        ctx.set_materialize_grads(False)
+        return y1, fm.reshape(-1, 1), lin.reshape(-1, 1)
+
+    @staticmethod
+    def backward(ctx, dy1, dfm, dlin):
+        x, S, ids, dense, W1 = ctx.saved_tensors
+        B, m = ids.shape
+        k = ctx.table.shape[1]
+        N1 = W1.shape[1]
+        dev = ids.device
+        plan, ctx.plan = ctx.plan, None
+        g1 = torch.zeros(B, N1, dtype=torch.float32, device=dev) if dy1 is None else dy1.contiguous()
+        g_fm = torch.zeros(B, dtype=torch.float32, device=dev) if dfm is None else dfm.reshape(-1).contiguous()
+        g_lin = None if dlin is None else dlin.reshape(-1).contiguous()
+        db1 = g1.sum(0)
+        total = ctx.total_rows
+        if g_lin is not None and ctx.n_dense:
+            ctx.W_lin.rm_dense_tail = (total, dense.t() @ g_lin)
+        if ctx.use_bk:
+            kind, lr = ctx.fused_opt
+            dW1 = torch.empty(W1.shape, dtype=torch.float32, device=dev)
+            dW1_emb = ops.tower_bwd_update(ctx.table.data, ctx.scal[:total], plan, g1, S, g_fm, g_lin, W1.data, kind, lr,
+                                           status=ctx.status)
+            dW1[: m * k] = dW1_emb
+            if ctx.n_dense:
+                torch.mm(dense.t(), g1, out=dW1[m * k :])
+            return (None, None, None, None, None, dW1, db1) + (None,) * 6
+        d = m * k + ctx.n_dense
+        ld = x.shape[1]
+        if ops.narrow_linear_ok(N1):
+            dW1 = ops.linear_bwd_weight(x, ld, d, g1)
+            dxbuf = ops.linear_bwd_input(g1, W1.data, d_ld=ld)
+        else:
+            dW1 = x[:, :d].t() @ g1
+            dxbuf = torch.zeros_like(x)
+            torch.mm(g1, W1.t(), out=dxbuf[:, :d])
+        rows, ob, ol = ops.emb_fm_bwd(dxbuf, x, ld, S, g_fm, g_lin, plan, k, True, True, g_lin is not None)
+        attach_sparse_grad(ctx.table, ops.SparseGrad(plan.uniq_rows, rows, plan.n_unique))
+        attach_sparse_grad(ctx.bias_param, ops.SparseGrad(plan.uniq_rows, ob, plan.n_unique))
+        if g_lin is not None:
+            attach_sparse_grad(ctx.W_lin, ops.SparseGrad(plan.uniq_rows, ol, plan.n_unique))
+        return (None, None, None, None, None, dW1, db1) + (None,) * 6

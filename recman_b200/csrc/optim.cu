@@ -8,7 +8,7 @@
 
 namespace rm {
 
-__global__ void __launch_bounds__(256) sparse_opt_kernel(float* __restrict__ table, int k,
+__global__ void __launch_bounds__(256) sparse_opt_kernel(float* __restrict__ table, int k, int64_t row_stride,
                                                          const int64_t* __restrict__ uniq_rows,
                                                          const float* __restrict__ rows,
                                                          const int32_t* __restrict__ n_unique, OptParams o) {
@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(256) sparse_opt_kernel(float* __restrict__ tab
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t u = i / k;
     const int c = (int)(i - u * k);
-    float* p = table + uniq_rows[u] * (int64_t)k + c;
+    float* p = table + uniq_rows[u] * row_stride + c;
     *p = opt_update(*p, rows[i], o);
   }
 }
@@ -68,6 +68,22 @@ __global__ void __launch_bounds__(256) dense_opt_multi_kernel(const DenseBatch b
 
 extern "C" {
 
+int rm_sparse_opt_step_strided(float* table, int32_t k, int64_t row_stride, const int64_t* uniq_rows, const float* rows,
+                               const int32_t* n_unique, int64_t max_rows, int32_t opt, float lr, float l2,
+                               void* stream) {
+  using namespace rm;
+  RM_CHECK_ARG(table && uniq_rows && rows && n_unique, "null pointer");
+  RM_CHECK_ARG(k > 0 && max_rows >= 0 && row_stride >= k, "bad shape");
+  OptParams o;
+  int rc = make_params(opt, lr, l2, &o);
+  if (rc) return rc;
+  if (max_rows == 0) return 0;
+  sparse_opt_kernel<<<grid_for(max_rows * k, 256, 8), 256, 0, (cudaStream_t)stream>>>(table, k, row_stride, uniq_rows,
+                                                                                    rows, n_unique, o);
+  RM_LAUNCH_CHECK();
+  return 0;
+}
+
 int rm_sparse_opt_step(float* table, int32_t k, const int64_t* uniq_rows, const float* rows, const int32_t* n_unique,
                        int64_t max_rows, int32_t opt, float lr, float l2, void* stream) {
   using namespace rm;
@@ -82,7 +98,7 @@ int rm_sparse_opt_step(float* table, int32_t k, const int64_t* uniq_rows, const 
     sparse_opt_vec_kernel<<<grid_for(max_rows * (k / 4), 256, 8), 256, 0, st>>>(table, k / 4, uniq_rows, rows, n_unique,
                                                                                o);
   } else {
-    sparse_opt_kernel<<<grid_for(max_rows * k, 256, 8), 256, 0, st>>>(table, k, uniq_rows, rows, n_unique, o);
+    sparse_opt_kernel<<<grid_for(max_rows * k, 256, 8), 256, 0, st>>>(table, k, (int64_t)k, uniq_rows, rows, n_unique, o);
   }
   RM_LAUNCH_CHECK();
   return 0;
@@ -108,11 +124,11 @@ int rm_dense_opt_step_multi(float* const* ps, const float* const* gs, const int6
   OptParams o;
   int rc = make_params(opt, lr, l2, &o);
   if (rc) return rc;
-  for (int32_t base = 0; base < count; base += DENSE_BATCH) {
+  for (int32_t i = 0; i < count;) {  // consume tensors until a batch is full; empty tensors take no slot
     DenseBatch b;
     int nb = 0;
     int64_t max_n = 0;
-    for (int32_t i = base; i < count && nb < DENSE_BATCH; ++i) {
+    for (; i < count && nb < DENSE_BATCH; ++i) {
       RM_CHECK_ARG(ns[i] >= 0 && ns[i] < ((int64_t)1 << 32), "tensor too large for the multi-tensor update");
       if (ns[i] == 0) continue;
       RM_CHECK_ARG(ps[i] && gs[i], "null pointer");

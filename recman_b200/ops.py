@@ -427,6 +427,13 @@ def cin_layer_bwd(x0, xk, W, pre, dout, act: int, precision: int, dx0, dxk):
 def sparse_opt_step(table, sg: SparseGrad, opt: int, lr: float, l2: float = 0.0):
     _dev_check(table)
     k = table.shape[1] if table.dim() == 2 else 1
+    if not table.is_contiguous():  # a column of the interleaved [rows, 2] k=1 storage (tower layout)
+        assert k == 1 and table.stride(0) > 1
+        _C.call(
+            "rm_sparse_opt_step_strided", _p(table), 1, table.stride(0), _p(sg.uniq_rows), _p(sg.rows), _p(sg.n_unique),
+            sg.uniq_rows.numel(), opt, float(lr), float(l2), _stream(),
+        )
+        return
     _C.call(
         "rm_sparse_opt_step", _p(table), k, _p(sg.uniq_rows), _p(sg.rows), _p(sg.n_unique), sg.uniq_rows.numel(), opt,
         float(lr), float(l2), _stream(),
@@ -435,7 +442,13 @@ def sparse_opt_step(table, sg: SparseGrad, opt: int, lr: float, l2: float = 0.0)
 
 def dense_opt_step(p, g, opt: int, lr: float, l2: float = 0.0):
     _dev_check(p)
-    assert p.is_contiguous() and g.is_contiguous() and p.numel() == g.numel()
+    assert p.numel() == g.numel()
+    g = g.contiguous()
+    if not p.is_contiguous():  # strided view (tower layout): update a packed copy, write it back
+        tmp = p.contiguous()
+        _C.call("rm_dense_opt_step", _p(tmp), _p(g), tmp.numel(), opt, float(lr), float(l2), _stream())
+        p.copy_(tmp)
+        return
     _C.call("rm_dense_opt_step", _p(p), _p(g), p.numel(), opt, float(lr), float(l2), _stream())
 
 
@@ -599,3 +612,139 @@ def segment_reduce_p2p(G_ptrs, rows_per_rank, KP, k, plan: SegmentPlan, want_bia
         wsn, _stream(),
     )
     return out_rows, out_bias, out_lin
+
+
+# --------------------------------------------------------------------------- #
+# T  fused DeepFM tower (front end + first DNN layer on tcgen05; sorted fused backward + update)
+# --------------------------------------------------------------------------- #
+TOWER_UNIT = 2048  # sorted positions per work unit of the fused backward (16 tiles)
+
+
+def tower_supported(m: int, k: int, n_dense: int, N1: int) -> bool:
+    return bool(_C.lib.rm_tower_supported(int(m), int(k), int(n_dense), int(N1)))
+
+
+def tower_bwd_supported(k: int, N1: int) -> bool:
+    return k == 64 and N1 == 32
+
+
+def tower_fwd(table, scal, table_offsets, ids, dense, lin_dense, W1, b1, want_x=False, status=None):
+    """Fused front end + first DNN layer.  ``scal`` [rows, 2] = (bias, first-order weight) interleaved (or None),
+    ``lin_dense`` a 1-D (possibly strided) view of the dense first-order weights (or None), ``W1`` [m*k+n_dense, N1].
+    Returns (y1 [B,N1] pre-activation, fm [B], lin [B], S [B,k], x [B,ld] | None)."""
+    _dev_check(table)
+    _f32c(table, "table")
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and table.is_contiguous()
+    B, m = ids.shape
+    k = table.shape[1]
+    n_dense = 0 if dense is None else dense.shape[1]
+    d = m * k + n_dense
+    N1 = W1.shape[1]
+    assert W1.shape[0] == d and W1.is_contiguous() and b1.is_contiguous() and b1.numel() == N1
+    dev = table.device
+    x = None
+    ld = (d + 3) // 4 * 4
+    if want_x:
+        x = torch.empty(B, ld, dtype=torch.float32, device=dev)
+        if ld > d:
+            x[:, d:].zero_()
+    y1 = torch.empty(B, N1, dtype=torch.float32, device=dev)
+    fm = torch.empty(B, dtype=torch.float32, device=dev)
+    lin = torch.empty(B, dtype=torch.float32, device=dev)
+    S = torch.empty(B, k, dtype=torch.float32, device=dev)
+    if dense is not None:
+        dense = _f32c(dense, "dense").contiguous()
+    if scal is not None:
+        assert scal.dim() == 2 and scal.shape[1] == 2 and scal.is_contiguous()
+    ld_stride = 1
+    if lin_dense is not None:
+        assert lin_dense.dim() == 1 and lin_dense.numel() == n_dense
+        ld_stride = lin_dense.stride(0) if n_dense > 1 else 1
+    ws_bytes = _C.lib.rm_tower_fwd_workspace_bytes(m, k, N1)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _C.call(
+        "rm_tower_fwd", _p(table), _p(scal), _p(table_offsets), _p(ids), _p(dense), _p(lin_dense), ld_stride, n_dense,
+        _p(W1), _p(b1), N1, B, m, k, _p(x), ld, _p(y1), _p(fm), _p(lin), _p(S), _p(status), _p(ws), ws_bytes, _stream(),
+    )
+    return y1, fm, lin, S, x
+
+
+@dataclass
+class TowerPlan:
+    """Sorted (table row, position) pairs of one batch + the work units of the fused backward (ids only)."""
+
+    B: int
+    m: int
+    unit: int
+    sorted_keys: torch.Tensor  # uint32 as int32 storage [N]
+    sorted_pos: torch.Tensor  # int32 [N]
+    field_bounds: torch.Tensor  # int32 [m+1]
+    unit_bounds: torch.Tensor  # int32 [m*(upf+1)]
+    workspace: torch.Tensor
+    ready: Optional["torch.cuda.Event"] = None
+
+    def wait(self) -> None:
+        if self.ready is not None:
+            torch.cuda.current_stream().wait_event(self.ready)
+            self.ready = None
+
+
+def tower_plan(ids, table_offsets, total_rows, unit: int = TOWER_UNIT, status=None, side: bool = False) -> TowerPlan:
+    _dev_check(ids)
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and ids.dim() == 2
+    B, m = ids.shape
+    N = B * m
+    dev = ids.device
+    upf = _C.lib.rm_tower_units_per_field(B, unit)
+    ws_bytes = _C.lib.rm_tower_plan_workspace_bytes(N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    keys = torch.empty(N, dtype=torch.int32, device=dev)
+    pos = torch.empty(N, dtype=torch.int32, device=dev)
+    fb = torch.empty(m + 1, dtype=torch.int32, device=dev)
+    ub = torch.empty(m * (upf + 1), dtype=torch.int32, device=dev)
+    ev = _launch_maybe_side(side, lambda: _C.call(
+        "rm_tower_plan", _p(ids), _p(table_offsets), B, m, int(total_rows), unit, _p(ws), ws_bytes, _p(keys), _p(pos),
+        _p(fb), _p(ub), _p(status), _stream(),
+    ))
+    return TowerPlan(B, m, unit, keys, pos, fb, ub, ws, ev)
+
+
+def tower_bwd_update(table, scal, plan: TowerPlan, g1, S, g_fm, g_lin, W1, opt: int, lr: float, l2: float = 0.0,
+                     update: bool = True, debug: bool = False, status=None):
+    """Fused sparse backward + optimizer update (in place on ``table`` / ``scal``).  Returns dW1[:m*k] [m*k, N1]
+    (and, with ``debug``, the summed gradient rows / k=1 gradients at the sorted position closing each segment)."""
+    _dev_check(g1)
+    B, m = plan.B, plan.m
+    k = S.shape[1]
+    N1 = g1.shape[1]
+    assert g1.is_contiguous() and S.is_contiguous() and g_fm.is_contiguous() and W1.is_contiguous()
+    assert g1.shape[0] == B and S.shape[0] == B and g_fm.numel() == B and W1.shape[0] >= m * k and W1.shape[1] == N1
+    assert g_lin is None or (g_lin.is_contiguous() and g_lin.numel() == B)
+    dev = g1.device
+    dW1 = torch.empty(m * k, N1, dtype=torch.float32, device=dev)
+    out_rows = out_scal = None
+    if debug:
+        out_rows = torch.zeros(B * m, k, dtype=torch.float32, device=dev)
+        out_scal = torch.zeros(B * m, 2, dtype=torch.float32, device=dev)
+    ws_bytes = _C.lib.rm_tower_bwd_workspace_bytes(B, m, plan.unit)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    plan.wait()
+    _C.call(
+        "rm_tower_bwd_update", _p(table), _p(scal), _p(plan.sorted_keys),
+        _p(plan.sorted_pos), _p(plan.unit_bounds), _p(g1), _p(S), _p(g_fm), _p(g_lin), _p(W1), B, m, k, N1, plan.unit,
+        opt if update else -1, float(lr), float(l2), _p(dW1), _p(out_rows), _p(out_scal), _p(status), _p(ws), ws_bytes,
+        _stream(),
+    )
+    if debug:
+        return dW1, out_rows, out_scal
+    return dW1
+
+
+def umma_probe(At, Bt, variant: int = 0):
+    _dev_check(At)
+    K = At.shape[0]
+    assert At.shape == (K, 128) and Bt.shape == (K, 32) and At.is_contiguous() and Bt.is_contiguous()
+    D = torch.empty(128, 32, dtype=torch.float32, device=At.device)
+    st = new_status(At.device)
+    _C.call("rm_umma_probe", _p(At), _p(Bt), K, variant, _p(D), _p(st), _stream())
+    return D, st

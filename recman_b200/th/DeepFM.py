@@ -66,6 +66,20 @@ class DeepFM(DeepModel):
         fm_dropout = hp["fm_dropout"] if training else (1.0,) * len(hp["fm_dropout"])
         fm_identity = all(p >= 1 for p in fm_dropout)
 
+        tower = None
+        if self.use_fm and self.use_deep and fm_identity and (not training or hp["deep_dropout"][0] >= 1):
+            self.dnn = DNN(self.variables, hp["deep_hidden_units"],
+                           hp["deep_dropout"] if training else (1.0,) * len(hp["deep_dropout"]),
+                           hp["deep_activation"], hp["deep_l2_reg"])
+            self.dnn.training = training
+            tower = self._tower_front_end(self.embeddings, self.linear, self.dnn, inputs, training)
+        if tower is not None:
+            # one kernel: gather + FM + first-order + first DNN layer (tcgen05); the row buffer is never written
+            y1, fm_logit, linear_logit = tower
+            final_logit = linear_logit + fm_logit + self.dnn.from_first_layer(y1)
+            self.final_logit = final_logit.detach()
+            return PredictionLayer(self.variables, self.task, use_bias=False)(final_logit)
+
         fused = self._fused_front_end(self.embeddings, inputs, self.linear, want_fm=self.use_fm and fm_identity)
         if fused is not None:
             rows, fm_logit, linear_logit = fused

@@ -203,6 +203,63 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
             rows.fm_back = fm_back  # the model hooks fm_back.on_g_fm onto its final logit (see DeepFM._out)
         return rows, (fm if want_fm else None), (lin if linear is not None else None)
 
+    # ------------------------------------------------------------------ fused DeepFM tower (front end + first DNN layer)
+    def _tower_front_end(self, layer: FeatEmbeddingLayer, linear: LinearLayer, dnn, inputs: DataInputs, training: bool):
+        """One kernel for gather + FM + first-order term + the first DNN layer (``rm_tower_fwd``), and - inside a
+        training step whose update can be fused - one sorted pass for the whole sparse backward + optimizer
+        (``rm_tower_bwd_update``).  Returns (y1 pre-activation, fm_logit, lin_logit) or None when not eligible:
+        every embedding feature one-hot, k in {32, 64}, first hidden layer <= 64 wide, linear features ==
+        [sparse..., dense...], single GPU.  The two k=1 tables (``feat_bias_table``, ``linear_w``) then share ONE
+        interleaved [rows + n_dense, 2] storage, so an id costs one 8-byte lookup instead of two sector fetches."""
+        if not self.hparams.get("tower", True) or self.shard is not None or inputs.sparse_ids is None:
+            return None
+        k = layer.embedding_size
+        if not layer.all_one_hot or not layer.use_bias:
+            return None
+        lay = layer.layout()
+        dense = inputs.dense
+        n_dense = 0 if dense is None else dense.shape[1]
+        hidden0 = dnn.hidden_units[0]
+        if hidden0 is None or not ops.tower_supported(lay.m, k, n_dense, int(hidden0)):
+            return None
+        want = self.feat_dict.sparse_feats + self.feat_dict.dense_feats
+        if [f.name for f in linear.linear_feats] != [f.name for f in want]:
+            return None
+        total = layer.total_rows
+        bname, wname = layer.bias_name, f"{linear.prefix}linear_w"
+        cache = self.__dict__.setdefault("_cache", {})
+        if "scal_storage" not in cache:
+            if bname in self.variables or wname in self.variables:
+                return None  # the k=1 tables already exist in the separate layout
+            st = torch.zeros(total + n_dense, 2, dtype=torch.float32, device=self.device)
+            self.variables[bname] = torch.nn.Parameter(st[:total, 0], requires_grad=True)
+            self.variables[wname] = torch.nn.Parameter(st[:, 1:2], requires_grad=True)
+            cache["scal_storage"] = st
+        scal = cache["scal_storage"]
+        layer._upsert_variables()
+        linear._upsert_variables()
+        table = self.variables[layer.table_name]
+        bias_param, W_lin = self.variables[bname], self.variables[wname]
+        if bias_param.data_ptr() != scal.data_ptr() or W_lin.data_ptr() != scal.data_ptr() + 4:
+            return None  # a parameter was re-bound: the interleaved storage is no longer what the model trains
+        d = lay.m * k + n_dense
+        W1, b1 = dnn.first_layer(d)
+        scal_fwd = scal
+        if not training:  # inference-time per-id weights (layers.py:338-345, 426-437) are added to linear_w
+            extra = np.concatenate([np.asarray(f.weights, dtype=np.float32).reshape(-1) for f in linear.linear_feats])
+            if np.any(extra != 0):
+                scal_fwd = scal.clone()
+                scal_fwd[:, 1] += torch.from_numpy(extra).to(scal.device)
+        fused = getattr(self, "_fused_opt", None)
+        if fused is not None and (layer.l2_reg or linear.l2_reg or getattr(table, "rm_l2_touched", 0.0)):
+            fused = None
+        from ..autograd import TowerFunction
+
+        y1, fm, lin = TowerFunction.apply(table, scal, scal_fwd, bias_param, W_lin, W1, b1, lay.runs[0].offsets, total,
+                                          self._status(), inputs.sparse_ids, dense, fused)
+        lin = lin + self.variables[f"{linear.prefix}linear_w0"]
+        return y1, fm, lin
+
     # ------------------------------------------------------------------ reference API
     def predict(self, X, training=False, batch_number_to_show_progress=50):
         n = len(X) if not isinstance(X, dict) else len(next(iter(X.values())))
@@ -385,6 +442,13 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
                     dense.append(tail[1])
             allreduce_dense(dense, self.shard.group)
         dense_pairs = []  # (parameter, gradient) of every dense update: one multi-tensor launch at the end
+
+        def add_dense(pv, g):
+            if pv.is_contiguous():
+                dense_pairs.append((pv, g.contiguous()))
+            else:  # a strided view of the interleaved k=1 storage (tower layout): packed copy, update, write back
+                ops.dense_opt_step(pv, g.reshape(pv.shape), kind, lr, 0.0)
+
         for name, p in self.variables.items():
             sparse = pop_sparse_grads(p)
             tail = getattr(p, "rm_dense_tail", None)
@@ -395,7 +459,7 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
                     ops.sparse_opt_step(p.data, sg, kind, lr, l2)
                 if tail is not None:
                     first, g = tail
-                    dense_pairs.append((p.data.reshape(-1)[first:], g.contiguous()))
+                    add_dense(p.data.reshape(-1)[first:], g)
             elif sparse:
                 # a dense part exists (the reference's whole-table L2, layers.py:188-193): densify and update all rows
                 p.rm_sparse_grads = sparse
@@ -405,10 +469,10 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
                     g.reshape(-1)[first:] += gt
                 ops.dense_opt_step(p.data, g.contiguous(), kind, lr, 0.0)
             elif p.grad is not None:
-                dense_pairs.append((p.data, p.grad.contiguous()))
+                add_dense(p.data, p.grad)
             elif tail is not None:  # id rows already updated by the fused backward kernel: only the dense tail is left
                 first, g = tail
-                dense_pairs.append((p.data.reshape(-1)[first:], g.contiguous()))
+                add_dense(p.data.reshape(-1)[first:], g)
             p.grad = None
         ops.dense_opt_step_multi(dense_pairs, kind, lr, 0.0)
 

@@ -518,6 +518,27 @@ class DNN:
         if f"{p}dnn_w0" not in v:
             v[f"{p}dnn_w0"] = _param(torch.zeros(1, dtype=torch.float32, device=DEVICE))
 
+    def first_layer(self, d_in):
+        """(W, b) of the first layer, created on demand: the fused DeepFM tower computes ``x @ W + b`` itself."""
+        if any(u is None for u in self.hidden_units):
+            self.hidden_units = compute_hidden_units_s2(len(self.hidden_units), d_in)
+        self._create_weights(d_in)
+        return self.variables[f"{self.prefix}dnn_layer_0_weights"], self.variables[f"{self.prefix}dnn_layer_0_bias"]
+
+    def from_first_layer(self, y1):
+        """The rest of the network given the first layer's pre-activation ``y1`` [B, hidden_units[0]]."""
+        v, p = self.variables, self.prefix
+        y = _dropout(self.activation(y1), self.dropout[1], self.training)
+        for i in range(1, len(self.hidden_units)):
+            W, b = v[f"{p}dnn_layer_{i}_weights"], v[f"{p}dnn_layer_{i}_bias"]
+            if ops.narrow_linear_ok(W.shape[1]) and y.shape[1] % 4 == 0:
+                y = NarrowLinearFunction.apply(y.contiguous(), W, b)
+            else:
+                y = torch.addmm(b, y, W)
+            y = self.activation(y)
+            y = _dropout(y, self.dropout[i + 1], self.training)
+        return torch.addmm(v[f"{p}dnn_w0"], y, v[f"{p}dnn_w"])
+
     def __call__(self, inputs):
         d_in = inputs.shape[1]
         if any(u is None for u in self.hidden_units):

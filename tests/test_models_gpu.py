@@ -270,3 +270,123 @@ def test_fit_encode_once_prefetch_path_equals_per_batch_path():
     assert fast.samples_seen == slow.samples_seen == 2000
     for name, p in fast.variables.items():
         assert torch.equal(p.data, slow.variables[name].data), name
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# fused DeepFM tower (rm_tower_fwd / rm_tower_bwd_update): k = 64, first hidden layer 32
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("opt", ["adam", "adagrad", "gd"])
+@pytest.mark.parametrize("B", [128, 777])
+def test_tower_fit_on_batch_matches_oracle_update(opt, B):
+    """One full step through the fused tower (forward kernel, sorted backward + in-kernel update) against the oracle's
+    gradients + fresh-optimizer rule, every variable."""
+    from recman_b200.th import DeepFM
+    from recman_b200.th.input import DataInputs
+
+    fd = pu.make_feat_dict([40, 9, 300, 5000, 3], n_dense=13)
+    X, y = pu.synth_batch(fd, B, seed=17)
+    lr = 0.05 if opt == "gd" else 0.01
+    model = DeepFM(fd, embedding_size=64, deep_hidden_units=(32, 32), deep_dropout=(1, 1, 1), batch_size=B, optimizer=opt,
+                   learning_rate=lr, embedding_l2_reg=0.0, linear_l2_reg=0.0)
+    with torch.no_grad():
+        model._out(DataInputs("cuda").load(fd, X, y))
+    assert "scal_storage" in model._cache, "the tower path did not engage"
+    pu.randomize_variables(model)
+    st, _, o_loss = pu.oracle_loss(model, X, y, torch.float64)
+    o_loss.backward()
+    before = {k: v.detach().clone() for k, v in st.items()}
+    from recman_b200 import ops
+
+    n0 = ops.launch_count()
+    model.fit_on_batch(X, y)
+    torch.cuda.synchronize()
+    model.check_ids()
+    assert ops.launch_count() > n0
+    for name, p in model.variables.items():
+        g = st[name].grad if st[name].grad is not None else torch.zeros_like(st[name])
+        exp = oracle.fresh_optimizer_step(before[name], g, opt, lr)
+        got = p.detach().cpu().double()
+        if opt == "adam":
+            solid = g.abs() > 1e-4 * g.abs().max()
+            assert torch.all((got - before[name]).abs() <= lr * 1.0001 + 1e-12), name
+            torch.testing.assert_close(got[solid], exp[solid], rtol=1e-5, atol=lr * 2e-3, msg=lambda m: f"{name}: {m}")
+        else:
+            torch.testing.assert_close(got, exp, rtol=1e-5, atol=1e-7, msg=lambda m: f"{name}: {m}")
+
+
+def test_tower_matches_separate_kernels_and_graph_replay():
+    """Three DeepFM models with the same weights: fused tower (eager), fused tower (CUDA graph) and the separate
+    kernels (hparams tower=False).  Same parameters after several steps (1e-5: the tensor-core GEMMs are 3xTF32)."""
+    from recman_b200.th import DeepFM
+    from recman_b200.th.input import DataInputs
+
+    fd = pu.make_feat_dict(CRITEO_SMALL, n_dense=13)
+    batches = [pu.synth_batch(fd, 512, seed=60 + i) for i in range(4)]
+    kw = dict(embedding_size=64, deep_hidden_units=(32, 32), deep_dropout=(1, 1, 1), batch_size=512, learning_rate=0.01,
+              embedding_l2_reg=0.0, linear_l2_reg=0.0, optimizer="adagrad")
+    first = DataInputs("cuda").load(fd, *batches[0])
+    models = []
+    for tower in (True, True, False):
+        mdl = DeepFM(fd, **kw)
+        mdl.hparams["tower"] = tower
+        with torch.no_grad():
+            mdl._out(first)
+        models.append(mdl)
+    eager, graph, plain = models
+    assert "scal_storage" in eager._cache and "scal_storage" not in plain._cache
+    pu.randomize_variables(eager, seed=5)
+    for other in (graph, plain):
+        for name, p in eager.variables.items():
+            other.variables[name].data.copy_(p.data)
+    eager.fit_on_batch(first, None)
+    plain.fit_on_batch(first, None)
+    graph.compile_step(first, warmup=1)
+    for X, y in batches[1:]:
+        le = eager.fit_on_batch(X, y)
+        lg = graph.fit_on_batch(X, y)
+        lp = plain.fit_on_batch(X, y)
+        torch.testing.assert_close(lg, le, rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(lp, le, rtol=1e-5, atol=1e-6)
+    for name in eager.variables:
+        a = eager.variables[name].data
+        torch.testing.assert_close(graph.variables[name].data, a, rtol=1e-6, atol=1e-7, msg=lambda m_: f"{name}: {m_}")
+        scale = float(a.abs().max())
+        torch.testing.assert_close(plain.variables[name].data, a, rtol=1e-5, atol=2e-6 * max(scale, 1e-3),
+                                   msg=lambda m_: f"{name}: {m_}")
+    eager.check_ids()
+    graph.check_ids()
+
+
+def test_tower_inference_weight_override():
+    """Inference-time per-id weights (layers.py:426-437, examples/xDeepFM_test.py:124): added to linear_w when
+    training=False - through the fused tower forward and through the separate kernels, against the oracle."""
+    from recman_b200.th import DeepFM
+    from recman_b200.th.input import DataInputs
+
+    fd = pu.make_feat_dict([40, 9, 300], n_dense=2)
+    X, y = pu.synth_batch(fd, 200, seed=3)
+    outs = {}
+    for tower in (True, False):
+        model = DeepFM(fd, embedding_size=64, deep_hidden_units=(32, 32), deep_dropout=(1, 1, 1), batch_size=200)
+        model.hparams["tower"] = tower
+        inputs = DataInputs("cuda").load(fd, X, y)
+        with torch.no_grad():
+            model._out(inputs)
+        pu.randomize_variables(model, seed=9)
+        with torch.no_grad():
+            base = model._out(inputs, training=False).cpu()
+        fd["C1"].set_weights({3: -5.0})  # the reference's set_weights({"Outdoor": -5}) with ids for keys
+        try:
+            with torch.no_grad():
+                pred = model._out(inputs, training=False).cpu()
+                pred_train = model._out(inputs, training=True).cpu()  # the override is inference-only
+        finally:
+            fd["C1"].set_weights(None)
+        hit = torch.from_numpy(np.asarray(X["C1"]) == 3)
+        assert hit.any()
+        logit = lambda p: torch.log(p.double() / (1 - p.double()))
+        torch.testing.assert_close(logit(pred)[hit], logit(base)[hit] - 5.0, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(pred[~hit], base[~hit], rtol=0, atol=0)
+        torch.testing.assert_close(pred_train, base, rtol=1e-6, atol=1e-7)
+        outs[tower] = pred
+    torch.testing.assert_close(outs[True], outs[False], rtol=1e-5, atol=1e-6)

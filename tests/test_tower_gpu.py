@@ -1,0 +1,273 @@
+"""Parity of the fused DeepFM tower kernels (rm_tower_*, through the C ABI) against the CPU oracle.
+
+Forward: gathered rows bit-exact, FM / first-order / first-layer outputs within 1e-5 of the fp64 oracle.
+Backward: per-row summed gradients, k=1 gradients, dW1 and the updated tables within 1e-5; run-to-run bit-identical.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def _ops():
+    from recman_b200 import ops
+
+    return ops
+
+
+def assert_close(got, exp, rtol=RTOL, atol_scale=1e-6, msg=""):
+    got = got.detach().cpu().double()
+    exp = exp.detach().cpu().double()
+    atol = atol_scale * max(1e-30, float(exp.abs().max())) if exp.numel() else 0.0
+    torch.testing.assert_close(got, exp, rtol=rtol, atol=atol, msg=lambda m: f"{msg}: {m}")
+
+
+def _setup(sizes, k, B, nd, N1, seed=0, dup=False):
+    g = torch.Generator().manual_seed(seed)
+    m = len(sizes)
+    tabs = [torch.randn(v, k, generator=g) * 0.1 for v in sizes]
+    offs = torch.tensor([0] + list(np.cumsum(sizes)), dtype=torch.int64)
+    total = int(offs[-1])
+    scal = torch.randn(total, 2, generator=g) * 0.1
+    cols = []
+    for v in sizes:
+        hi = min(v, 3) if dup else v
+        cols.append(torch.randint(0, hi, (B,), generator=g))
+    ids = torch.stack(cols, 1).contiguous()
+    if B > 1:
+        ids[0] = 0
+        ids[-1] = torch.tensor([v - 1 for v in sizes])
+    dense = torch.randn(B, nd, generator=g) if nd else None
+    d = m * k + nd
+    W1 = torch.randn(d, N1, generator=g) * 0.05
+    b1 = torch.randn(N1, generator=g) * 0.05
+    lin_dense = torch.randn(nd, generator=g) * 0.1 if nd else None
+    return dict(tabs=tabs, table=torch.cat(tabs, 0), offs=offs, scal=scal, ids=ids, dense=dense, W1=W1, b1=b1,
+                lin_dense=lin_dense, m=m, k=k, B=B, nd=nd, N1=N1, total=total)
+
+
+def _forward_oracle(s, dtype=torch.float64):
+    """DeepFM front end + first DNN matmul through the oracle's layers (layers.py:238-261, 457-478, 589-592)."""
+    m = s["m"]
+    ids = s["ids"]
+    tabs = [t.to(dtype) for t in s["tabs"]]
+    offs = s["offs"]
+    biases = [s["scal"][int(offs[f]):int(offs[f + 1]), 0:1].to(dtype) for f in range(m)]
+    embeds, bias = oracle.feat_embedding_layer(tabs, [ids[:, f] for f in range(m)], biases)  # [B,m,k], [B,m,1]
+    fm = oracle.fm_layer(embeds, bias).reshape(-1)
+    rows = oracle.global_rows(ids.numpy(), offs.numpy())
+    lin = s["scal"][:, 1].to(dtype)[torch.from_numpy(rows)].sum(1)
+    x = embeds.reshape(embeds.shape[0], -1)
+    if s["nd"]:
+        dn = s["dense"].to(dtype)
+        lin = lin + dn @ s["lin_dense"].to(dtype)
+        x = torch.cat([x, dn], 1)
+    y1 = x @ s["W1"].to(dtype) + s["b1"].to(dtype)
+    return embeds, fm, lin, y1, embeds.sum(1)
+
+
+def test_umma_mn_major_layout():
+    """The MN-major SWIZZLE_128B operand layout the weight-gradient GEMM relies on: exact small-integer product."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    K = 64
+    At = torch.randint(-4, 5, (K, 128), generator=g).float()
+    Bt = torch.randint(-4, 5, (K, 32), generator=g).float()
+    D, st = ops.umma_probe(At.cuda(), Bt.cuda(), 0)
+    torch.cuda.synchronize()
+    assert int(st.item()) == 0
+    assert torch.equal(D.cpu(), At.t() @ Bt)
+
+
+@pytest.mark.parametrize("shape", [
+    # sizes, k, B, nd, N1
+    ([50, 7, 1000, 3, 200], 64, 300, 3, 32),
+    ([944, 1683, 3, 22, 796, 11, 64], 64, 401, 13, 32),
+    ([50, 7, 1000], 32, 200, 0, 16),
+    ([5, 9], 64, 128, 13, 64),
+    ([30] * 26, 64, 515, 13, 32),
+    ([17, 5, 300, 41], 32, 77, 5, 24),
+])
+def test_tower_forward(shape):
+    ops = _ops()
+    sizes, k, B, nd, N1 = shape
+    s = _setup(sizes, k, B, nd, N1)
+    assert ops.tower_supported(len(sizes), k, nd, N1)
+    st = ops.new_status("cuda")
+    dev = lambda t: None if t is None else t.cuda()
+    y1, fm, lin, S, x = ops.tower_fwd(dev(s["table"]), dev(s["scal"]), dev(s["offs"]), dev(s["ids"]), dev(s["dense"]),
+                                      dev(s["lin_dense"]), dev(s["W1"]), dev(s["b1"]), want_x=True, status=st)
+    torch.cuda.synchronize()
+    assert int(st.item()) == 0
+    embeds, o_fm, o_lin, o_y1, o_S = _forward_oracle(s)
+    m = len(sizes)
+    assert torch.equal(x[:, : m * k].cpu(), embeds.float().reshape(B, -1))  # gathered rows: bit-exact
+    if nd:
+        assert torch.equal(x[:, m * k : m * k + nd].cpu(), s["dense"])
+    assert_close(S, o_S, msg="S")
+    assert_close(fm, o_fm, msg="fm")
+    assert_close(lin, o_lin, msg="lin")
+    assert_close(y1, o_y1, msg="y1")
+    # without the row buffer: same results
+    y1b, fmb, linb, Sb, xb = ops.tower_fwd(dev(s["table"]), dev(s["scal"]), dev(s["offs"]), dev(s["ids"]),
+                                           dev(s["dense"]), dev(s["lin_dense"]), dev(s["W1"]), dev(s["b1"]))
+    assert xb is None and torch.equal(y1b, y1) and torch.equal(fmb, fm) and torch.equal(linb, lin) and torch.equal(Sb, S)
+
+
+def test_tower_forward_bad_id_zero_fills_and_flags():
+    ops = _ops()
+    sizes, k, B, nd, N1 = [50, 7, 1000], 64, 130, 2, 32
+    s = _setup(sizes, k, B, nd, N1)
+    s["ids"][5, 1] = 7  # == feat_size: outside
+    s["ids"][77, 2] = -3
+    st = ops.new_status("cuda")
+    dev = lambda t: None if t is None else t.cuda()
+    y1, fm, lin, S, x = ops.tower_fwd(dev(s["table"]), dev(s["scal"]), dev(s["offs"]), dev(s["ids"]), dev(s["dense"]),
+                                      dev(s["lin_dense"]), dev(s["W1"]), dev(s["b1"]), want_x=True, status=st)
+    torch.cuda.synchronize()
+    assert int(st.item()) & 1
+    assert torch.count_nonzero(x[5, k : 2 * k]) == 0 and torch.count_nonzero(x[77, 2 * k : 3 * k]) == 0
+    assert torch.isfinite(y1).all()
+
+
+def _backward_reference(s, g1, g_fm, g_lin):
+    """fp64: per unique row the summed gradient of (MLP layer-1 input gradient + FM backward), k=1 gradients, dW1."""
+    m, k, B = s["m"], s["k"], s["B"]
+    rows = oracle.global_rows(s["ids"].numpy(), s["offs"].numpy())  # [B, m]
+    T = s["table"].double()
+    x = T[torch.from_numpy(rows)]  # [B, m, k]
+    S = x.sum(1)
+    W1 = s["W1"].double()
+    dx = (g1.double() @ W1[: m * k].t()).reshape(B, m, k)
+    G = dx + g_fm.double()[:, None, None] * (S[:, None, :] - x)  # dL/d e[b,f,:]  (layers.py:457-478 backward)
+    dense_rows = torch.zeros(s["total"], k, dtype=torch.float64)
+    dense_rows.index_add_(0, torch.from_numpy(rows.reshape(-1)), G.reshape(-1, k))
+    dsc = torch.zeros(s["total"], 2, dtype=torch.float64)
+    gsc = torch.stack([g_fm.double(), g_lin.double()], 1)[:, None, :].expand(B, m, 2).reshape(-1, 2)
+    dsc.index_add_(0, torch.from_numpy(rows.reshape(-1)), gsc)
+    dW1 = x.reshape(B, m * k).t() @ g1.double()
+    return rows, dense_rows, dsc, dW1, S.float()
+
+
+@pytest.mark.parametrize("case", [
+    # sizes, B, dup, unit
+    ([50, 7, 1000, 3, 200], 300, False, 2048),
+    ([944, 1683, 3, 22, 796, 11, 64], 1111, False, 256),
+    ([40, 40, 40], 700, True, 128),       # 3 distinct ids per field: segments of ~230 positions across tiles and units
+    ([100000] * 4, 4096, False, 2048),    # almost all singletons
+    ([30] * 26, 515, False, 512),
+])
+@pytest.mark.parametrize("opt", ["gd", "adam"])
+def test_tower_backward(case, opt):
+    from recman_b200 import _C
+
+    ops = _ops()
+    sizes, B, dup, unit = case
+    k, nd, N1 = 64, 3, 32
+    s = _setup(sizes, k, B, nd, N1, seed=5, dup=dup)
+    m = s["m"]
+    g = torch.Generator().manual_seed(11)
+    g1 = torch.randn(B, N1, generator=g) * 1e-2
+    g_fm = torch.randn(B, generator=g) * 1e-2
+    g_lin = torch.randn(B, generator=g) * 1e-2
+    rows, o_rows, o_sc, o_dW1, S = _backward_reference(s, g1, g_fm, g_lin)
+    table, scal = s["table"].cuda(), s["scal"].cuda()
+    st = ops.new_status("cuda")
+    plan = ops.tower_plan(s["ids"].cuda(), s["offs"].cuda(), s["total"], unit=unit, status=st)
+    torch.cuda.synchronize()
+    keys = plan.sorted_keys.cpu().numpy().view(np.uint32).astype(np.int64)
+    pos = plan.sorted_pos.cpu().numpy()
+    # sorted by (row, position): bit-exact against a stable argsort
+    order = np.argsort(rows.reshape(-1), kind="stable")
+    assert np.array_equal(pos, order.astype(np.int32)) and np.array_equal(keys, rows.reshape(-1)[order])
+    fb = plan.field_bounds.cpu().numpy()
+    assert np.array_equal(fb, np.arange(m + 1) * B)
+    ub = plan.unit_bounds.cpu().numpy()
+    for p in ub:  # every cut sits on a segment head
+        assert p in fb or keys[p] != keys[p - 1]
+
+    lr = 0.5 if opt == "gd" else 1e-3
+    kind = _C.OPT_KINDS[opt]
+    args = (plan, g1.cuda(), S.cuda(), g_fm.cuda(), g_lin.cuda(), s["W1"].cuda(), kind, lr)
+    # 1) gradients only
+    t0, s0 = table.clone(), scal.clone()
+    dW1, out_rows, out_scal = ops.tower_bwd_update(t0, s0, *args, update=False, debug=True, status=st)
+    torch.cuda.synchronize()
+    assert int(st.item()) == 0
+    assert torch.equal(t0, table) and torch.equal(s0, scal)
+    closing = np.flatnonzero(np.append(keys[1:] != keys[:-1], True))  # sorted position closing each segment
+    uniq = keys[closing]
+    assert_close(out_rows.cpu()[closing], o_rows[uniq], atol_scale=1e-5, msg="summed gradient rows")
+    assert_close(out_scal.cpu()[closing], o_sc[uniq], atol_scale=1e-5, msg="k=1 gradients")
+    mask = np.ones(B * m, dtype=bool)
+    mask[closing] = False
+    assert torch.count_nonzero(out_rows.cpu()[mask]) == 0
+    assert_close(dW1, o_dW1, atol_scale=1e-5, msg="dW1")
+    # 2) fused update, twice: deterministic and equal to the oracle's fresh-optimizer step on the touched rows
+    outs = []
+    for _ in range(2):
+        t1, s1 = table.clone(), scal.clone()
+        dW1b = ops.tower_bwd_update(t1, s1, *args, status=st)
+        torch.cuda.synchronize()
+        outs.append((t1, s1, dW1b))
+    assert int(st.item()) == 0
+    assert all(torch.equal(a, b) for a, b in zip(outs[0], outs[1]))
+    assert torch.equal(outs[0][2], dW1)
+    t1, s1, _ = outs[0]
+    exp_t = s["table"].double().clone()
+    exp_s = s["scal"].double().clone()
+    ut = torch.from_numpy(uniq)
+    exp_t[ut] = oracle.fresh_optimizer_step(exp_t[ut], o_rows[ut], opt, lr)
+    exp_s[ut] = oracle.fresh_optimizer_step(exp_s[ut], o_sc[ut], opt, lr)
+    assert_close(t1, exp_t, atol_scale=2e-6, msg="updated table")
+    assert_close(s1, exp_s, atol_scale=2e-6, msg="updated k=1 tables")
+    untouched = np.ones(s["total"], dtype=bool)
+    untouched[uniq] = False
+    assert torch.equal(t1.cpu()[untouched], s["table"][untouched])
+
+
+def test_tower_backward_drops_out_of_range_ids():
+    """ids outside their table sort behind every row and never reach the update (no foreign-row writes)."""
+    ops = _ops()
+    sizes, B = [50, 7, 1000], 260
+    k, nd, N1 = 64, 0, 32
+    s = _setup(sizes, k, B, nd, N1, seed=2)
+    s["ids"][3, 1] = 9
+    s["ids"][100, 0] = -1
+    st = ops.new_status("cuda")
+    plan = ops.tower_plan(s["ids"].cuda(), s["offs"].cuda(), s["total"], unit=256, status=st)
+    torch.cuda.synchronize()
+    assert int(st.item()) & 1
+    fb = plan.field_bounds.cpu().numpy()
+    assert fb[-1] == B * 3 - 2 and fb[1] == B - 1 and fb[2] == 2 * B - 2
+    keys = plan.sorted_keys.cpu().numpy().view(np.uint32)
+    assert (keys[-2:] == s["total"]).all()
+    g = torch.Generator().manual_seed(1)
+    g1 = torch.randn(B, N1, generator=g) * 1e-2
+    g_fm = torch.randn(B, generator=g) * 1e-2
+    S = torch.randn(B, k, generator=g)
+    t1, s1 = s["table"].cuda(), s["scal"].cuda()
+    st2 = ops.new_status("cuda")
+    ops.tower_bwd_update(t1, s1, plan, g1.cuda(), S.cuda(), g_fm.cuda(), None, s["W1"].cuda(), 2, 0.1, status=st2)
+    torch.cuda.synchronize()
+    assert int(st2.item()) == 0
+    valid = s["ids"].clone()
+    valid[3, 1] = 0
+    valid[100, 0] = 0
+    rows = oracle.global_rows(valid.numpy(), s["offs"].numpy())
+    touched = np.zeros(s["total"], dtype=bool)
+    touched[rows.reshape(-1)] = True
+    # rows 0 of fields 0 / 1 may or may not be touched by other samples; every untouched row must be unchanged
+    rows_real = rows.copy().reshape(-1)
+    keep = np.ones(B * 3, dtype=bool)
+    keep[3 * 3 + 1] = False
+    keep[100 * 3 + 0] = False
+    touched2 = np.zeros(s["total"], dtype=bool)
+    touched2[rows_real[keep]] = True
+    assert torch.equal(t1.cpu()[~touched2], s["table"][~touched2])
+    assert torch.isfinite(t1).all()
