@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--no-library-baseline", action="store_true", help="skip the torch-eager-CUDA comparison")
     ap.add_argument("--no-graph", action="store_true", help="do not CUDA-graph the step")
     ap.add_argument("--cin-precision", default="3xtf32")
+    ap.add_argument("--blocks", type=int, default=5, help="timed blocks of --steps steps each; the median block is reported")
+    ap.add_argument("--no-other-workloads", action="store_true", help="c5 only: skip the c2 / c3 lines")
     ap.add_argument("--cpu-batch", type=int, default=8192)
     ap.add_argument("--cpu-rows", type=int, default=100_000)
     return ap.parse_args()
@@ -194,6 +196,15 @@ def algorithmic_bytes(kind, B, m, k, n_dense, n_unique=None):
     if kind == "rm_pack_grad_rows":
         # per (b,f): dx row + x row read, G row (k+4) written; S row + 2 scalars per sample
         return B * m * (8 * k + 4 * (k + 4)) + B * (4 * k + 8)
+    if kind == "rm_tower_fwd":
+        # per (b,f): id 8 + row read 4k + interleaved (bias, weight) 8; per sample: dense read, S + y1 + 2 logits written
+        # (N1 = 32 at the bench shape; the row buffer is not written)
+        return B * (m * (8 + 4 * k + 8) + 4 * n_dense + 4 * k + 4 * 32 + 8)
+    if kind == "rm_tower_bwd_update":
+        # per position: sorted key + position 8, table row read 4k; per sample (read once): g1 row 4*32, S row 4k,
+        # g_fm + g_lin 8; per unique row: table row written 4k, (bias, weight) read + written 16
+        nu = n_unique if n_unique is not None else B * m
+        return B * m * (8 + 4 * k) + B * (4 * 32 + 4 * k + 8) + nu * (4 * k + 16)
     # rm_sparse_opt_step is launched once per table kind (k = 64, 1, 1): its averaged time is not a single-kernel
     # figure, so it is listed without bytes
     return None
@@ -212,28 +223,23 @@ def cin_flops_per_step(w, B, k):
     return total
 
 
-def run_ours(args):
+def measure(args, wname, world, rank, local_rank, dev, primary=True):
+    """Build the workload's model, time it (device-resident and end-to-end) and return the JSON-able record.
+    `primary` adds the CPU / library baselines; secondary workloads (other_workloads) are timed more briefly."""
     import torch.distributed as dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    w = WORKLOADS[args.workload]
+    w = WORKLOADS[wname]
     from recman_b200 import ops
-    from recman_b200.th.input import DataInputs
+    from recman_b200.th.input import DataInputs, HostPrefetcher
 
+    model, fd, rows, k, B = build_model(w, args, world, rank)
     if world > 1:
         from recman_b200.th import dist as rdist
 
-        model, fd, rows, k, B = build_model(w, args, world, rank)
         rdist.shard_model(model, world, rank)
-    else:
-        model, fd, rows, k, B = build_model(w, args, world, rank)
     m, n_dense = w["m"], w["n_dense"]
+    steps = args.steps if primary else max(10, min(args.steps, 20))
+    blocks = max(1, args.blocks if primary else min(args.blocks, 3))
 
     # rotating pool of distinct batches (ids differ per step so nothing is served from L2 by repetition)
     NB = 8
@@ -244,8 +250,6 @@ def run_ours(args):
 
     def step_resident(i):
         return model.fit_on_batch(resident[i % NB], None)
-
-    from recman_b200.th.input import HostPrefetcher
 
     # e2e input pipeline: every step's batch is copied from pinned host memory (double-buffered: the copy of step i+1
     # rides under step i on a copy stream); the loss is read back to the host every step
@@ -277,9 +281,9 @@ def run_ours(args):
     #      are launched); the timed region below replays the CUDA graph of the step ----
     ops.enable_profile()
     launches0 = ops.launch_count()
-    for i in range(min(args.steps, 10)):
+    prof_steps = min(steps, 10)
+    for i in range(prof_steps):
         step_resident(i)
-    prof_steps = min(args.steps, 10)
     launches_per_step = (ops.launch_count() - launches0) // prof_steps
     prof = ops.disable_profile()
     graphed = False
@@ -295,12 +299,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, nsteps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
-        for i in range(steps):
+        for i in range(nsteps):
             fn(i)
         e1.record()
         torch.cuda.synchronize()
@@ -317,22 +321,33 @@ def run_ours(args):
     ncu_range = os.environ.get("RM_NCU_RANGE") == "1"  # ncu --profile-from-start off: profile the timed region only
     if ncu_range:
         torch.cuda.profiler.start()
-    ms_total, wall_total = timed(step_resident, args.steps)
+    # `blocks` timed blocks of exactly `steps` steps each (barrier + synchronize on both sides, max over ranks);
+    # the reported step time is the median block
+    block_ms, block_wall = [], []
+    for _ in range(blocks):
+        ms_b, wall_b = timed(step_resident, steps)
+        block_ms.append(ms_b)
+        block_wall.append(wall_b)
     if ncu_range:
         torch.cuda.profiler.stop()
-    launches = launches_per_step * args.steps
-    clocks = sampler.stop() if rank == 0 else None
-    ms_step = ms_total / args.steps
+    launches = launches_per_step * steps
+    ms_total = statistics.median(block_ms)
+    wall_total = statistics.median(block_wall)
+    ms_step = ms_total / steps
     value = B * world / (ms_step * 1e-3)
 
     # ---- e2e: pinned host buffers -> H2D -> step -> D2H loss ----
     for i in range(2):
         step_e2e(i)
-    prefetch._pending = None  # the timed region starts cold: its first batch is copied inside it
-    loss_ev[0] = loss_ev[1] = None
-    e2e_ms, e2e_wall = timed(step_e2e, args.steps)
+    e2e_blocks = []
+    for _ in range(blocks):
+        prefetch._pending = None  # every block starts cold: its first batch is copied inside it
+        loss_ev[0] = loss_ev[1] = None
+        e2e_ms, e2e_wall = timed(step_e2e, steps)
+        e2e_blocks.append(max(e2e_ms, e2e_wall))  # includes the host wait for the D2H read
+    clocks = sampler.stop() if rank == 0 else None
     assert all(np.isfinite(v) for v in e2e_losses)
-    e2e_ms_step = max(e2e_ms, e2e_wall) / args.steps  # includes the host wait for the D2H read
+    e2e_ms_step = statistics.median(e2e_blocks) / steps
     e2e_value = B * world / (e2e_ms_step * 1e-3)
     h2d = sum(t.numel() * t.element_size() for t in pinned[0])
 
@@ -354,7 +369,7 @@ def run_ours(args):
                              "alg_bytes": ab, "gbs": (round(ab / (avg * 1e-3) / 1e9, 1) if ab and avg > 0 else None)}
         traffic = {}
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {})
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wname, {})
         except Exception:
             pass
         cand = [(v["ms_per_step"], n) for n, v in kernels.items() if v["alg_bytes"]]
@@ -388,7 +403,7 @@ def run_ours(args):
                         "traffic_source": (traffic.get(dom) or {}).get("source"), "avg_launch_ms": kv["avg_ms"],
                         "alg_bytes_per_launch": kv["alg_bytes"]}
         cpu = None
-        if not args.no_cpu_baseline and world == 1:
+        if primary and not args.no_cpu_baseline and world == 1:
             cpu = cpu_baseline(args, w, steps=3, warmup=1)
         lib = None
         if not args.no_library_baseline and world == 1:
@@ -398,7 +413,7 @@ def run_ours(args):
                 lib = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
         out = {
             "metric": "CTR train samples/sec", "value": round(value, 1), "unit": "samples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["desc"], "model": w["model"], "fields": m, "rows_per_table": rows, "k": k,
                        "n_dense": n_dense, "batch_per_gpu": B, "global_batch": B * world, "ids": args.ids,
@@ -407,8 +422,13 @@ def run_ours(args):
                        "parallelism": ("single GPU" if world == 1 else f"row-sharded tables x{world} "
                                        f"({'NVLink peer-memory gather/reduce' if model.shard.peer is not None else 'NCCL all-to-all'})"
                                        " + DP dense all-reduce"),
-                       "step_launch": ("CUDA graph replay" if graphed else "eager")},
+                       "step_launch": ("CUDA graph replay" if graphed else "eager"),
+                       "timing": f"median of {blocks} blocks of {steps} steps; each block bracketed by barrier + "
+                                 "synchronize, CUDA events, max over ranks",
+                       "front_end": ("fused tower: rm_tower_fwd / rm_tower_bwd_update (tcgen05)"
+                                     if "rm_tower_fwd" in kernels else "rm_gather_fm_fwd + separate backward kernels")},
             "clocks": clocks,
+            "block_ms": [round(v, 3) for v in block_ms],
             "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "ms_per_step": round(e2e_ms_step, 4),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "input_pipeline": "pinned host buffers, double-buffered H2D on a copy stream (HostPrefetcher); "
@@ -418,8 +438,46 @@ def run_ours(args):
             "kernels": kernels,
             "cpu_baseline": cpu,
             "library_baseline": lib,
-            "wall_ms_per_step": round(wall_total / args.steps, 4),
+            "wall_ms_per_step": round(wall_total / steps, 4),
         }
+    # release the workload's device memory before the next one is built
+    del model, resident, prefetch, pinned, host
+    import gc
+
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    parity = None
+    if world > 1:
+        try:
+            parity = sharded_parity_check(world, rank, dev)
+        except Exception as exc:
+            parity = f"FAILED: {type(exc).__name__}: {exc}"[:400]
+    out = measure(args, args.workload, world, rank, local_rank, dev, primary=True)
+    if rank == 0 and parity is not None:
+        out["parity_check"] = parity
+    if world == 1 and args.workload == "c5" and not args.no_other_workloads and not (args.rows or args.batch or args.k):
+        # BASELINE.json configs[1] and configs[2] in the same run, timed more briefly (their own clocks / roofline)
+        others = {}
+        for name in ("c2", "c3"):
+            try:
+                others[name] = measure(args, name, world, rank, local_rank, dev, primary=False)
+            except Exception as exc:
+                others[name] = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
+        out["other_workloads"] = others
+    if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
@@ -432,6 +490,89 @@ def run_ours(args):
     return out
 
 
+def sharded_parity_check(world, rank, dev, k=64, b=256):
+    """Before timing at N > 1: one batch through a row-sharded DeepFM (small tables, same kernels and exchange as the
+    timed model) against the single-GPU model on the concatenated global batch - logits per sample, and the
+    parameters after one optimizer step.  Product code on both sides (no oracle).  Returns "ok" or raises."""
+    import torch.distributed as dist
+
+    from recman_b200.th import DeepFM
+    from recman_b200.th import dist as rdist
+    from recman_b200.th.input import DataInputs, DenseFeat, FeatureDictionary, SparseFeat
+
+    sizes = [50, 7, 1000, 3, 200, 31, 2, 90, 1]
+    n_dense = 5
+    fd = FeatureDictionary()
+    for i, v in enumerate(sizes):
+        fd[f"C{i}"] = SparseFeat(f"C{i}", v - 1, encoder=False)
+    for j in range(n_dense):
+        fd[f"I{j}"] = DenseFeat(f"I{j}", scaler=False)
+    kw = dict(embedding_size=k, deep_hidden_units=(32, 32), deep_dropout=(1, 1, 1), batch_size=b, embedding_l2_reg=0.0,
+              linear_l2_reg=0.0, deep_l2_reg=0.0, learning_rate=0.05, optimizer="gd")
+
+    def batch(r):
+        rng = np.random.RandomState(100 + r)
+        ids = np.stack([rng.randint(0, v, size=b) for v in sizes], 1).astype(np.int64)
+        return ids, rng.randn(b, n_dense).astype(np.float32), (rng.rand(b) < 0.3).astype(np.float32)
+
+    parts = [batch(r) for r in range(world)]
+    glob = tuple(np.concatenate([p[i] for p in parts]) for i in range(3))
+    to_inputs = lambda t: DataInputs.from_tensors(fd, torch.from_numpy(t[0]).to(dev), torch.from_numpy(t[1]).to(dev),
+                                                  torch.from_numpy(t[2]).to(dev))
+    ref = DeepFM(fd, **dict(kw, batch_size=b * world))
+    ref.hparams["tower"] = False  # the sharded path runs the separate kernels: compare like with like first
+    gi = to_inputs(glob)
+    with torch.no_grad():
+        ref._out(gi)
+    g = torch.Generator().manual_seed(1)
+    for name, p in ref.variables.items():
+        p.data.copy_((torch.randn(p.shape, generator=g) * 0.05).to(dev))
+    model = DeepFM(fd, **kw)
+    rdist.shard_model(model, world, rank)
+    li = to_inputs(parts[rank])
+    with torch.no_grad():
+        model._out(li)
+    plan = model.shard
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    total = int(offs[-1])
+    rows_of = [plan.local_rows_of(f) + int(offs[f]) for f in range(len(sizes))]
+
+    for name, p in model.variables.items():
+        gten = ref.variables[name].data
+        if name in ("feat_embed_table", "feat_bias_table", "linear_w"):
+            for f, rows in enumerate(rows_of):
+                lo = plan.local_offsets[f]
+                p.data[lo : lo + rows.numel()] = gten[rows.to(dev)]
+            if name == "linear_w":
+                p.data[plan.total_local :] = gten[total:]
+        else:
+            p.data.copy_(gten)
+    with torch.no_grad():
+        lg = ref._out(gi, training=True)
+        ll = model._out(li, training=True)
+    torch.testing.assert_close(ll, lg[rank * b : (rank + 1) * b], rtol=1e-5, atol=2e-6)
+    ref.fit_on_batch(gi, None)
+    model.fit_on_batch(li, None)
+    torch.cuda.synchronize()
+    model.check_ids()
+    for name, p in model.variables.items():
+        gten = ref.variables[name].data
+        if name in ("feat_embed_table", "feat_bias_table", "linear_w"):
+            for f, rows in enumerate(rows_of):
+                lo = plan.local_offsets[f]
+                exp = gten[rows.to(dev)]
+                torch.testing.assert_close(p.data[lo : lo + rows.numel()], exp, rtol=1e-5,
+                                           atol=1e-5 * max(float(exp.abs().max()) if exp.numel() else 0.0, 1e-3),
+                                           msg=lambda m_: f"{name}[table {f}]: {m_}")
+        else:
+            torch.testing.assert_close(p.data, gten, rtol=1e-5, atol=1e-5 * max(float(gten.abs().max()), 1e-3),
+                                       msg=lambda m_: f"{name}: {m_}")
+    dist.barrier()
+    del model, ref
+    torch.cuda.empty_cache()
+    return f"ok: row-sharded DeepFM x{world} (k={k}, b={b}/rank) == single-GPU on the global batch: logits 1e-5, all parameters after one step 1e-5"
+
+
 # --------------------------------------------------------------------------------------- library bar (torch eager)
 def library_baseline(args, w, model, resident, B, m, k, rows, n_dense, steps=5, warmup=2):
     """the same step written with stock PyTorch CUDA ops (F.embedding with sparse gradients, cuBLAS,
@@ -442,10 +583,11 @@ def library_baseline(args, w, model, resident, B, m, k, rows, n_dense, steps=5, 
     dev = resident[0].sparse_ids.device
     v = model.variables
     T = v["feat_embed_table"].data.requires_grad_()
-    Bt = v["feat_bias_table"].data.view(-1, 1).requires_grad_() if "feat_bias_table" in v else None
     total = m * rows
+    # own contiguous copies of the k=1 tables (the fused tower keeps them interleaved in one [rows, 2] array)
+    Bt = v["feat_bias_table"].data.reshape(-1, 1).clone().requires_grad_() if "feat_bias_table" in v else None
     lw = v["linear_w"].data
-    Lt = lw[:total].view(-1, 1).requires_grad_()
+    Lt = lw[:total].reshape(-1, 1).clone().requires_grad_()
     offs = (torch.arange(m, device=dev, dtype=torch.int64) * rows)[None, :]
     g = torch.Generator(device=dev).manual_seed(7)
     d = m * k + n_dense
@@ -560,6 +702,10 @@ def cpu_baseline(args, w, steps=3, warmup=1):
     k = args.k or w["k"]
     rows = min(args.cpu_rows, args.rows or w["rows"])
     B = min(args.cpu_batch, args.batch or w["batch"])
+    # every host core: torchrun exports OMP_NUM_THREADS=1, which would silently make this a one-core run
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if torch.get_num_threads() != ncpu:
+        torch.set_num_threads(ncpu)
     cores = torch.get_num_threads()
     g = torch.Generator().manual_seed(2020)
     table = torch.randn(m * rows, k, generator=g) * 0.01
@@ -618,7 +764,7 @@ def cpu_baseline(args, w, steps=3, warmup=1):
                 if p.grad is not None:
                     p.copy_(oracle.fresh_optimizer_step(p, p.grad, "adam", lr))
                     p.grad = None
-        return float(loss)
+        return loss.detach().item()
 
     for i in range(warmup):
         step(i)
@@ -629,7 +775,7 @@ def cpu_baseline(args, w, steps=3, warmup=1):
     return {"value": round(B / dt, 1), "unit": "samples/s", "cores": cores, "kind": "port",
             "sample": f"{steps} steps of B={B} (same model; tables {m} x {rows} x k={k} to bound host RAM), "
                       f"torch-CPU oracle fwd+bwd + numpy segment-sum + sparse update, {dt * 1e3:.1f} ms/step",
-            "cpu_model": _cpu_model(), "ms_per_step": round(dt * 1e3, 2)}
+            "cpu_model": _cpu_model(), "ms_per_step": round(dt * 1e3, 2), "batch": B, "rows_per_table": rows}
 
 
 def _cpu_model():
@@ -649,16 +795,18 @@ def run_reference(args):
     w = WORKLOADS[args.workload]
     steps = max(1, min(args.steps, 10))
     cpu = cpu_baseline(args, w, steps=steps, warmup=max(1, min(args.warmup, 2)))
-    rows = args.rows or w["rows"]
     k = args.k or w["k"]
-    B = args.batch or w["batch"]
     out = {
         "impl": "reference", "metric": "CTR train samples/sec", "value": cpu["value"], "unit": "samples/s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": args.warmup,
         "ms_per_step": cpu["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["desc"], "model": w["model"], "fields": w["m"], "rows_per_table": rows, "k": k,
-                   "n_dense": w["n_dense"], "batch_per_gpu": B, "ids": args.ids},
+        # the configuration this arm ACTUALLY runs: a bounded sample of the workload (smaller batch and tables so that
+        # the CPU run ends within minutes and fits host RAM); "full_workload" names what it is a sample of
+        "config": {"workload": w["desc"] + " - CPU sample", "model": w["model"], "fields": w["m"],
+                   "rows_per_table": cpu["rows_per_table"], "k": k, "n_dense": w["n_dense"], "batch_per_gpu": cpu["batch"],
+                   "ids": args.ids, "host_threads": cpu["cores"],
+                   "full_workload": {"rows_per_table": args.rows or w["rows"], "batch_per_gpu": args.batch or w["batch"]}},
         "cpu_baseline": cpu,
         "e2e": {"value": cpu["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

@@ -8,7 +8,7 @@
 //   dW1  += x^T @ g1                          weight gradient of the first DNN matmul
 //
 // A tile is 128 consecutive sorted positions of ONE field.  Its table rows x (256 B each, HBM) and its g1 rows
-// (128 B, L2) are gathered with cp.async straight into SWIZZLE_128B tiles; the same tiles are the K-major A operand of
+// (128 B, L2) are gathered into swizzled shared-memory tiles (cp.async for the rows); the tiles are the K-major A operand of
 // GEMM 1 (dx tile = g1 tile @ W1_f^T, M = 128 positions) and the MN-major A / B operands of GEMM 2
 // (dW1_f += x tile^T @ g1 tile, K = 128 positions) - nothing is transposed, nothing is written back.  Both GEMMs run
 // on tcgen05 in 3xTF32 (operand = trunc + exact remainder; W1 pre-split round-to-nearest).  The epilogue owns one
@@ -39,7 +39,7 @@ constexpr int BK_PRODUCERS = 128;
 constexpr int BK_EPI = 256;
 constexpr int BK_THREADS = 128 + 32 + 256;  // 4 producer warps, 1 MMA warp, 8 epilogue warps
 constexpr int BK_DRAIN = 4;  // tiles per TMEM accumulation group of GEMM 2
-constexpr uint32_t BK_XT = 32768, BK_GT = 16384, BK_STAGE = BK_XT + BK_GT;
+constexpr uint32_t BK_XT = 32768, BK_GT = 16384, BK_STAGE = BK_XT;  // a gather stage holds the x tile only
 constexpr uint32_t BK_META = 1088;  // key[130] (prev, 128, next) + b[128], padded
 
 // ------------------------------------------------------------------------------------------------ plan
@@ -180,13 +180,14 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   auto x_hi = [&](int s) { return base + (uint32_t)s * BK_STAGE; };
-  auto g_hi = [&](int s) { return base + (uint32_t)s * BK_STAGE + BK_XT; };
   const uint32_t x_lo = base + BK_NS * BK_STAGE;
-  const uint32_t g_lo = x_lo + BK_XT;
-  const uint32_t w_img = g_lo + BK_GT;             // hi 8 KB | lo 8 KB
+  // g1 rows of the tile, four images: K-major SWIZZLE_128B (A of GEMM 1) and MN-major SWIZZLE_128B_BASE32B (B of
+  // GEMM 2), each as truncated value ("hi" = the raw word) and exact remainder ("lo")
+  const uint32_t g1_hi = x_lo + BK_XT, g1_lo = g1_hi + BK_GT, g2_hi = g1_lo + BK_GT, g2_lo = g2_hi + BK_GT;
+  const uint32_t w_img = g2_lo + BK_GT;            // hi 8 KB | lo 8 KB
   const uint32_t meta_base = w_img + 16384u;        // 4 slots
-  const uint32_t sc_base = meta_base + 4u * BK_META;  // [128] float2
-  const uint32_t carry_base = sc_base + 1024u;      // [2][64] floats
+  const uint32_t sc_base0 = meta_base + 4u * BK_META;  // [2][128] float2 (tile parity)
+  const uint32_t carry_base = sc_base0 + 2048u;      // [2][64] floats
   const uint32_t carry_sc = carry_base + 512u;      // [2] float2
   const uint32_t bar_base = carry_sc + 16u;
   auto full = [&](int s) { return bar_base + 8u * s; };
@@ -237,8 +238,10 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
     it_cons.load_unit();
     const int cx = tid & 15, rgx = tid >> 4;  // x rows rgx + 8i, chunk cx
     const int cg = tid & 7, rgg = tid >> 3;   // g rows rgg + 16i, chunk cg
-    const uint32_t xoff = (uint32_t)(cx >> 3) * 16384u + (uint32_t)rgx * 128u + ((uint32_t)((cx & 7) ^ rgx) << 4);
-    const uint32_t goff = (uint32_t)rgg * 128u + ((uint32_t)(cg ^ (rgg & 7)) << 4);
+    // x tile: MN-major operand of GEMM 2 -> SWIZZLE_128B_BASE32B (two 32-column blocks of [128 rows x 128 B])
+    const uint32_t xoff = (uint32_t)(cx >> 3) * 16384u + (uint32_t)rgx * 128u + sw32b_chunk((uint32_t)(cx & 7), (uint32_t)rgx);
+    const uint32_t g1off = (uint32_t)rgg * 128u + ((uint32_t)(cg ^ (rgg & 7)) << 4);
+    const uint32_t g2off = (uint32_t)rgg * 128u + sw32b_chunk((uint32_t)cg, (uint32_t)rgg);
     uint32_t mkey = TW_NONE, mprev = TW_NONE, mnext = TW_NONE;
     int32_t mb = 0;
     auto load_meta = [&](const TileIter& ti) {
@@ -273,13 +276,6 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
         const uint32_t key = live ? lds32(ms + 4u * (r + 1)) : 0u;
         cp_async16(x_hi(s) + xoff + (uint32_t)i * 1024u, P.table + (int64_t)key * BK_K + 4 * cx, live ? 16u : 0u);
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = rgg + 16 * i;
-        const bool live = r < cnt;
-        const int32_t b = live ? (int32_t)lds32(ms + 4u * (130 + r)) : 0;
-        cp_async16(g_hi(s) + goff + (uint32_t)i * 2048u, P.g1 + (int64_t)b * BK_N1 + 4 * cg, live ? 16u : 0u);
-      }
       ++X;
     };
     if (it_issue.valid()) load_meta(it_issue);
@@ -290,6 +286,21 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
     for (int Y = 0; it_cons.valid(); ++Y) {
       cp_async_wait<BK_DEPTH - 1>();  // all but the newest BK_DEPTH-1 groups: tile Y has landed (this thread's chunks)
       const int s = Y % BK_NS;
+      // this thread's chunks of the tile's g1 rows (L2-resident), requested before the wait below
+      float4 gv[8];
+      {
+        const int cnt = it_cons.cnt();
+        const uint32_t ms = meta_base + (uint32_t)(Y & 3) * BK_META;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = rgg + 16 * i;
+          gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < cnt) {
+            const int32_t b = (int32_t)lds32(ms + 4u * (130 + r));
+            gv[i] = __ldg(reinterpret_cast<const float4*>(P.g1 + (int64_t)b * BK_N1 + 4 * cg));
+          }
+        }
+      }
       if (Y > 0) ok = ok && mbar_wait(lo_free, ((uint32_t)(Y - 1)) & 1u);
       // exact remainders of the truncated operands
 #pragma unroll
@@ -299,8 +310,11 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float4 v = lds128(g_hi(s) + goff + (uint32_t)i * 2048u);
-        sts128(g_lo + goff + (uint32_t)i * 2048u, trunc_lo4(v));
+        const float4 lo = trunc_lo4(gv[i]);
+        sts128(g1_hi + g1off + (uint32_t)i * 2048u, gv[i]);
+        sts128(g1_lo + g1off + (uint32_t)i * 2048u, lo);
+        sts128(g2_hi + g2off + (uint32_t)i * 2048u, gv[i]);
+        sts128(g2_lo + g2off + (uint32_t)i * 2048u, lo);
       }
       fence_proxy_async_smem();
       mbar_arrive(full(s));
@@ -335,10 +349,10 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
 #pragma unroll 4
         for (int ks = 0; ks < 16; ++ks) {
           const uint32_t ko = (uint32_t)ks * 1024u;
-          const uint64_t a_hi = umma_desc_sw128(x_hi(s) + ko, 16384u, 1024u);
-          const uint64_t a_lo = umma_desc_sw128(x_lo + ko, 16384u, 1024u);
-          const uint64_t b_hi = umma_desc_sw128(g_hi(s) + ko, 16384u, 1024u);
-          const uint64_t b_lo = umma_desc_sw128(g_lo + ko, 16384u, 1024u);
+          const uint64_t a_hi = umma_desc_make(x_hi(s) + ko, 16384u, 512u, 1u);
+          const uint64_t a_lo = umma_desc_make(x_lo + ko, 16384u, 512u, 1u);
+          const uint64_t b_hi = umma_desc_make(g2_hi + ko, 16384u, 512u, 1u);
+          const uint64_t b_lo = umma_desc_make(g2_lo + ko, 16384u, 512u, 1u);
           umma_tf32(d2, a_hi, b_hi, idesc2, (tin > 0 || ks > 0) ? 1u : 0u);
           umma_tf32(d2, a_hi, b_lo, idesc2, 1u);
           umma_tf32(d2, a_lo, b_hi, idesc2, 1u);
@@ -347,7 +361,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const uint32_t ko = (uint32_t)ks * 32u;
-          const uint64_t a_hi = umma_desc(g_hi(s) + ko), a_lo = umma_desc(g_lo + ko);
+          const uint64_t a_hi = umma_desc(g1_hi + ko), a_lo = umma_desc(g1_lo + ko);
           const uint64_t b_hi = umma_desc(w_img + ko), b_lo = umma_desc(w_img + 8192u + ko);
           umma_tf32(d1, a_hi, b_hi, idesc1, ks > 0 ? 1u : 0u);
           umma_tf32(d1, a_lo, b_hi, idesc1, 1u);
@@ -371,7 +385,6 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
     const int q = warp & 3, h = e >> 2;  // TMEM lane quadrant of this warp, column half
     const int j = 32 * q + lane;
     const uint32_t rowoff = (uint32_t)h * 16384u + (uint32_t)j * 128u;
-    const uint32_t jx = (uint32_t)(j & 7);
     float dwacc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) dwacc[i] = 0.f;
@@ -389,6 +402,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
     while (it.valid()) {
       const int s = Y % BK_NS, db = Y & 1, gb = G & 1;
       const uint32_t ms = meta_base + (uint32_t)(Y & 3) * BK_META;
+      const uint32_t sc_base = sc_base0 + (uint32_t)(Y & 1) * 1024u;
       const int cnt = it.cnt();
       ok = ok && mbar_wait(full(s), ((uint32_t)(Y / BK_NS)) & 1u);
       const bool valid = j < cnt;
@@ -423,7 +437,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
       float4 xr[8], gr[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        xr[c] = lds128(x_hi(s) + rowoff + (((uint32_t)c ^ jx) << 4));
+        xr[c] = lds128(x_hi(s) + rowoff + sw32b_chunk((uint32_t)c, (uint32_t)j));
         gr[c].x = __uint_as_float(dr[4 * c + 0]) + gf * (Sv[c].x - xr[c].x);
         gr[c].y = __uint_as_float(dr[4 * c + 1]) + gf * (Sv[c].y - xr[c].y);
         gr[c].z = __uint_as_float(dr[4 * c + 2]) + gf * (Sv[c].z - xr[c].z);
@@ -432,7 +446,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
       const bool single = is_head && is_tail;
       if (valid && !single) {  // members of longer segments exchange their rows through the (now dead) x tile
 #pragma unroll
-        for (int c = 0; c < 8; ++c) sts128(x_hi(s) + rowoff + (((uint32_t)c ^ jx) << 4), gr[c]);
+        for (int c = 0; c < 8; ++c) sts128(x_hi(s) + rowoff + sw32b_chunk((uint32_t)c, (uint32_t)j), gr[c]);
         if (h == 0) {
           sts32(sc_base + 8u * j, __float_as_uint(gf));
           sts32(sc_base + 8u * j + 4u, __float_as_uint(gl));
@@ -458,10 +472,9 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
         if (!is_tail) {
           while (jj < cnt && lds32(ms + 4u * (jj + 1)) == key) {
             const uint32_t ro = (uint32_t)h * 16384u + (uint32_t)jj * 128u;
-            const uint32_t jjx = (uint32_t)(jj & 7);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              const float4 v = lds128(x_hi(s) + ro + (((uint32_t)c ^ jjx) << 4));
+              const float4 v = lds128(x_hi(s) + ro + sw32b_chunk((uint32_t)c, (uint32_t)jj));
               gr[c].x += v.x; gr[c].y += v.y; gr[c].z += v.z; gr[c].w += v.w;
             }
             if (h == 0) {
@@ -549,7 +562,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
   }
 }
 
-constexpr size_t BK_SMEM = 1024 + BK_NS * BK_STAGE + BK_STAGE + 16384 + 4 * BK_META + 1024 + 512 + 16 + 8 * 17 + 64;
+constexpr size_t BK_SMEM = 1024 + BK_NS * BK_STAGE + BK_XT + 4 * BK_GT + 16384 + 4 * BK_META + 2048 + 512 + 16 + 8 * 17 + 64;
 
 // ------------------------------------------------------------------------------------------------ UMMA layout probe
 // D[128, 32] = At^T @ Bt for At [K, 128], Bt [K, 32] (K <= 64, multiple of 8) with both operands MN-major, built with
@@ -568,12 +581,12 @@ __global__ void __launch_bounds__(160, 1) umma_probe_kernel(const float* __restr
   for (int i = tid; i < K * 128; i += 160) {
     const int kk = i / 128, mm = i - kk * 128;
     sts32(a_base + (uint32_t)(mm >> 5) * 16384u + (uint32_t)kk * 128u +
-              ((uint32_t)(((mm & 31) >> 2) ^ (kk & 7)) << 4) + 4u * (mm & 3),
+              sw32b_chunk((uint32_t)((mm & 31) >> 2), (uint32_t)kk) + 4u * (mm & 3),
           __float_as_uint(At[i]));
   }
   for (int i = tid; i < K * 32; i += 160) {
     const int kk = i / 32, nn = i - kk * 32;
-    sts32(b_base + (uint32_t)kk * 128u + ((uint32_t)((nn >> 2) ^ (kk & 7)) << 4) + 4u * (nn & 3), __float_as_uint(Bt[i]));
+    sts32(b_base + (uint32_t)kk * 128u + sw32b_chunk((uint32_t)(nn >> 2), (uint32_t)kk) + 4u * (nn & 3), __float_as_uint(Bt[i]));
   }
   fence_proxy_async_smem();
   __syncthreads();
@@ -585,10 +598,10 @@ __global__ void __launch_bounds__(160, 1) umma_probe_kernel(const float* __restr
   bool ok = true;
   if (warp == 4 && lane == 0) {
     const uint32_t idesc = umma_idesc_tf32_major(128, 32, 1, 1);
-    const uint32_t lbo = variant == 0 ? 16384u : 1024u, sbo = variant == 0 ? 1024u : 16384u;
+    const uint32_t lbo = variant == 0 ? 16384u : 512u, sbo = variant == 0 ? 512u : 16384u;
     for (int ks = 0; ks < K / 8; ++ks) {
-      umma_tf32(tmem_base, umma_desc_sw128(a_base + (uint32_t)ks * 1024u, lbo, sbo),
-                umma_desc_sw128(b_base + (uint32_t)ks * 1024u, lbo, sbo), idesc, ks > 0 ? 1u : 0u);
+      umma_tf32(tmem_base, umma_desc_make(a_base + (uint32_t)ks * 1024u, lbo, sbo, 1u),
+                umma_desc_make(b_base + (uint32_t)ks * 1024u, lbo, sbo, 1u), idesc, ks > 0 ? 1u : 0u);
     }
     umma_commit(bar);
   }

@@ -18,18 +18,24 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// SWIZZLE_128B operand descriptor with explicit leading / stride byte offsets (cute::UMMA::SmemDescriptor bits).
-//   K-major  : rows of 128 B, 8-row atoms 1024 B apart           -> lbo = 16 (unused), sbo = 1024
-//   MN-major : canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: the 32-float MN atoms are `lbo` bytes
-//              apart, the 8-row K groups `sbo` bytes apart.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory operand descriptor with explicit layout type and leading / stride byte offsets
+// (cute::UMMA::SmemDescriptor bits).  layout_type: 2 = SWIZZLE_128B (K-major operands: rows of 128 B, 16-byte chunks
+// XOR row & 7, 8-row atoms `sbo` = 1024 B apart), 1 = SWIZZLE_128B_BASE32B - the only swizzled layout the tensor core
+// accepts for MN-major tf32 operands: rows (= K index) of 128 B holding 32 consecutive M/N elements, 32-byte chunks
+// XOR row & 3, atoms of 4 rows `sbo` = 512 B apart, the 32-element M/N atoms `lbo` bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_make(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(layout_type & 7u) << 61;
   return d;
+}
+// byte offset of 16-byte chunk q (0..7) inside row `r` of a SWIZZLE_128B_BASE32B tile
+__device__ __forceinline__ uint32_t sw32b_chunk(uint32_t q, uint32_t r) {
+  return ((((q >> 1) ^ (r & 3u)) << 5) | ((q & 1u) << 4));
 }
 // kind::tf32 instruction descriptor with operand majors (bit 15: A is MN-major, bit 16: B is MN-major)
 __host__ __device__ constexpr uint32_t umma_idesc_tf32_major(int M, int N, int a_mn, int b_mn) {

@@ -89,7 +89,7 @@ def test_umma_mn_major_layout():
     ([50, 7, 1000, 3, 200], 64, 300, 3, 32),
     ([944, 1683, 3, 22, 796, 11, 64], 64, 401, 13, 32),
     ([50, 7, 1000], 32, 200, 0, 16),
-    ([5, 9], 64, 128, 13, 64),
+    ([5, 9], 32, 128, 13, 64),
     ([30] * 26, 64, 515, 13, 32),
     ([17, 5, 300, 41], 32, 77, 5, 24),
 ])
