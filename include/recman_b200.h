@@ -128,13 +128,15 @@ int rm_gather_fm_fwd(const float* table, const float* bias_table, const float* l
  * uniq_rows[N] ascending (first n_unique valid), n_unique[1].
  * Step 2 (reduce): out_rows[u,:] = sum over j in segment u, ascending position,
  * of grad[(p/m)*ld + (p%m)*k + :], p = sorted_pos[j] - a fixed order, no atomics.
- * N = B*m < 2^31, total_rows < 2^32.
+ * N = B*m < 2^31, total_rows < 2^32 - 1.  An id outside its table (or, with table_offsets
+ * NULL, outside [0, total_rows)) sets *status |= 1 (status nullable), is keyed with the
+ * sentinel total_rows and dropped: it sorts behind every row and never appears in uniq_rows.
  * ------------------------------------------------------------------------- */
 size_t rm_segment_plan_workspace_bytes(int64_t N);
 int rm_segment_plan(const int64_t* ids, const int64_t* table_offsets, int64_t N, int32_t m,
                     int64_t total_rows, void* workspace, size_t workspace_bytes,
                     int32_t* sorted_pos, int32_t* seg_start, int64_t* uniq_rows, int32_t* n_unique,
-                    void* stream);
+                    int32_t* status, void* stream);
 int rm_segment_reduce(const float* grad, int64_t ld, int32_t m, int32_t k, int64_t N,
                       const int32_t* sorted_pos, const int32_t* seg_start, const int32_t* n_unique,
                       float* out_rows, void* workspace, size_t workspace_bytes, void* stream);

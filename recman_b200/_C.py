@@ -46,7 +46,7 @@ _SIGS = {
     ),
     "rm_segment_reduce_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "rm_segment_plan_workspace_bytes": (c_size_t, [c_int64]),
-    "rm_segment_plan": (ctypes.c_int, [P, P, c_int64, c_int32, c_int64, P, c_size_t, P, P, P, P, P]),
+    "rm_segment_plan": (ctypes.c_int, [P, P, c_int64, c_int32, c_int64, P, c_size_t, P, P, P, P, P, P]),
     "rm_segment_reduce": (ctypes.c_int, [P, c_int64, c_int32, c_int32, c_int64, P, P, P, P, P, c_size_t, P]),
     "rm_emb_fm_bwd": (
         ctypes.c_int,

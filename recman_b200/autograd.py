@@ -108,6 +108,7 @@ class EmbeddingLayerFunction(Function):
                 ops.gather_pooled(bias_table.reshape(-1, 1), mf.row_offset, mf.rows, values, offsets,
                                   out=bias_out[:, mf.col :], status=status)
         ctx.layout = layout
+        ctx.status = status
         ctx.table = table
         ctx.bias_table = bias_table
         ctx.run_ids = run_ids
@@ -132,7 +133,7 @@ class EmbeddingLayerFunction(Function):
             if not gb.is_contiguous():
                 gb = gb.contiguous()
         for run, ids in zip(layout.runs, ctx.run_ids):
-            plan = ops.segment_plan(ids, run.offsets, layout.total_rows)
+            plan = ops.segment_plan(ids, run.offsets, layout.total_rows, status=ctx.status)
             rows = ops.segment_reduce(ge[:, run.col * k :], plan, k, ld=m * k)
             attach_sparse_grad(table, ops.SparseGrad(plan.uniq_rows, rows, plan.n_unique))
             if gb is not None:
@@ -143,8 +144,10 @@ class EmbeddingLayerFunction(Function):
             if values.numel() == 0:
                 continue
             sample, scale = _expand_csr(values, offsets, B)
-            keys = (values + mf.row_offset).contiguous()
-            plan = ops.segment_plan(keys, None, layout.total_rows)
+            # a tag id outside its table gets the sentinel key (dropped by the plan) instead of a foreign row
+            inside = (values >= 0) & (values < mf.rows)
+            keys = torch.where(inside, values + mf.row_offset, torch.full_like(values, layout.total_rows)).contiguous()
+            plan = ops.segment_plan(keys, None, layout.total_rows, status=ctx.status)
             grows = (ge[:, mf.col * k : (mf.col + 1) * k][sample] * scale[:, None]).contiguous()
             rows = ops.segment_reduce(grows, plan, k, ld=k)
             attach_sparse_grad(table, ops.SparseGrad(plan.uniq_rows, rows, plan.n_unique))
@@ -291,7 +294,9 @@ class FrontEndFunction(Function):
         ctx.fused_opt = fused_opt  # (opt kind, lr): apply the sparse update inside the backward kernel (N1)
         ctx.lin_table = lin_table
         # K2's plan needs the ids only: build it on the side stream, under the front-end kernel and the MLP forward
-        ctx.plan = ops.segment_plan(ids, offsets, total_rows, side=True) if any(ctx.needs_input_grad) else None
+        ctx.status = status
+        ctx.plan = (ops.segment_plan(ids, offsets, total_rows, side=True, status=status)
+                    if any(ctx.needs_input_grad) else None)
         ctx.save_for_backward(x, S, ids, offsets, dense)
         ctx.set_materialize_grads(False)
         return x, fm.reshape(-1, 1), lin.reshape(-1, 1)
@@ -303,7 +308,7 @@ class FrontEndFunction(Function):
         ld = x.shape[1]
         plan, ctx.plan = ctx.plan, None
         if plan is None:
-            plan = ops.segment_plan(ids, offsets, ctx.total_rows)
+            plan = ops.segment_plan(ids, offsets, ctx.total_rows, status=ctx.status)
         if dx is not None and (dx.stride(1) != 1 or dx.stride(0) != ld):
             dx = dx.contiguous()
         g_fm = None if dfm is None else dfm.reshape(-1).contiguous()
@@ -447,7 +452,7 @@ class TowerFunction(Function):
         ctx.plan = None
         if need_grad:  # the plans need the ids only: built on the side stream, under the forward
             ctx.plan = (ops.tower_plan(ids, offsets, total_rows, status=status, side=True) if use_bk
-                        else ops.segment_plan(ids, offsets, total_rows, side=True))
+                        else ops.segment_plan(ids, offsets, total_rows, side=True, status=status))
         ctx.save_for_backward(x, S, ids, dense, W1)
         ctx.set_materialize_grads(False)
         return y1, fm.reshape(-1, 1), lin.reshape(-1, 1)

@@ -24,15 +24,35 @@
 
 namespace rm {
 
+// key = global table row of position p.  An id outside its table (the forward gather zero-fills such a row and raises the
+// status flag) must never become a key inside another field's row range: it gets the sentinel key `total_rows`, sorts
+// behind every real row and its segment is dropped from the plan (drop_sentinel_kernel).
 __global__ void __launch_bounds__(256) make_keys_kernel(const int64_t* __restrict__ ids,
                                                         const int64_t* __restrict__ offs, uint32_t N, uint32_t m,
-                                                        uint32_t* __restrict__ keys, int32_t* __restrict__ pos) {
+                                                        int64_t total_rows, uint32_t* __restrict__ keys,
+                                                        int32_t* __restrict__ pos, int32_t* status) {
   for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
     int64_t key = ids[p];
-    if (offs) key += offs[p % m];
-    keys[p] = (uint32_t)key;
+    bool ok;
+    if (offs) {
+      const uint32_t f = p % m;
+      const int64_t lo = offs[f], hi = offs[f + 1];
+      ok = key >= 0 && key < hi - lo;
+      key += lo;
+    } else {
+      ok = key >= 0 && key < total_rows;
+    }
+    if (!ok && status) atomicOr(status, 1);
+    keys[p] = ok ? (uint32_t)key : (uint32_t)total_rows;
     pos[p] = (int32_t)p;
   }
+}
+
+// the (at most one) trailing segment of sentinel keys is not a table row: remove it from the unique-row count
+__global__ void drop_sentinel_kernel(const uint32_t* __restrict__ sorted_keys, const int32_t* __restrict__ seg_start,
+                                     int32_t* __restrict__ n_unique, int64_t total_rows) {
+  const int32_t U = *n_unique;
+  if (U > 0 && (int64_t)sorted_keys[seg_start[U - 1]] >= total_rows) *n_unique = U - 1;
 }
 
 struct HeadOfRun {
@@ -691,13 +711,13 @@ size_t rm_segment_plan_workspace_bytes(int64_t N) {
 
 int rm_segment_plan(const int64_t* ids, const int64_t* table_offsets, int64_t N, int32_t m, int64_t total_rows,
                     void* workspace, size_t workspace_bytes, int32_t* sorted_pos, int32_t* seg_start,
-                    int64_t* uniq_rows, int32_t* n_unique, void* stream) {
+                    int64_t* uniq_rows, int32_t* n_unique, int32_t* status, void* stream) {
   using namespace rm;
   RM_CHECK_ARG(seg_start && n_unique, "null pointer");
   RM_CHECK_ARG(N >= 0 && m > 0 && total_rows > 0, "bad shape");
   RM_CHECK_ARG(N == 0 || (ids && sorted_pos && uniq_rows), "null pointer");
   RM_UNSUPPORTED(N < ((int64_t)1 << 31) - 1, "N must be < 2^31 - 1");
-  RM_UNSUPPORTED(total_rows <= ((int64_t)1 << 32), "total_rows must be <= 2^32 (32-bit sort keys)");
+  RM_UNSUPPORTED(total_rows < ((int64_t)1 << 32) - 1, "total_rows must be < 2^32 - 1 (32-bit sort keys + sentinel)");
   cudaStream_t st = (cudaStream_t)stream;
   if (N == 0) {
     RM_CUDA(cudaMemsetAsync(n_unique, 0, sizeof(int32_t), st));
@@ -710,11 +730,11 @@ int rm_segment_plan(const int64_t* ids, const int64_t* table_offsets, int64_t N,
     set_error("rm_segment_plan: workspace %zu < required %zu", workspace_bytes, w.total);
     return RM_E_WORKSPACE;
   }
-  make_keys_kernel<<<grid_for(N, 256, 8), 256, 0, st>>>(ids, table_offsets, (uint32_t)N, (uint32_t)m, w.keys_in,
-                                                        w.pos_in);
+  make_keys_kernel<<<grid_for(N, 256, 8), 256, 0, st>>>(ids, table_offsets, (uint32_t)N, (uint32_t)m, total_rows,
+                                                        w.keys_in, w.pos_in, status);
   RM_LAUNCH_CHECK();
   int end_bit = 1;
-  while (end_bit < 32 && ((int64_t)1 << end_bit) < total_rows) ++end_bit;
+  while (end_bit < 32 && ((int64_t)1 << end_bit) <= total_rows) ++end_bit;  // the sentinel key total_rows sorts too
   size_t bytes = w.cub_bytes;
   RM_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, bytes, (const uint32_t*)w.keys_in, w.keys_out,
                                           (const int32_t*)w.pos_in, sorted_pos, (int)N, 0, end_bit, st));
@@ -725,6 +745,8 @@ int rm_segment_plan(const int64_t* ids, const int64_t* table_offsets, int64_t N,
   RM_CUDA(cub::DeviceSelect::If(w.cub_temp, bytes, counting, seg_start, n_unique, (int)N, pred, st));
   count_launch();
   finish_plan_kernel<<<grid_for(N + 1, 256, 8), 256, 0, st>>>(w.keys_out, seg_start, n_unique, (int32_t)N, uniq_rows);
+  RM_LAUNCH_CHECK();
+  drop_sentinel_kernel<<<1, 1, 0, st>>>(w.keys_out, seg_start, n_unique, total_rows);
   RM_LAUNCH_CHECK();
   return 0;
 }

@@ -212,7 +212,7 @@ def _launch_maybe_side(side: bool, launch):
     return ev
 
 
-def segment_plan(ids, table_offsets, total_rows, side: bool = False) -> SegmentPlan:
+def segment_plan(ids, table_offsets, total_rows, side: bool = False, status=None) -> SegmentPlan:
     _dev_check(ids)
     assert ids.dtype == torch.int64 and ids.is_contiguous()
     if ids.dim() == 2:
@@ -229,7 +229,7 @@ def segment_plan(ids, table_offsets, total_rows, side: bool = False) -> SegmentP
     n_unique = torch.empty(1, dtype=torch.int32, device=dev)
     ev = _launch_maybe_side(side, lambda: _C.call(
         "rm_segment_plan", _p(ids), _p(table_offsets), N, m, int(total_rows), _p(ws), ws_bytes, _p(sorted_pos),
-        _p(seg_start), _p(uniq_rows), _p(n_unique), _stream(),
+        _p(seg_start), _p(uniq_rows), _p(n_unique), _p(status), _stream(),
     ))
     return SegmentPlan(N, m, sorted_pos, seg_start, uniq_rows, n_unique, ws, ev)
 

@@ -80,12 +80,16 @@ class DeepFM(DeepModel):
             self.final_logit = final_logit.detach()
             return PredictionLayer(self.variables, self.task, use_bias=False)(final_logit)
 
-        fused = self._fused_front_end(self.embeddings, inputs, self.linear, want_fm=self.use_fm and fm_identity)
+        # FM dropout (a legal reference hyper-parameter, DeepFM.py:36) needs the [B,m,k] block and the bias block
+        # before the reduction: the unfused layers handle it
+        fused = None
+        if fm_identity or not self.use_fm or self.shard is not None:
+            fused = self._fused_front_end(self.embeddings, inputs, self.linear, want_fm=self.use_fm and fm_identity)
         if fused is not None:
             rows, fm_logit, linear_logit = fused
             m, k = len(self.embeddings.feats), hp["embedding_size"]
-            if self.use_fm and fm_logit is None:  # FM dropout active: unfused FM on the gathered block
-                raise NotImplementedError("fm_dropout < 1 with the fused front end")
+            if self.use_fm and fm_logit is None:
+                raise NotImplementedError("row-sharded tables: fm_dropout < 1 is not supported")
             dnn_input = rows
         else:
             feat_embeds, feat_bias = self.embeddings(inputs)

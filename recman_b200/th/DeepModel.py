@@ -143,6 +143,11 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
         """
         k = layer.embedding_size
         if not (layer.all_one_hot and k % 4 == 0 and k <= 128 and inputs.sparse_ids is not None):
+            if self.shard is not None:
+                # the unfused layers know nothing about the exchange: they would index the LOCAL shard with global ids
+                raise NotImplementedError(
+                    "row-sharded tables need the fused front end: every embedding feature one-hot (no multi-valued "
+                    "fields), embedding_size % 4 == 0 and <= 128")
             return None
         layer._upsert_variables()
         table = self.variables[layer.table_name]
@@ -156,6 +161,8 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
             feats = linear.linear_feats
             want = self.feat_dict.sparse_feats + self.feat_dict.dense_feats
             if [f.name for f in feats] != [f.name for f in want]:
+                if self.shard is not None:
+                    raise NotImplementedError("row-sharded tables: linear features must be [sparse..., dense...]")
                 return None
             if self.shard is not None:
                 linear.total = self.shard.total_local + n_dense  # id rows are sharded like the tables, tail replicated
@@ -314,26 +321,78 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
         return X[start:end], y[start:end]
 
     # ------------------------------------------------------------------ state
-    def state_dict(self) -> Dict[str, torch.Tensor]:
-        """Reference-named tensors: per-feature ``*_feat_embed`` / ``*_feat_bias`` views instead of the fused tables."""
+    def _table_layers(self):
+        """(embedding layer, linear layer | None) of the last forward, for the reference-named views."""
+        return getattr(self, "embeddings", None), getattr(self, "linear", None)
+
+    def state_dict(self, reference_names: bool = True) -> Dict[str, torch.Tensor]:
+        """Every variable under the reference's names.  The fused tables are exported as the per-feature variables
+        the reference creates (layers.py:95-110): ``{feat}_feat_embed`` [V_f, k] and ``{feat}_feat_bias`` [V_f, 1]
+        (row-range views of ``feat_embed_table`` / ``feat_bias_table``); everything else keeps its name.  With
+        ``reference_names=False`` the fused tables are exported as they are stored."""
         out = {}
+        emb, _ = self._table_layers()
+        fused = set()
+        if reference_names and emb is not None and self.shard is None and emb.table_name in self.variables:
+            out.update(emb.feature_tables())
+            fused = {emb.table_name, emb.bias_name}
         for name, p in self.variables.items():
-            out[name] = p.data
+            if name not in fused:
+                out[name] = p.data
         return out
 
     def load_state_dict(self, state: Dict[str, torch.Tensor], strict=True):
+        """Accepts both the reference-named per-feature tables and the fused tables.  Returns (missing, unexpected);
+        with ``strict`` (default) either raises."""
+        emb, _ = self._table_layers()
+        views = emb.feature_tables() if (emb is not None and self.shard is None and emb.table_name in self.variables) else {}
+        seen, unexpected = set(), []
         for name, t in state.items():
             if name in self.variables:
-                self.variables[name].data.copy_(t.to(self.device))
-            elif strict:
-                raise KeyError(name)
+                self.variables[name].data.copy_(t.to(self.device).reshape(self.variables[name].shape))
+                seen.add(name)
+            elif name in views:
+                views[name].copy_(t.to(self.device).reshape(views[name].shape))
+                seen.add(name)
+            else:
+                unexpected.append(name)
+        covered = set(seen)
+        if emb is not None and views:
+            per_table = [n for n in views if n.endswith("_feat_embed")]
+            if per_table and all(n in seen for n in per_table):
+                covered.add(emb.table_name)
+            per_bias = [n for n in views if n.endswith("_feat_bias")]
+            if per_bias and all(n in seen for n in per_bias):
+                covered.add(emb.bias_name)
+        missing = [n for n in self.variables if n not in covered]
+        if strict and (missing or unexpected):
+            raise KeyError(f"load_state_dict: missing {missing}, unexpected {unexpected}")
+        return missing, unexpected
 
     def save(self, path="ckpt_model.pt"):
-        torch.save({k: v.cpu() for k, v in self.state_dict().items()}, path)
+        """torch.save of ``state_dict()``.  With row-sharded tables every rank holds different rows: the file gets a
+        ``.rank{r}`` suffix and keeps the fused (local-shard) layout."""
+        if self.shard is not None:
+            path = f"{path}.rank{self.shard.rank}"
+        torch.save({k: v.cpu() for k, v in self.state_dict(reference_names=self.shard is None).items()}, path)
 
-    def restore(self, path="ckpt_model.pt"):
-        """DeepModel.restore (DeepModel.py:83-86) with torch.save files instead of tf.train.Checkpoint."""
-        self.load_state_dict(torch.load(path), strict=False)
+    def restore(self, path="ckpt_model.pt", example=None, strict=True):
+        """DeepModel.restore (DeepModel.py:83-86) with torch.save files instead of tf.train.Checkpoint.
+
+        Variables are created lazily by the first forward: on a fresh model pass ``example`` (a DataFrame / dict of
+        columns, or DataInputs) so that they exist before the file is loaded; restoring into a model that has no
+        variables raises instead of silently loading nothing."""
+        if self.shard is not None:
+            path = f"{path}.rank{self.shard.rank}"
+        if example is not None and not self.variables:
+            inputs = example if isinstance(example, DataInputs) else DataInputs(self.device).load(
+                self.feat_dict, example, np.zeros(len(next(iter(example.values()))) if isinstance(example, dict)
+                                                  else len(example), dtype=np.float32))
+            with torch.no_grad():
+                self._out(inputs, training=False)
+        if not self.variables:
+            raise RuntimeError("restore(): the model has no variables yet - run a forward first or pass example=...")
+        return self.load_state_dict(torch.load(path), strict=strict)
 
     # ------------------------------------------------------------------ training
     @abstractmethod
@@ -348,6 +407,8 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
         """One optimisation step (xDeepFM.py:116-126): encode, forward, backward, fresh-optimizer update."""
         inputs = X if isinstance(X, DataInputs) else DataInputs(self.device).load(self.feat_dict, X, y)
         self.samples_seen += inputs.batch_size
+        if self.shard is not None and not getattr(self, "_replicas_synced", False):
+            self._sync_replicated(inputs)
         if getattr(self, "_graph", None) is not None:
             loss = self._graph_step(inputs)
             if loss is not None:
@@ -355,6 +416,31 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
         # eager: with sharded tables every rank's loss is a mean over its local batch; 1/W makes the summed
         # gradients those of the global-batch mean (and counts the replicated L2 terms once)
         return self._eager_step(inputs)
+
+    def _sync_replicated(self, inputs: DataInputs):
+        """Row-sharded mode: the dense (replicated) parameters must start equal on every rank - only their gradients
+        are all-reduced afterwards.  Creates the variables with one forward and broadcasts rank 0's values."""
+        import torch.distributed as dist
+
+        with torch.no_grad():
+            self._out(inputs, training=False)
+        emb, lin = getattr(self, "embeddings", None), getattr(self, "linear", None)
+        sharded = {emb.table_name, emb.bias_name} if emb is not None else set()
+        lin_name = f"{lin.prefix}linear_w" if lin is not None else None
+        for name, p in self.variables.items():
+            if name in sharded:
+                continue
+            t = p.data
+            if name == lin_name:  # id rows are sharded like the tables, the dense tail is replicated
+                t = t.reshape(-1)[self.shard.total_local:]
+                if t.numel() == 0:
+                    continue
+            buf = t.contiguous()
+            dist.broadcast(buf, src=dist.get_global_rank(self.shard.group, 0) if self.shard.group is not None else 0,
+                           group=self.shard.group)
+            if buf.data_ptr() != t.data_ptr():
+                t.copy_(buf)
+        self._replicas_synced = True
 
     # ------------------------------------------------------------------ CUDA-graphed step (N1)
     def compile_step(self, example: DataInputs, warmup: int = 3):
@@ -371,6 +457,8 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
                                       "use peer-memory sharding")
         from .. import ops as _ops
 
+        if self.shard is not None and not getattr(self, "_replicas_synced", False):
+            self._sync_replicated(example)
         st = DataInputs.from_tensors(
             self.feat_dict, example.sparse_ids.clone(), None if example.dense is None else example.dense.clone(),
             example["y"].clone())

@@ -609,7 +609,7 @@ class CIN:
             field_nums.append(size // 2)
             final_size += field_nums[-1] if i != len(self.cross_layer_units) - 1 else size
         if f"{p}cin_w" not in v:
-            v[f"{p}cin_w"] = _param(glorot_uniform([final_size, 1]))
+            v[f"{p}cin_w"] = _param(glorot_uniform([final_size, 1], seed=int(self.seed) + 1))  # seeded: equal on every rank
         if f"{p}cin_w0" not in v:
             v[f"{p}cin_w0"] = _param(torch.zeros(1, dtype=torch.float32, device=DEVICE))
 
