@@ -5,7 +5,7 @@ import torch
 from recman_b200 import ops
 
 torch.manual_seed(0)
-for variant in (0, 1):
+for variant in (0,):  # variant 1 (LBO / SBO swapped) reads outside the tile: illegal address on the device
     K = 64
     At = torch.randint(-4, 5, (K, 128)).float()
     Bt = torch.randint(-4, 5, (K, 32)).float()

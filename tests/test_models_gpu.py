@@ -366,13 +366,19 @@ def test_tower_inference_weight_override():
     fd = pu.make_feat_dict([40, 9, 300], n_dense=2)
     X, y = pu.synth_batch(fd, 200, seed=3)
     outs = {}
+    first = None
     for tower in (True, False):
         model = DeepFM(fd, embedding_size=64, deep_hidden_units=(32, 32), deep_dropout=(1, 1, 1), batch_size=200)
         model.hparams["tower"] = tower
         inputs = DataInputs("cuda").load(fd, X, y)
         with torch.no_grad():
             model._out(inputs)
-        pu.randomize_variables(model, seed=9)
+        if first is None:
+            pu.randomize_variables(model, seed=9)
+            first = model
+        else:  # same weights by name (the two layouts create their variables in a different order)
+            for name, p in first.variables.items():
+                model.variables[name].data.copy_(p.data)
         with torch.no_grad():
             base = model._out(inputs, training=False).cpu()
         fd["C1"].set_weights({3: -5.0})  # the reference's set_weights({"Outdoor": -5}) with ids for keys
