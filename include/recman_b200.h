@@ -20,7 +20,8 @@
  *     `rm_last_error()` returns a thread-local message for the last failure;
  *   - there is no CPU path and no other-architecture path: `rm_device_check`
  *     refuses anything but compute capability 10.x.
- *   - all floating point is IEEE fp32 (no fast-math), ids are int64 as in the
+ *   - all floating point is fp32 without fast-math (the one exception: the optimizer update's division is the
+ *     2-ulp __fdividef, see csrc/optim.cuh), ids are int64 as in the
  *     reference (tf/inputs.py:158).
  */
 #ifndef RECMAN_B200_H_

@@ -13,17 +13,24 @@ struct OptParams {
   float l2;
 };
 
+// p <- first step of a freshly created optimizer (zero slot variables) on gradient g (+ l2 * p).
+// Adam (beta1 0.9, beta2 0.999, eps 1e-7): p - lr_t * m / (sqrt(v) + eps) with m = 0.1 g, v = 0.001 g^2, and
+// sqrt(0.001 g^2) = sqrt(0.001) |g| - evaluated in that form (no underflow of g^2 for tiny g, as in the fp64 oracle) with
+// one approximate division (2 ulp): the update is lr-sized, so its rounding is ~1e-10 absolute, far inside the 1e-5
+// parity bound, and it keeps the fused backward kernels off the IEEE div / sqrt instruction sequences.
+// Every operation is an explicit round-to-nearest intrinsic, so the compiler contracts nothing differently from one
+// kernel to the next: the fused reduce+update kernels stay bit-identical to reduce followed by rm_sparse_opt_step.
 __device__ __forceinline__ float opt_update(float p, float g, const OptParams& o) {
-  g += o.l2 * p;
+  g = __fmaf_rn(o.l2, p, g);
   if (o.opt == RM_OPT_ADAM) {
-    const float m = 0.1f * g;             // (1 - beta1) * g, beta1 = 0.9
-    const float v = 0.001f * g * g;       // (1 - beta2) * g^2, beta2 = 0.999
-    return p - o.lr_t * m / (sqrtf(v) + 1e-7f);
+    const float q = __fdividef(__fmul_rn(0.1f, g), __fmaf_rn(0.0316227766f, fabsf(g), 1e-7f));
+    return __fmaf_rn(-o.lr_t, q, p);
   } else if (o.opt == RM_OPT_ADAGRAD) {
-    const float acc = 0.1f + g * g;       // initial_accumulator_value = 0.1
-    return p - o.lr * g / (sqrtf(acc) + 1e-7f);
+    const float acc = __fmaf_rn(g, g, 0.1f);  // initial_accumulator_value = 0.1
+    const float q = __fdividef(g, __fadd_rn(__fsqrt_rn(acc), 1e-7f));
+    return __fmaf_rn(-o.lr, q, p);
   }
-  return p - o.lr * g;                    // gd / fresh momentum
+  return __fmaf_rn(-o.lr, g, p);  // gd / fresh momentum
 }
 
 static inline int make_params(int opt, float lr, float l2, OptParams* o) {

@@ -36,8 +36,10 @@ constexpr int BK_TILE = 128;
 constexpr int BK_NS = 3;    // gather stages
 constexpr int BK_DEPTH = 2; // tiles in flight per producer thread
 constexpr int BK_PRODUCERS = 128;
-constexpr int BK_EPI = 256;
-constexpr int BK_THREADS = 128 + 32 + 256;  // 4 producer warps, 1 MMA warp, 8 epilogue warps
+constexpr bool BK_PREFETCH = false;  // request the next tile's per-sample operands one tile ahead
+constexpr int BK_NH = 2;              // epilogue threads per position (each owns 64 / BK_NH columns of the row)
+constexpr int BK_EPI = 128 * BK_NH;
+constexpr int BK_THREADS = 128 + 32 + BK_EPI;  // 4 producer warps, 1 MMA warp, 4 * BK_NH epilogue warps
 constexpr int BK_DRAIN = 4;  // tiles per TMEM accumulation group of GEMM 2
 constexpr uint32_t BK_XT = 32768, BK_GT = 16384, BK_STAGE = BK_XT;  // a gather stage holds the x tile only
 constexpr uint32_t BK_META = 1088;  // key[130] (prev, 128, next) + b[128], padded
@@ -189,7 +191,9 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
   const uint32_t sc_base0 = meta_base + 4u * BK_META;  // [2][128] float2 (tile parity)
   const uint32_t carry_base = sc_base0 + 2048u;      // [2][64] floats
   const uint32_t carry_sc = carry_base + 512u;      // [2] float2
-  const uint32_t bar_base = carry_sc + 16u;
+  const uint32_t scal_st = carry_sc + 16u;          // [BK_NS][128] float2: old (bias, weight) of the tile's rows
+  const uint32_t wr_base = scal_st + BK_NS * 1024u; // [2][128] u32: table row to store (TW_NONE = none), tile parity
+  const uint32_t bar_base = wr_base + 1024u;
   auto full = [&](int s) { return bar_base + 8u * s; };
   auto empty = [&](int s) { return bar_base + 8u * (3 + s); };
   auto d1_full = [&](int b) { return bar_base + 8u * (6 + b); };
@@ -261,6 +265,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
       const uint32_t ms = meta_base + (uint32_t)(X & 3) * BK_META;
       ok = ok && mbar_wait(empty(s), (((uint32_t)(X / BK_NS)) & 1u) ^ 1u);
       const int cnt = it_issue.cnt();
+      const uint32_t mkey_cur = mkey;
       // key slots: [0] previous key, [1..cnt] the tile, [cnt+1] next key, the rest TW_NONE
       sts32(ms + 4u * (tid < cnt ? tid + 1 : tid + 2), mkey);
       sts32(ms + 4u * (130 + tid), (uint32_t)mb);
@@ -275,6 +280,10 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
         const bool live = r < cnt;
         const uint32_t key = live ? lds32(ms + 4u * (r + 1)) : 0u;
         cp_async16(x_hi(s) + xoff + (uint32_t)i * 1024u, P.table + (int64_t)key * BK_K + 4 * cx, live ? 16u : 0u);
+      }
+      if (P.scal) {  // the row's (bias, weight) pair rides with the gather instead of stalling the epilogue
+        const bool live = tid < cnt;
+        cp_async8(scal_st + (uint32_t)s * 1024u + 8u * tid, P.scal + 2 * (int64_t)(live ? mkey_cur : 0u), live ? 8u : 0u);
       }
       ++X;
     };
@@ -326,7 +335,8 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
     // ================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc1 = umma_idesc_tf32_major(128, BK_K, 0, 0);
-      const uint32_t idesc2 = umma_idesc_tf32_major(128, BK_N1, 1, 1);
+      const uint32_t idesc2w = umma_idesc_tf32_major(128, 2 * BK_N1, 1, 1);  // x_hi^T x [g_hi | g_lo]
+      const uint32_t idesc2 = umma_idesc_tf32_major(128, BK_N1, 1, 1);       // x_lo^T x g_hi
       it.load_unit();
       int Y = 0, G = 0, tin = 0, cur_f = -1, wloads = 0;
       while (it.valid()) {
@@ -344,18 +354,17 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
         if (tin == 0) ok = ok && mbar_wait(d2_empty(gb), (((uint32_t)(G >> 1)) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d1 = tmem_base + (uint32_t)(64 * db);
-        const uint32_t d2 = tmem_base + 128u + (uint32_t)(32 * gb);
+        const uint32_t d2 = tmem_base + 128u + (uint32_t)(64 * gb);
         // GEMM 2: dW1_f[c, n] += sum_pos x[pos, c] * g1[pos, n]   (rows 64..127 of the accumulator are unused)
 #pragma unroll 4
         for (int ks = 0; ks < 16; ++ks) {
           const uint32_t ko = (uint32_t)ks * 1024u;
           const uint64_t a_hi = umma_desc_make(x_hi(s) + ko, 16384u, 512u, 1u);
           const uint64_t a_lo = umma_desc_make(x_lo + ko, 16384u, 512u, 1u);
-          const uint64_t b_hi = umma_desc_make(g2_hi + ko, 16384u, 512u, 1u);
-          const uint64_t b_lo = umma_desc_make(g2_lo + ko, 16384u, 512u, 1u);
-          umma_tf32(d2, a_hi, b_hi, idesc2, (tin > 0 || ks > 0) ? 1u : 0u);
-          umma_tf32(d2, a_hi, b_lo, idesc2, 1u);
-          umma_tf32(d2, a_lo, b_hi, idesc2, 1u);
+          // g2_lo sits 16 KB behind g2_hi: with the 32-column N atoms 16 KB apart, [g_hi | g_lo] is one N = 64 operand
+          const uint64_t b_g = umma_desc_make(g2_hi + ko, 16384u, 512u, 1u);
+          umma_tf32(d2, a_hi, b_g, idesc2w, (tin > 0 || ks > 0) ? 1u : 0u);
+          umma_tf32(d2, a_lo, b_g, idesc2, 1u);
         }
         // GEMM 1: dx[pos, c] = sum_n g1[pos, n] * W1_f[c, n]
 #pragma unroll
@@ -380,85 +389,120 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
       }
     }
   } else {
-    // ================================================================== epilogue: one position per thread pair
-    const int e = warp - 5;
-    const int q = warp & 3, h = e >> 2;  // TMEM lane quadrant of this warp, column half
+    // ================================================================== epilogue: BK_NH threads per position
+    // thread (j, h): position j = TMEM lane, 16-byte chunks h*CPT .. h*CPT+CPT-1 of the 64-float row
+    constexpr int CPT = 16 / BK_NH;   // chunks per thread
+    constexpr int DWC = BK_N1 / BK_NH;  // dW1 columns per thread
+    const int q = warp & 3, h = (warp - 5) >> 2;  // TMEM lane quadrant of this warp, column group
     const int j = 32 * q + lane;
-    const uint32_t rowoff = (uint32_t)h * 16384u + (uint32_t)j * 128u;
-    float dwacc[16];
+    // all addressing that does not depend on the tile is computed once
+    uint32_t xo[CPT];  // this thread's chunks of row j inside a gather stage
 #pragma unroll
-    for (int i = 0; i < 16; ++i) dwacc[i] = 0.f;
+    for (int c = 0; c < CPT; ++c) {
+      const uint32_t cq = (uint32_t)(h * CPT + c);
+      xo[c] = (cq >> 3) * 16384u + (uint32_t)j * 128u + sw32b_chunk(cq & 7u, (uint32_t)j);
+    }
+    const int et = tid - 160;  // index inside the epilogue group
+    const int qc = et & 15, r0 = et >> 4;  // write-back: chunk qc of rows r0 + (BK_EPI/16) i
+    const uint32_t so0 = (uint32_t)(qc >> 3) * 16384u + (uint32_t)r0 * 128u + sw32b_chunk((uint32_t)(qc & 7), (uint32_t)r0);
+    const uint32_t tm_lane = tmem_base + ((uint32_t)(32 * q) << 16);
+    float dwacc[DWC];
+#pragma unroll
+    for (int i = 0; i < DWC; ++i) dwacc[i] = 0.f;
     // units without positions still own a slab: zero it
     for (int u = u_begin; u < it.u_end; ++u) {
       const int f = u / P.upf, i = u - f * P.upf;
       if (P.ub[f * (P.upf + 1) + i + 1] <= P.ub[f * (P.upf + 1) + i] && j < BK_K) {
-        float* dst = P.slabs + ((int64_t)u * BK_K + j) * BK_N1 + 16 * h;
+        float* dst = P.slabs + ((int64_t)u * BK_K + j) * BK_N1 + DWC * h;
 #pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) st4(dst + 4 * i4, make_float4(0.f, 0.f, 0.f, 0.f));
+        for (int i4 = 0; i4 < DWC / 4; ++i4) st4(dst + 4 * i4, make_float4(0.f, 0.f, 0.f, 0.f));
       }
     }
     it.load_unit();
+    TileIter it_next = it;
+    if (it_next.valid()) it_next.next();
+    // per-sample operands of the tile (S row part, g_fm, g_lin): loaded one tile ahead when that tile has landed
+    float4 Sv[CPT];
+    float gf = 0.f, gl = 0.f;
+    bool have = false;
+    auto load_sample = [&](const TileIter& ti, int Yt) {
+      const uint32_t mst = meta_base + (uint32_t)(Yt & 3) * BK_META;
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) Sv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      gf = 0.f;
+      gl = 0.f;
+      if (j < ti.cnt()) {
+        const int32_t b = (int32_t)lds32(mst + 4u * (130 + j));
+        const float4* Sp = reinterpret_cast<const float4*>(P.S + (int64_t)b * BK_K + 4 * CPT * h);
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) Sv[c] = __ldg(Sp + c);
+        gf = __ldg(P.g_fm + b);
+        if (h == 0 && P.g_lin) gl = __ldg(P.g_lin + b);
+      }
+    };
     int Y = 0, G = 0, tin = 0;
     while (it.valid()) {
       const int s = Y % BK_NS, db = Y & 1, gb = G & 1;
       const uint32_t ms = meta_base + (uint32_t)(Y & 3) * BK_META;
       const uint32_t sc_base = sc_base0 + (uint32_t)(Y & 1) * 1024u;
+      const uint32_t xs = x_hi(s);
       const int cnt = it.cnt();
       ok = ok && mbar_wait(full(s), ((uint32_t)(Y / BK_NS)) & 1u);
       const bool valid = j < cnt;
       const uint32_t key = lds32(ms + 4u * (j + 1));
       const uint32_t kprev = lds32(ms + 4u * j);
       const uint32_t knext = valid ? lds32(ms + 4u * (j + 2)) : TW_NONE;
-      const int32_t b = (int32_t)lds32(ms + 4u * (130 + j));
       const bool is_head = valid && key != kprev;
       const bool is_tail = valid && key != knext;
-      float4 Sv[8];
-      float gf = 0.f, gl = 0.f;
-      float2 sold = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) Sv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid) {
-        const float* Sp = P.S + (int64_t)b * BK_K + 32 * h;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) Sv[c] = __ldg(reinterpret_cast<const float4*>(Sp) + c);
-        gf = __ldg(P.g_fm + b);
-        if (h == 0) {
-          if (P.g_lin) gl = __ldg(P.g_lin + b);
-          if (P.scal && (is_head || j == 0)) sold = *reinterpret_cast<const float2*>(P.scal + 2 * (int64_t)key);
-        }
-      }
+      if (!have) load_sample(it, Y);
+      have = false;
       ok = ok && mbar_wait(d1_full(db), ((uint32_t)(Y >> 1)) & 1u);
       tc_fence_after();
-      uint32_t dr[32];
-      tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(64 * db + 32 * h), dr);
+      uint32_t dr[4 * CPT];
+      tmem_ld_cols<4 * CPT>(tm_lane + (uint32_t)(64 * db + 4 * CPT * h), dr);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(d1_empty(db));
-      float4 xr[8], gr[8];
+      float4 xr[CPT], gr[CPT];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        xr[c] = lds128(x_hi(s) + rowoff + sw32b_chunk((uint32_t)c, (uint32_t)j));
+      for (int c = 0; c < CPT; ++c) {
+        xr[c] = lds128(xs + xo[c]);
         gr[c].x = __uint_as_float(dr[4 * c + 0]) + gf * (Sv[c].x - xr[c].x);
         gr[c].y = __uint_as_float(dr[4 * c + 1]) + gf * (Sv[c].y - xr[c].y);
         gr[c].z = __uint_as_float(dr[4 * c + 2]) + gf * (Sv[c].z - xr[c].z);
         gr[c].w = __uint_as_float(dr[4 * c + 3]) + gf * (Sv[c].w - xr[c].w);
       }
+      float asf = gf, asl = gl;
       const bool single = is_head && is_tail;
       if (valid && !single) {  // members of longer segments exchange their rows through the (now dead) x tile
 #pragma unroll
-        for (int c = 0; c < 8; ++c) sts128(x_hi(s) + rowoff + sw32b_chunk((uint32_t)c, (uint32_t)j), gr[c]);
+        for (int c = 0; c < CPT; ++c) sts128(xs + xo[c], gr[c]);
         if (h == 0) {
           sts32(sc_base + 8u * j, __float_as_uint(gf));
           sts32(sc_base + 8u * j + 4u, __float_as_uint(gl));
         }
       }
+      // next tile's per-sample operands: requested now (if that tile has landed), consumed one iteration later
+      if (BK_PREFETCH && it_next.valid()) {
+        const int sn = (Y + 1) % BK_NS;
+        uint32_t done;
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(full(sn)), "r"(((uint32_t)((Y + 1) / BK_NS)) & 1u)
+            : "memory");
+        if (__all_sync(0xffffffffu, done != 0)) {
+          load_sample(it_next, Y + 1);
+          have = true;
+        }
+      }
       named_bar_sync(3, BK_EPI);
+      uint32_t wkey = TW_NONE;  // table row this position finished (its new values sit in the x tile)
       if (valid && (is_head || j == 0)) {  // leader of a segment (or of its part inside this tile)
-        float asf = gf, asl = gl;
         if (!is_head) {  // continues from the previous tile: the carried partial sum comes first (position order)
-          const uint32_t cb = carry_base + (uint32_t)((Y + 1) & 1) * 256u + (uint32_t)h * 128u;
+          const uint32_t cb = carry_base + (uint32_t)((Y + 1) & 1) * 256u + (uint32_t)(h * CPT) * 16u;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
+          for (int c = 0; c < CPT; ++c) {
             const float4 cv = lds128(cb + 16u * c);
             gr[c].x = cv.x + gr[c].x; gr[c].y = cv.y + gr[c].y; gr[c].z = cv.z + gr[c].z; gr[c].w = cv.w + gr[c].w;
           }
@@ -471,10 +515,10 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
         int jj = j + 1;
         if (!is_tail) {
           while (jj < cnt && lds32(ms + 4u * (jj + 1)) == key) {
-            const uint32_t ro = (uint32_t)h * 16384u + (uint32_t)jj * 128u;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 v = lds128(x_hi(s) + ro + sw32b_chunk((uint32_t)c, (uint32_t)jj));
+            for (int c = 0; c < CPT; ++c) {
+              const uint32_t cq = (uint32_t)(h * CPT + c);
+              const float4 v = lds128(xs + (cq >> 3) * 16384u + (uint32_t)jj * 128u + sw32b_chunk(cq & 7u, (uint32_t)jj));
               gr[c].x += v.x; gr[c].y += v.y; gr[c].z += v.z; gr[c].w += v.w;
             }
             if (h == 0) {
@@ -490,23 +534,24 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
           const int64_t opos = (int64_t)it.p0 + jj - 1;  // sorted position that closes the segment
           if (P.out_rows) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) st4(P.out_rows + opos * BK_K + 32 * h + 4 * c, gr[c]);
+            for (int c = 0; c < CPT; ++c) st4(P.out_rows + opos * BK_K + 4 * (h * CPT + c), gr[c]);
           }
-          if (P.do_update) {
-            float* trow = P.table + (int64_t)key * BK_K + 32 * h;
+          if (P.do_update) {  // new row -> this thread's slot of the (dead) x tile; stored 256 B at a time below
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < CPT; ++c) {
               float4 nv;
               nv.x = opt_update(xr[c].x, gr[c].x, P.o);
               nv.y = opt_update(xr[c].y, gr[c].y, P.o);
               nv.z = opt_update(xr[c].z, gr[c].z, P.o);
               nv.w = opt_update(xr[c].w, gr[c].w, P.o);
-              st4(trow + 4 * c, nv);
+              sts128(xs + xo[c], nv);
             }
+            wkey = key;
           }
           if (h == 0) {
             if (P.out_scal) *reinterpret_cast<float2*>(P.out_scal + 2 * opos) = make_float2(asf, asl);
             if (P.scal && P.do_update) {
+              const float2 sold = lds64f(scal_st + (uint32_t)s * 1024u + 8u * j);
               float2 nv;
               nv.x = opt_update(sold.x, asf, P.o);
               nv.y = P.g_lin ? opt_update(sold.y, asl, P.o) : sold.y;
@@ -514,12 +559,26 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
             }
           }
         } else {
-          const uint32_t cb = carry_base + (uint32_t)(Y & 1) * 256u + (uint32_t)h * 128u;
+          const uint32_t cb = carry_base + (uint32_t)(Y & 1) * 256u + (uint32_t)(h * CPT) * 16u;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) sts128(cb + 16u * c, gr[c]);
+          for (int c = 0; c < CPT; ++c) sts128(cb + 16u * c, gr[c]);
           if (h == 0) {
             sts32(carry_sc + (uint32_t)(Y & 1) * 8u, __float_as_uint(asf));
             sts32(carry_sc + (uint32_t)(Y & 1) * 8u + 4u, __float_as_uint(asl));
+          }
+        }
+      }
+      if (P.do_update) {
+        // coalesced write-back: 16 lanes per finished row store its 256 bytes contiguously
+        const uint32_t wb = wr_base + (uint32_t)(Y & 1) * 512u;
+        if (h == 0) sts32(wb + 4u * j, wkey);
+        named_bar_sync(3, BK_EPI);
+#pragma unroll
+        for (int i = 0; i < 2048 / BK_EPI; ++i) {
+          const uint32_t wk = lds32(wb + 4u * (uint32_t)(r0 + (BK_EPI / 16) * i));
+          if (wk != TW_NONE) {
+            const float4 v = lds128(xs + so0 + (uint32_t)i * ((BK_EPI / 16) * 128u));
+            st4(P.table + (int64_t)wk * BK_K + 4 * qc, v);
           }
         }
       }
@@ -529,28 +588,32 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
       if (tin == BK_DRAIN || unit_end) {  // drain the GEMM 2 accumulator (fp32 round-to-nearest adds)
         ok = ok && mbar_wait(d2_full(gb), ((uint32_t)(G >> 1)) & 1u);
         tc_fence_after();
-        uint32_t w[16];
-        tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + 128u + (uint32_t)(32 * gb + 16 * h), w);
+        // accumulator = [x_hi*g_hi + x_lo*g_hi | x_hi*g_lo]: columns n and 32 + n belong together
+        uint32_t w0[DWC], w1[DWC];
+        const uint32_t ta = tm_lane + 128u + (uint32_t)(64 * gb + DWC * h);
+        tmem_ld_cols<DWC>(ta, w0);
+        tmem_ld_cols<DWC>(ta + 32u, w1);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(d2_empty(gb));
 #pragma unroll
-        for (int i = 0; i < 16; ++i) dwacc[i] += __uint_as_float(w[i]);
+        for (int i = 0; i < DWC; ++i) dwacc[i] += __uint_as_float(w0[i]) + __uint_as_float(w1[i]);
         ++G;
         tin = 0;
         if (unit_end) {
           if (j < BK_K) {
-            float* dst = P.slabs + ((int64_t)it.u * BK_K + j) * BK_N1 + 16 * h;
+            float* dst = P.slabs + ((int64_t)it.u * BK_K + j) * BK_N1 + DWC * h;
 #pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4)
+            for (int i4 = 0; i4 < DWC / 4; ++i4)
               st4(dst + 4 * i4, make_float4(dwacc[4 * i4], dwacc[4 * i4 + 1], dwacc[4 * i4 + 2], dwacc[4 * i4 + 3]));
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dwacc[i] = 0.f;
+          for (int i = 0; i < DWC; ++i) dwacc[i] = 0.f;
         }
       }
       ++Y;
       it.next();
+      if (it_next.valid()) it_next.next();
     }
   }
   if (!ok && P.status) atomicOr(P.status, 2);
@@ -562,7 +625,8 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
   }
 }
 
-constexpr size_t BK_SMEM = 1024 + BK_NS * BK_STAGE + BK_XT + 4 * BK_GT + 16384 + 4 * BK_META + 2048 + 512 + 16 + 8 * 17 + 64;
+constexpr size_t BK_SMEM = 1024 + BK_NS * BK_STAGE + BK_XT + 4 * BK_GT + 16384 + 4 * BK_META + 2048 + 512 + 16 +
+                           BK_NS * 1024 + 1024 + 8 * 17 + 64;
 
 // ------------------------------------------------------------------------------------------------ UMMA layout probe
 // D[128, 32] = At^T @ Bt for At [K, 128], Bt [K, 32] (K <= 64, multiple of 8) with both operands MN-major, built with

@@ -27,8 +27,9 @@
 namespace rm {
 
 constexpr int TF_ROWS = 128;
-constexpr int TF_STAGES = 3;
-constexpr int TF_DEPTH = 2;  // fields in flight per producer thread
+constexpr int TF_STAGES = 4;   // gather stages (one field of the tile each)
+constexpr int TF_DEPTH = 3;    // fields in flight per producer thread
+constexpr int TF_WSLOTS = 2;   // W1 field images in flight
 constexpr int TF_PRODUCERS = 256;
 constexpr int TF_THREADS = 320;
 
@@ -55,7 +56,8 @@ struct TowerFwdParams {
   uint32_t tmem_cols;
 };
 
-// W1 field images for the forward: B operand = W1_f^T, K-major.  Per field f: [part hi|lo][blk][n < N1PAD][128 B];
+// W1 field images for the forward: B operand = W1_f^T, K-major.  Per field f: [blk][part hi|lo][n < N1PAD][128 B] - the hi
+// and lo rows of a block are adjacent, so [w_hi | w_lo] is ONE operand of N = 2*N1PAD rows;
 // chunk ch of row n holds W1[f*k + blk*32 + 4ch .. +3][n] at chunk position ch ^ (n & 7).
 __global__ void __launch_bounds__(256) tower_pack_w1t_kernel(const float* __restrict__ W1, int m, int k, int N1,
                                                              int N1PAD, uint32_t* __restrict__ out) {
@@ -65,9 +67,9 @@ __global__ void __launch_bounds__(256) tower_pack_w1t_kernel(const float* __rest
     const int ch = (int)(i & 7);
     int64_t t = i >> 3;
     const int n = (int)(t % N1PAD); t /= N1PAD;
-    const int blk = (int)(t % KB); t /= KB;
-    const int part = (int)(t & 1);
-    const int f = (int)(t >> 1);
+    const int part = (int)(t & 1); t >>= 1;
+    const int blk = (int)(t % KB);
+    const int f = (int)(t / KB);
     uint32_t v[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(256) tower_pack_w1t_kernel(const float* __rest
       const uint32_t hi = f32_to_tf32(w);
       v[e] = part ? f32_to_tf32(w - __uint_as_float(hi)) : hi;
     }
-    uint32_t* dst = out + ((((int64_t)f * 2 + part) * KB + blk) * N1PAD + n) * 32 + ((ch ^ (n & 7)) << 2);
+    uint32_t* dst = out + ((((int64_t)f * KB + blk) * 2 + part) * N1PAD + n) * 32 + ((ch ^ (n & 7)) << 2);
     *reinterpret_cast<uint4*>(dst) = make_uint4(v[0], v[1], v[2], v[3]);
   }
 }
@@ -84,39 +86,41 @@ __global__ void __launch_bounds__(256) tower_pack_w1t_kernel(const float* __rest
 template <int KB>
 __global__ void __launch_bounds__(TF_THREADS, 1) tower_fwd_kernel(const TowerFwdParams P) {
   constexpr int K = 32 * KB;
-  constexpr int CPR = 8 * KB;              // 16-byte chunks per embedding row
-  constexpr int RPP = TF_PRODUCERS / CPR;  // rows covered by one pass of the producer threads
-  constexpr int R = TF_ROWS / RPP;         // rows per producer thread
-  constexpr uint32_t XT = KB * 16384u;     // bytes of one [128 x k] tile
+  constexpr int R = 4;                  // rows per producer thread: rg + 32 i, 16-byte chunk c8 of every 32-column block
+  constexpr uint32_t XT = KB * 16384u;  // bytes of one [128 x k] tile: KB blocks of [128 rows x 128 B]
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t WB = 2u * KB * (uint32_t)P.N1PAD * 128u;  // bytes of one W1 field image (hi + lo)
-  const uint32_t x_lo = base + TF_STAGES * XT;
-  const uint32_t w_base = x_lo + XT;
-  const uint32_t scal_base = w_base + TF_STAGES * WB;      // [stage][128] float2
+  const uint32_t WB = 2u * KB * (uint32_t)P.N1PAD * 128u;  // bytes of one W1 field image: per block [hi rows | lo rows]
+  const uint32_t lo_base = base + TF_STAGES * XT;          // 2 remainder ("lo") tiles of one 32-column block each
+  const uint32_t w_base = lo_base + 2u * 16384u;
+  const uint32_t scal_base = w_base + TF_WSLOTS * WB;      // [stage][128] float2
   const uint32_t rowidx_base = scal_base + TF_STAGES * 1024u;
   const uint32_t w1d_base = rowidx_base + (((uint32_t)TF_ROWS * P.m * 4u + 15u) & ~15u);
   const uint32_t b1_base = w1d_base + (uint32_t)P.nd * P.N1PAD * 4u;
   const uint32_t rowsum_base = b1_base + (uint32_t)P.N1PAD * 4u;  // [128] second-order terms
   const uint32_t bar_base = (rowsum_base + TF_ROWS * 4u + 7u) & ~7u;
-  auto full = [&](int s) { return bar_base + 8u * s; };
+  auto empty = [&](int s) { return bar_base + 8u * s; };
   auto wfull = [&](int s) { return bar_base + 8u * (TF_STAGES + s); };
-  auto empty = [&](int s) { return bar_base + 8u * (2 * TF_STAGES + s); };
-  const uint32_t lo_free = bar_base + 8u * (3 * TF_STAGES);
-  const uint32_t accum_full = bar_base + 8u * (3 * TF_STAGES + 1);
-  const uint32_t tmem_slot = bar_base + 8u * (3 * TF_STAGES + 2);
+  auto wempty = [&](int s) { return bar_base + 8u * (TF_STAGES + TF_WSLOTS + s); };
+  auto lo_ready = [&](int s) { return bar_base + 8u * (TF_STAGES + 2 * TF_WSLOTS + s); };
+  auto lo_free = [&](int s) { return bar_base + 8u * (TF_STAGES + 2 * TF_WSLOTS + 2 + s); };
+  const uint32_t accum_full = bar_base + 8u * (TF_STAGES + 2 * TF_WSLOTS + 4);
+  const uint32_t tmem_slot = accum_full + 8u;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t b0 = (int64_t)blockIdx.x * TF_ROWS;
   const int m = P.m;
 
   if (tid == 0) {
-    for (int s = 0; s < TF_STAGES; ++s) {
-      mbar_init(full(s), TF_PRODUCERS);
+    for (int s = 0; s < TF_STAGES; ++s) mbar_init(empty(s), 1);
+    for (int s = 0; s < TF_WSLOTS; ++s) {
       mbar_init(wfull(s), 1);
-      mbar_init(empty(s), 1);
+      mbar_init(wempty(s), 1);
     }
-    mbar_init(lo_free, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(lo_ready(s), TF_PRODUCERS);
+      mbar_init(lo_free(s), 1);
+    }
     mbar_init(accum_full, 1);
     fence_barrier_init();
   }
@@ -149,11 +153,13 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tower_fwd_kernel(const TowerFwd
 
   if (warp < 8) {
     // ================================================================== producers
-    const int c = tid % CPR, rg = tid / CPR;
-    const uint32_t dst0 = (uint32_t)(c >> 3) * 16384u + (uint32_t)rg * 128u + ((uint32_t)((c & 7) ^ (rg & 7)) << 4);
-    float4 S[R], Q[R];
+    const int c8 = tid & 7, rg = tid >> 3;  // rows rg + 32 i: (row & 7) == (rg & 7) for every i
+    const uint32_t dst0 = (uint32_t)rg * 128u + ((uint32_t)(c8 ^ (rg & 7)) << 4);
+    float4 S[KB][R], Q[KB][R];
 #pragma unroll
-    for (int i = 0; i < R; ++i) S[i] = Q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int blk = 0; blk < KB; ++blk)
+#pragma unroll
+      for (int i = 0; i < R; ++i) S[blk][i] = Q[blk][i] = make_float4(0.f, 0.f, 0.f, 0.f);
     float bias_acc = 0.f, lin_acc = 0.f;  // threads 0..127: row tid
 
     auto issue = [&](int f) {
@@ -162,10 +168,13 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tower_fwd_kernel(const TowerFwd
       const uint32_t xs = base + (uint32_t)s * XT + dst0;
 #pragma unroll
       for (int i = 0; i < R; ++i) {
-        const int r = rg + RPP * i;
+        const int r = rg + 32 * i;
         const uint32_t row = lds32(rowidx_base + 4u * (uint32_t)(r * m + f));
         const bool live = row != TW_NONE;
-        cp_async16(xs + (uint32_t)i * (RPP * 128u), P.table + (int64_t)(live ? row : 0u) * K + 4 * c, live ? 16u : 0u);
+        const float* src = P.table + (int64_t)(live ? row : 0u) * K + 4 * c8;
+#pragma unroll
+        for (int blk = 0; blk < KB; ++blk)
+          cp_async16(xs + (uint32_t)blk * 16384u + (uint32_t)i * 4096u, src + 32 * blk, live ? 16u : 0u);
       }
       if (P.scal && tid < TF_ROWS) {
         const uint32_t row = lds32(rowidx_base + 4u * (uint32_t)(tid * m + f));
@@ -178,29 +187,36 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tower_fwd_kernel(const TowerFwd
       issue(f);
       cp_async_commit();
     }
+    int t = 0;  // 32-column blocks handed to the tensor core so far
     for (int f = 0; f < m; ++f) {
       cp_async_wait<TF_DEPTH - 1>();  // all but the newest TF_DEPTH-1 groups: field f has landed (this thread's chunks)
-      if (f > 0) ok = ok && mbar_wait(lo_free, ((uint32_t)(f - 1)) & 1u);
       const int s = f % TF_STAGES;
-      const uint32_t xs = base + (uint32_t)s * XT + dst0;
 #pragma unroll
-      for (int i = 0; i < R; ++i) {
-        const float4 v = lds128(xs + (uint32_t)i * (RPP * 128u));
-        S[i].x += v.x; S[i].y += v.y; S[i].z += v.z; S[i].w += v.w;
-        Q[i].x += v.x * v.x; Q[i].y += v.y * v.y; Q[i].z += v.z * v.z; Q[i].w += v.w * v.w;
-        sts128(x_lo + dst0 + (uint32_t)i * (RPP * 128u), trunc_lo4(v));
-        if (P.x) {
-          const int64_t b = b0 + rg + RPP * i;
-          if (b < P.B) st4(P.x + b * P.ld + (int64_t)f * K + 4 * c, v);
+      for (int blk = 0; blk < KB; ++blk, ++t) {
+        // the remainder tile alternates between two buffers: block t+1 is prepared while the MMAs of block t run
+        const int ls = t & 1;
+        ok = ok && mbar_wait(lo_free(ls), (((uint32_t)(t >> 1)) & 1u) ^ 1u);
+        const uint32_t xs = base + (uint32_t)s * XT + (uint32_t)blk * 16384u + dst0;
+        const uint32_t ld = lo_base + (uint32_t)ls * 16384u + dst0;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          const float4 v = lds128(xs + (uint32_t)i * 4096u);
+          S[blk][i].x += v.x; S[blk][i].y += v.y; S[blk][i].z += v.z; S[blk][i].w += v.w;
+          Q[blk][i].x += v.x * v.x; Q[blk][i].y += v.y * v.y; Q[blk][i].z += v.z * v.z; Q[blk][i].w += v.w * v.w;
+          sts128(ld + (uint32_t)i * 4096u, trunc_lo4(v));
+          if (P.x) {
+            const int64_t b = b0 + rg + 32 * i;
+            if (b < P.B) st4(P.x + b * P.ld + (int64_t)f * K + 32 * blk + 4 * c8, v);
+          }
         }
+        fence_proxy_async_smem();
+        mbar_arrive(lo_ready(ls));
       }
       if (P.scal && tid < TF_ROWS) {
         const float2 sv = lds64f(scal_base + (uint32_t)s * 1024u + 8u * tid);
         bias_acc += sv.x;
         lin_acc += sv.y;
       }
-      fence_proxy_async_smem();
-      mbar_arrive(full(s));
       if (f + TF_DEPTH < m) issue(f + TF_DEPTH);
       cp_async_commit();  // one (possibly empty) group per field keeps the wait count uniform
     }
@@ -208,13 +224,21 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tower_fwd_kernel(const TowerFwd
     // ---- FM second order, field sums, first-order logits
 #pragma unroll
     for (int i = 0; i < R; ++i) {
-      float second = 0.5f * (S[i].x * S[i].x - Q[i].x) + 0.5f * (S[i].y * S[i].y - Q[i].y) +
-                     0.5f * (S[i].z * S[i].z - Q[i].z) + 0.5f * (S[i].w * S[i].w - Q[i].w);
-      second = group_sum<CPR>(second);
-      const int r = rg + RPP * i;
-      if (c == 0) sts32(rowsum_base + 4u * r, __float_as_uint(second));
+      float second = 0.f;
+#pragma unroll
+      for (int blk = 0; blk < KB; ++blk) {
+        const float4 s4 = S[blk][i], q4 = Q[blk][i];
+        second += 0.5f * (s4.x * s4.x - q4.x) + 0.5f * (s4.y * s4.y - q4.y) + 0.5f * (s4.z * s4.z - q4.z) +
+                  0.5f * (s4.w * s4.w - q4.w);
+      }
+      second = group_sum<8>(second);
+      const int r = rg + 32 * i;
+      if (c8 == 0) sts32(rowsum_base + 4u * r, __float_as_uint(second));
       const int64_t b = b0 + r;
-      if (P.sum_out && b < P.B) st4(P.sum_out + b * K + 4 * c, S[i]);
+      if (P.sum_out && b < P.B) {
+#pragma unroll
+        for (int blk = 0; blk < KB; ++blk) st4(P.sum_out + b * K + 32 * blk + 4 * c8, S[blk][i]);
+      }
     }
     named_bar_sync(1, TF_PRODUCERS);
     if (tid < TF_ROWS) {
@@ -242,11 +266,14 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tower_fwd_kernel(const TowerFwd
 #pragma unroll
       for (int j = 0; j < 16; ++j) acc[j] = 0.f;
       for (int a = 0; a < nacc; ++a) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(a * P.N1PAD + 16 * cc), v);
+        // an accumulator is [a_hi*w_hi + a_lo*w_hi | a_hi*w_lo]: columns n and N1PAD + n belong together
+        uint32_t v[16], w[16];
+        const uint32_t ta = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(a * 2 * P.N1PAD + 16 * cc);
+        tmem_ld16(ta, v);
+        tmem_ld16(ta + (uint32_t)P.N1PAD, w);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(v[j]);
+        for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(v[j]) + __uint_as_float(w[j]);
       }
       if (b < P.B) {
 #pragma unroll
@@ -267,33 +294,34 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tower_fwd_kernel(const TowerFwd
   } else if (warp == 8) {
     // ================================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(128, P.N1PAD);
-      const uint32_t nrow = (uint32_t)P.N1PAD * 128u;
+      const uint32_t idesc_wide = umma_idesc_tf32(128, 2 * P.N1PAD);  // a_hi x [w_hi | w_lo]
+      const uint32_t idesc_hi = umma_idesc_tf32(128, P.N1PAD);        // a_lo x w_hi
+      const uint32_t wblk = 2u * (uint32_t)P.N1PAD * 128u;            // one block of a field image: hi rows, lo rows
+      int t = 0;
       for (int f = 0; f < m; ++f) {
-        const int s = f % TF_STAGES;
-        const uint32_t par = ((uint32_t)(f / TF_STAGES)) & 1u;
-        ok = ok && mbar_wait(full(s), par);
-        ok = ok && mbar_wait(wfull(s), par);
-        tc_fence_after();
-        const uint32_t acc = tmem_base + (uint32_t)((f % P.NACC) * P.N1PAD);
+        const int s = f % TF_STAGES, ws = f % TF_WSLOTS;
+        ok = ok && mbar_wait(wfull(ws), ((uint32_t)(f / TF_WSLOTS)) & 1u);
+        const uint32_t acc = tmem_base + (uint32_t)((f % P.NACC) * 2 * P.N1PAD);
         const uint32_t xa = base + (uint32_t)s * XT;
-        const uint32_t wa = w_base + (uint32_t)s * WB;
+        const uint32_t wa = w_base + (uint32_t)ws * WB;
 #pragma unroll
-        for (int blk = 0; blk < KB; ++blk) {
+        for (int blk = 0; blk < KB; ++blk, ++t) {
+          const int ls = t & 1;
+          ok = ok && mbar_wait(lo_ready(ls), ((uint32_t)(t >> 1)) & 1u);  // block landed (all producers) + remainder tile
+          tc_fence_after();
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t off = (uint32_t)blk * 16384u + (uint32_t)ks * 32u;
-            const uint32_t woff = (uint32_t)blk * nrow + (uint32_t)ks * 32u;
-            const uint64_t a_hi = umma_desc(xa + off), a_lo = umma_desc(x_lo + off);
-            const uint64_t b_hi = umma_desc(wa + woff), b_lo = umma_desc(wa + KB * nrow + woff);
+            const uint64_t a_hi = umma_desc(xa + (uint32_t)blk * 16384u + (uint32_t)ks * 32u);
+            const uint64_t a_lo = umma_desc(lo_base + (uint32_t)ls * 16384u + (uint32_t)ks * 32u);
+            const uint64_t b_w = umma_desc(wa + (uint32_t)blk * wblk + (uint32_t)ks * 32u);
             const uint32_t accumulate = (f >= P.NACC || blk > 0 || ks > 0) ? 1u : 0u;
-            umma_tf32(acc, a_hi, b_hi, idesc, accumulate);
-            umma_tf32(acc, a_lo, b_hi, idesc, 1u);
-            umma_tf32(acc, a_hi, b_lo, idesc, 1u);
+            umma_tf32(acc, a_hi, b_w, idesc_wide, accumulate);
+            umma_tf32(acc, a_lo, b_w, idesc_hi, 1u);
           }
+          umma_commit(lo_free(ls));
         }
         umma_commit(empty(s));
-        umma_commit(lo_free);
+        umma_commit(wempty(ws));
       }
       umma_commit(accum_full);
     }
@@ -301,10 +329,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tower_fwd_kernel(const TowerFwd
     // ================================================================== W1 image loader
     if (lane == 0) {
       for (int f = 0; f < m; ++f) {
-        const int s = f % TF_STAGES;
-        ok = ok && mbar_wait(empty(s), (((uint32_t)(f / TF_STAGES)) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(wfull(s), WB);
-        bulk_g2s(w_base + (uint32_t)s * WB, P.wpack + (size_t)f * (WB / 4), WB, wfull(s));
+        const int ws = f % TF_WSLOTS;
+        ok = ok && mbar_wait(wempty(ws), (((uint32_t)(f / TF_WSLOTS)) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(wfull(ws), WB);
+        bulk_g2s(w_base + (uint32_t)ws * WB, P.wpack + (size_t)f * (WB / 4), WB, wfull(ws));
       }
     }
   }
@@ -321,10 +349,10 @@ static size_t tower_fwd_smem(int KB, int m, int nd, int N1PAD) {
   const size_t XT = (size_t)KB * 16384;
   const size_t WB = 2 * (size_t)KB * N1PAD * 128;
   size_t s = 1024;  // alignment slack
-  s += (TF_STAGES + 1) * XT + TF_STAGES * WB + TF_STAGES * 1024;
+  s += TF_STAGES * XT + 2 * 16384 + TF_WSLOTS * WB + TF_STAGES * 1024;
   s += ((size_t)TF_ROWS * m * 4 + 15) & ~(size_t)15;
   s += (size_t)nd * N1PAD * 4 + (size_t)N1PAD * 4 + TF_ROWS * 4 + 8;
-  s += 8 * (3 * TF_STAGES + 3);
+  s += 8 * (TF_STAGES + 2 * TF_WSLOTS + 6);
   return s;
 }
 
@@ -376,11 +404,11 @@ int rm_tower_fwd(const float* table, const float* scal, const int64_t* table_off
   P.lin_dense_stride = lin_dense_stride; P.wpack = wpack; P.W1 = W1; P.b1 = b1; P.x = x; P.ld = ld; P.y1 = y1;
   P.fm_out = fm_out; P.lin_out = lin_out; P.sum_out = sum_out; P.status = status; P.B = B; P.m = m; P.nd = n_dense;
   P.N1 = N1; P.N1PAD = N1PAD;
-  int nacc = 512 / N1PAD;
+  int nacc = 512 / (2 * N1PAD);  // an accumulator is 2*N1PAD columns wide: [.. x w_hi | .. x w_lo]
   if (nacc > 8) nacc = 8;
   P.NACC = nacc;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(nacc * N1PAD)) cols <<= 1;
+  while (cols < (uint32_t)(nacc * 2 * N1PAD)) cols <<= 1;
   P.tmem_cols = cols;
   const size_t smem = tower_fwd_smem(KB, m, n_dense, N1PAD);
   const int grid = (int)ceil_div(B, TF_ROWS);
