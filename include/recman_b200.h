@@ -387,6 +387,28 @@ int rm_tower_bwd_update(float* table, float* scal, const uint32_t* sorted_keys,
                         int64_t B, int32_t m, int32_t k, int32_t N1, int32_t unit, int32_t opt,
                         float lr, float l2, float* dW1, float* out_rows, float* out_scal,
                         int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+/* ------------------------------------------------------------------------- *
+ * H   fused DeepFM head: everything between the first DNN layer's pre-activation y1 and
+ *     the loss, forward and backward, for hidden_units = (32, 32).
+ * replaces: the rest of DNN.__call__ layers.py:589-609 (activation, second matmul,
+ *     output projection), the add_n of the towers tf/core/DeepFM.py:150-160,
+ *     PredictionLayer layers.py:796-808, create_loss utils.py:192-198 (Keras BCE with
+ *     clip eps = 1e-7, or MSE) and TF's autodiff of all of it.
+ * logit = lin + w0 + fm + dnn(y1); pred = sigmoid(logit) (task 0) or logit (task 1).
+ * labels == NULL: forward only (logit / pred, nullable).  Otherwise also loss[1] (batch
+ * mean), g[B] = grad_scale * dL/dlogit (the FM and first-order gradient), g1[B,32] =
+ * grad_scale * dL/dy1, dW2[32,32], db2[32], dw3[32], dscal[1] (= db3 = dw0), db1[32].
+ * Batch reductions are CTA partials added in CTA order: run-to-run identical.
+ * ------------------------------------------------------------------------- */
+int rm_deepfm_head_supported(int32_t N1, int32_t N2);
+size_t rm_deepfm_head_workspace_bytes(int64_t B);
+int rm_deepfm_head(const float* y1, const float* fm, const float* lin, const float* w0,
+                   const float* W2, const float* b2, const float* w3, const float* b3,
+                   const float* labels, int64_t B, int32_t N1, int32_t N2, int32_t act,
+                   int32_t task, float grad_scale, float* logit, float* pred, float* loss,
+                   float* g1, float* g, float* dW2, float* db2, float* dw3, float* dscal,
+                   float* db1, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Test-only: D[128,32] = At^T @ Bt (At [K,128], Bt [K,32]) through the MN-major SWIZZLE_128B
  * operand layout of the tower backward's weight-gradient GEMM (variant 0 = the layout used). */
 int rm_umma_probe(const float* At, const float* Bt, int32_t K, int32_t variant, float* D,

@@ -496,3 +496,28 @@ class TowerFunction(Function):
         if g_lin is not None:
             attach_sparse_grad(ctx.W_lin, ops.SparseGrad(plan.uniq_rows, ol, plan.n_unique))
         return (None, None, None, None, None, dW1, db1) + (None,) * 6
+
+
+class HeadFunction(Function):
+    """DeepFM head in one kernel (rm_deepfm_head): (y1, fm, lin, w0, W2, b2, w3, b3, labels) -> (loss, logit, pred).
+
+    The kernel computes the loss AND every gradient in the same pass; ``backward`` only scales them by the incoming
+    gradient of the loss (a scalar)."""
+
+    @staticmethod
+    def forward(ctx, y1, fm, lin, w0, W2, b2, w3, b3, labels, act, task):
+        out = ops.deepfm_head(y1.contiguous(), fm.reshape(-1).contiguous(), lin.reshape(-1).contiguous(), w0, W2, b2,
+                              w3.reshape(-1).contiguous(), b3, labels, act, task)
+        ctx.out = out
+        ctx.w3_shape = w3.shape
+        ctx.fm_shape, ctx.lin_shape = fm.shape, lin.shape
+        ctx.mark_non_differentiable(out["logit"], out["pred"])
+        return out["loss"].reshape(()), out["logit"], out["pred"]
+
+    @staticmethod
+    def backward(ctx, gloss, _glogit, _gpred):
+        o, ctx.out = ctx.out, None
+        g = o["g"] * gloss
+        ds = o["dscal"] * gloss
+        return (o["g1"].mul_(gloss), g.reshape(ctx.fm_shape), g.reshape(ctx.lin_shape), ds, o["dW2"] * gloss,
+                o["db2"] * gloss, (o["dw3"] * gloss).reshape(ctx.w3_shape), ds, None, None, None)

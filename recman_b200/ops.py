@@ -748,3 +748,36 @@ def umma_probe(At, Bt, variant: int = 0):
     st = new_status(At.device)
     _C.call("rm_umma_probe", _p(At), _p(Bt), K, variant, _p(D), _p(st), _stream())
     return D, st
+
+
+# --------------------------------------------------------------------------- #
+# H  fused DeepFM head (second DNN layer .. loss, forward + backward in one kernel)
+# --------------------------------------------------------------------------- #
+def deepfm_head_supported(N1: int, N2: int) -> bool:
+    return bool(_C.lib.rm_deepfm_head_supported(int(N1), int(N2)))
+
+
+def deepfm_head(y1, fm, lin, w0, W2, b2, w3, b3, labels, act: int, task: int, grad_scale: float = 1.0):
+    """labels None: forward only -> (logit, pred).  Otherwise -> dict with logit, pred, loss [1] and the gradients
+    g1 [B,N1], g [B], dW2, db2, dw3, dscal [1] (= db3 = dw0), db1 - all scaled by ``grad_scale``."""
+    _dev_check(y1)
+    B, N1 = y1.shape
+    N2 = W2.shape[1]
+    dev = y1.device
+    f = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+    for t in (y1, fm, lin, W2, b2, w3, b3):
+        assert t.is_contiguous() and t.dtype == torch.float32
+    logit, pred = f(B), f(B)
+    if labels is None:
+        _C.call("rm_deepfm_head", _p(y1), _p(fm), _p(lin), _p(w0), _p(W2), _p(b2), _p(w3), _p(b3), None, B, N1, N2, act,
+                task, 1.0, _p(logit), _p(pred), None, None, None, None, None, None, None, None, None, 0, _stream())
+        return logit, pred
+    labels = labels.to(torch.float32).contiguous()
+    out = dict(logit=logit, pred=pred, loss=f(1), g1=f(B, N1), g=f(B), dW2=f(N1, N2), db2=f(N2), dw3=f(N2), dscal=f(1),
+               db1=f(N1))
+    ws_bytes = _C.lib.rm_deepfm_head_workspace_bytes(B)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _C.call("rm_deepfm_head", _p(y1), _p(fm), _p(lin), _p(w0), _p(W2), _p(b2), _p(w3), _p(b3), _p(labels), B, N1, N2, act,
+            task, float(grad_scale), _p(logit), _p(pred), _p(out["loss"]), _p(out["g1"]), _p(out["g"]), _p(out["dW2"]),
+            _p(out["db2"]), _p(out["dw3"]), _p(out["dscal"]), _p(out["db1"]), _p(ws), ws_bytes, _stream())
+    return out

@@ -56,8 +56,67 @@ class DeepFM(DeepModel):
         self.use_deep = use_deep
         self.loss_type = loss_type
 
-    def _out(self, inputs: DataInputs, training=True):
+    def _tower_layers(self, inputs, training):
+        """The layers of the fused tower path and its raw outputs (y1, fm, lin without w0), or None when the model /
+        hyper-parameters are outside what the fused kernels cover."""
         hp = self.hparams
+        fm_dropout = hp["fm_dropout"] if training else (1.0,) * len(hp["fm_dropout"])
+        if not (self.use_fm and self.use_deep and all(p >= 1 for p in fm_dropout)
+                and (not training or hp["deep_dropout"][0] >= 1)):
+            return None
+        self.embeddings = self._embedding_layer(use_bias=True, l2_mode=hp["embedding_l2_mode"])
+        linear_feats = list(self.feat_dict.values())
+        fused_feats = self.feat_dict.sparse_feats + self.feat_dict.dense_feats
+        self.linear = LinearLayer(self.variables, fused_feats if len(fused_feats) == len(linear_feats) else linear_feats,
+                                  hp["linear_l2_reg"], training=training)
+        self.dnn = DNN(self.variables, hp["deep_hidden_units"],
+                       hp["deep_dropout"] if training else (1.0,) * len(hp["deep_dropout"]),
+                       hp["deep_activation"], hp["deep_l2_reg"])
+        self.dnn.training = training
+        return self._tower_front_end(self.embeddings, self.linear, self.dnn, inputs, training, add_w0=False)
+
+    def _head_args(self, training):
+        """(w0, W2, b2, w3, b3, act kind) when everything after the first DNN layer fits the fused head kernel:
+        two hidden layers of 32, identity / relu / leaky_relu, no dropout."""
+        from .. import _C, ops
+        from .layers import activation_kind
+
+        if not self.hparams.get("fused_head", True):
+            return None
+        hu = self.dnn.hidden_units
+        if len(hu) != 2 or not ops.deepfm_head_supported(int(hu[0]), int(hu[1])):
+            return None
+        if training and any(p < 1 for p in self.hparams["deep_dropout"][1:]):
+            return None
+        try:
+            act = activation_kind(self.hparams["deep_activation"])
+        except ValueError:
+            return None
+        v, p = self.variables, self.dnn.prefix
+        return (v[f"{self.linear.prefix}linear_w0"], v[f"{p}dnn_layer_1_weights"], v[f"{p}dnn_layer_1_bias"],
+                v[f"{p}dnn_w"], v[f"{p}dnn_w0"], act)
+
+    def _out(self, inputs: DataInputs, training=True, _tower=None):
+        hp = self.hparams
+        tower = _tower if _tower is not None else self._tower_layers(inputs, training)
+        if tower is not None:
+            # one kernel: gather + FM + first-order + first DNN layer (tcgen05); the row buffer is never written
+            y1, fm_logit, lin_raw = tower
+            head = self._head_args(training)
+            if head is not None and not torch.is_grad_enabled():
+                from .. import ops
+
+                w0, W2, b2, w3, b3, act = head
+                logit, pred = ops.deepfm_head(y1, fm_logit.reshape(-1), lin_raw.reshape(-1), w0.data, W2.data, b2.data,
+                                              w3.data.reshape(-1), b3.data, None, act,
+                                              0 if self.task == "classification" else 1)
+                self.final_logit = logit.reshape(-1, 1)
+                return pred
+            linear_logit = lin_raw + self.variables[f"{self.linear.prefix}linear_w0"]
+            final_logit = linear_logit + fm_logit + self.dnn.from_first_layer(y1)
+            self.final_logit = final_logit.detach()
+            return PredictionLayer(self.variables, self.task, use_bias=False)(final_logit)
+
         self.embeddings = self._embedding_layer(use_bias=True, l2_mode=hp["embedding_l2_mode"])
         linear_feats = list(self.feat_dict.values())  # LinearCombiner(self.feat_dict), DeepFM.py:122
         fused_feats = self.feat_dict.sparse_feats + self.feat_dict.dense_feats
@@ -65,20 +124,6 @@ class DeepFM(DeepModel):
                                   hp["linear_l2_reg"], training=training)
         fm_dropout = hp["fm_dropout"] if training else (1.0,) * len(hp["fm_dropout"])
         fm_identity = all(p >= 1 for p in fm_dropout)
-
-        tower = None
-        if self.use_fm and self.use_deep and fm_identity and (not training or hp["deep_dropout"][0] >= 1):
-            self.dnn = DNN(self.variables, hp["deep_hidden_units"],
-                           hp["deep_dropout"] if training else (1.0,) * len(hp["deep_dropout"]),
-                           hp["deep_activation"], hp["deep_l2_reg"])
-            self.dnn.training = training
-            tower = self._tower_front_end(self.embeddings, self.linear, self.dnn, inputs, training)
-        if tower is not None:
-            # one kernel: gather + FM + first-order + first DNN layer (tcgen05); the row buffer is never written
-            y1, fm_logit, linear_logit = tower
-            final_logit = linear_logit + fm_logit + self.dnn.from_first_layer(y1)
-            self.final_logit = final_logit.detach()
-            return PredictionLayer(self.variables, self.task, use_bias=False)(final_logit)
 
         # FM dropout (a legal reference hyper-parameter, DeepFM.py:36) needs the [B,m,k] block and the bias block
         # before the reduction: the unfused layers handle it
@@ -119,9 +164,34 @@ class DeepFM(DeepModel):
         self.final_logit = final_logit.detach()  # detached: keeping the graph alive would pin its grad accumulators
         return PredictionLayer(self.variables, self.task, use_bias=False)(final_logit)
 
+    def _l2_terms(self):
+        hp = self.hparams
+        terms = []
+        if self.embeddings.l2_reg:
+            terms.append(self.embeddings.l2())
+        if self.linear.l2_reg:
+            terms.append(self.linear.l2())
+        if self.use_deep and self.dnn is not None and self.dnn.l2_reg:
+            terms.append(self.dnn.l2())
+        return terms
+
     def _loss(self, inputs):
-        loss = create_loss(inputs.y, self._out(inputs), task=self.task)
-        loss = loss + self.embeddings.l2() + self.linear.l2()
-        if self.use_deep:
-            loss = loss + self.dnn.l2()
+        tower = self._tower_layers(inputs, True) if torch.is_grad_enabled() else None
+        if tower is not None:
+            head = self._head_args(True)
+            if head is not None:
+                # second DNN layer .. loss, forward and backward, in one kernel
+                from ..autograd import HeadFunction
+
+                y1, fm_logit, lin_raw = tower
+                w0, W2, b2, w3, b3, act = head
+                loss, logit, _ = HeadFunction.apply(y1, fm_logit, lin_raw, w0, W2, b2, w3, b3, inputs.y, act,
+                                                    0 if self.task == "classification" else 1)
+                self.final_logit = logit.reshape(-1, 1)
+                for t in self._l2_terms():
+                    loss = loss + t
+                return loss
+        loss = create_loss(inputs.y, self._out(inputs, _tower=tower), task=self.task)
+        for t in self._l2_terms():
+            loss = loss + t
         return loss

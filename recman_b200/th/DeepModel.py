@@ -211,7 +211,8 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
         return rows, (fm if want_fm else None), (lin if linear is not None else None)
 
     # ------------------------------------------------------------------ fused DeepFM tower (front end + first DNN layer)
-    def _tower_front_end(self, layer: FeatEmbeddingLayer, linear: LinearLayer, dnn, inputs: DataInputs, training: bool):
+    def _tower_front_end(self, layer: FeatEmbeddingLayer, linear: LinearLayer, dnn, inputs: DataInputs, training: bool,
+                         add_w0: bool = True):
         """One kernel for gather + FM + first-order term + the first DNN layer (``rm_tower_fwd``), and - inside a
         training step whose update can be fused - one sorted pass for the whole sparse backward + optimizer
         (``rm_tower_bwd_update``).  Returns (y1 pre-activation, fm_logit, lin_logit) or None when not eligible:
@@ -264,7 +265,8 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
 
         y1, fm, lin = TowerFunction.apply(table, scal, scal_fwd, bias_param, W_lin, W1, b1, lay.runs[0].offsets, total,
                                           self._status(), inputs.sparse_ids, dense, fused)
-        lin = lin + self.variables[f"{linear.prefix}linear_w0"]
+        if add_w0:
+            lin = lin + self.variables[f"{linear.prefix}linear_w0"]
         return y1, fm, lin
 
     # ------------------------------------------------------------------ reference API

@@ -271,3 +271,51 @@ def test_tower_backward_drops_out_of_range_ids():
     touched2[rows_real[keep]] = True
     assert torch.equal(t1.cpu()[~touched2], s["table"][~touched2])
     assert torch.isfinite(t1).all()
+
+
+@pytest.mark.parametrize("act", ["relu", "leaky_relu", "identity"])
+@pytest.mark.parametrize("task", ["classification", "regression"])
+@pytest.mark.parametrize("B", [1, 300, 4097])
+def test_deepfm_head_forward_backward(act, task, B):
+    """rm_deepfm_head: second DNN layer .. loss and every gradient against fp64 autograd over the oracle's layers."""
+    from recman_b200 import _C
+
+    ops = _ops()
+    g = torch.Generator().manual_seed(B)
+    N = 32
+    y1 = torch.randn(B, N, generator=g)
+    fm = torch.randn(B, generator=g) * 0.3
+    lin = torch.randn(B, generator=g) * 0.3
+    w0 = torch.randn(1, generator=g) * 0.1
+    W2 = torch.randn(N, N, generator=g) * 0.2
+    b2 = torch.randn(N, generator=g) * 0.1
+    w3 = torch.randn(N, 1, generator=g) * 0.2
+    b3 = torch.randn(1, generator=g) * 0.1
+    y = (torch.rand(B, generator=g) < 0.3).float() if task == "classification" else torch.randn(B, generator=g)
+    leaf = lambda t: t.double().clone().requires_grad_()
+    Y1, FM, LIN, W0, W2d, B2, W3, B3 = map(leaf, (y1, fm, lin, w0, W2, b2, w3, b3))
+    fn = {"relu": oracle.relu, "leaky_relu": oracle.leaky_relu_tf, "identity": (lambda t: t)}[act]
+    h2 = fn(fn(Y1) @ W2d + B2)
+    logit = (LIN + W0 + FM).reshape(-1, 1) + (h2 @ W3 + B3)
+    pred = oracle.prediction(logit, task)
+    loss = oracle.create_loss(y.double(), pred, task)
+    loss.backward()
+    out = ops.deepfm_head(y1.cuda(), fm.cuda(), lin.cuda(), w0.cuda(), W2.cuda(), b2.cuda(), w3.reshape(-1).cuda(),
+                          b3.cuda(), y.cuda(), _C.ACT_KINDS[act], 0 if task == "classification" else 1)
+    torch.cuda.synchronize()
+    assert_close(out["logit"], logit.detach().reshape(-1), atol_scale=2e-6, msg="logit")
+    assert_close(out["pred"], pred.detach().reshape(-1), atol_scale=2e-6, msg="pred")
+    assert_close(out["loss"], loss.detach().reshape(1), atol_scale=2e-6, msg="loss")
+    for name, got, exp in [("g1", out["g1"], Y1.grad), ("g", out["g"], FM.grad), ("g(lin)", out["g"], LIN.grad),
+                           ("dW2", out["dW2"], W2d.grad), ("db2", out["db2"], B2.grad),
+                           ("dw3", out["dw3"], W3.grad.reshape(-1)), ("db3", out["dscal"], B3.grad),
+                           ("dw0", out["dscal"], W0.grad), ("db1", out["db1"], Y1.grad.sum(0))]:
+        assert_close(got, exp, atol_scale=1e-5, msg=name)
+    # forward only, and run-to-run identical reductions
+    lg, pr = ops.deepfm_head(y1.cuda(), fm.cuda(), lin.cuda(), w0.cuda(), W2.cuda(), b2.cuda(), w3.reshape(-1).cuda(),
+                             b3.cuda(), None, _C.ACT_KINDS[act], 0 if task == "classification" else 1)
+    assert torch.equal(lg, out["logit"]) and torch.equal(pr, out["pred"])
+    out2 = ops.deepfm_head(y1.cuda(), fm.cuda(), lin.cuda(), w0.cuda(), W2.cuda(), b2.cuda(), w3.reshape(-1).cuda(),
+                           b3.cuda(), y.cuda(), _C.ACT_KINDS[act], 0 if task == "classification" else 1)
+    for k in out:
+        assert torch.equal(out[k], out2[k]), k
