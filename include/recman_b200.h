@@ -14,8 +14,10 @@
  *   - every pointer is a DEVICE pointer unless its comment says "host";
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
  *   - the caller owns every buffer including workspaces (`*_workspace_bytes`
- *     queries); no hidden allocation, no hidden synchronisation, no global
- *     mutable state -> thread-safe per (stream, workspace);
+ *     queries); no hidden allocation, no hidden synchronisation, no environment
+ *     variables, no mutable state that results depend on (the library keeps a
+ *     launch counter and per-kernel "shared-memory opt-in done" flags) ->
+ *     thread-safe per (stream, workspace);
  *   - return value: 0 = ok, >0 = cudaError_t, <0 = RM_E_* below;
  *     `rm_last_error()` returns a thread-local message for the last failure;
  *   - there is no CPU path and no other-architecture path: `rm_device_check`

@@ -13,11 +13,6 @@ static std::atomic<long long> g_launches{0};
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-int tune_variant(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
-
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -42,9 +37,6 @@ int rm_device_check(int device) {
                   prop.major, prop.minor);
     return RM_E_ARCH;
   }
-  // tuning run only: L2 sector-promotion granularity (32 / 64 / 128 bytes) for the k=1 random lookups
-  const int l2g = rm::tune_variant("RM_TUNE_L2_FETCH", 0);
-  if (l2g > 0) RM_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)l2g));
   return 0;
 }
 

@@ -404,7 +404,7 @@ int cin_dF_dbias(const float* dout, const float* pre, int64_t B, int N, int D, i
   if (G > 4 * RM_NUM_SMS) G = 4 * RM_NUM_SMS;
   if (G > B) G = B;
   if (G >= 1 && smem <= 200 * 1024) {
-    RM_CUDA(cudaFuncSetAttribute(cin_dF_dbias_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RM_SMEM_ATTR_ONCE(smem, cin_dF_dbias_kernel);
     cin_dF_dbias_kernel<<<(unsigned)G, 256, smem, st>>>(dout, pre, B, N, D, act, dF, scratch);
     RM_LAUNCH_CHECK();
     cin_dbias_final_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(scratch, (int)G, N, dbias);
@@ -425,7 +425,7 @@ int cin_fwd_simt(const float* x0, int64_t bs0, const float* xk, int64_t bsk, con
   RM_UNSUPPORTED(TB > 0, "embedding size D must be <= 128");
   const size_t smem = ((size_t)TB * (m + H) * D + CIN_BK * CIN_AS + CIN_BK * CIN_BN) * sizeof(float);
   RM_UNSUPPORTED(smem <= 227 * 1024, "m + H too large for the shared-memory row cache");
-  RM_CUDA(cudaFuncSetAttribute(cin_fwd_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RM_SMEM_ATTR_ONCE(smem, cin_fwd_simt_kernel);
   dim3 grid((unsigned)ceil_div(B, TB), (unsigned)ceil_div(N, CIN_BN));
   cin_fwd_simt_kernel<<<grid, 256, smem, st>>>(x0, bs0, xk, bsk, W, bias, (int)B, m, H, D, N, act, TB, out, pre);
   RM_LAUNCH_CHECK();
@@ -467,7 +467,7 @@ int cin_bwd_simt(const float* x0, int64_t bs0, const float* xk, int64_t bsk, con
     const int rc = cin_dF_dbias(dout, pre, B, N, D, act, ws.dF, dbias, ws.partial, (size_t)ws.slabs * m * H * N, st);
     if (rc) return rc;
   }
-  RM_CUDA(cudaFuncSetAttribute(cin_bwd_dx_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RM_SMEM_ATTR_ONCE(smem, cin_bwd_dx_simt_kernel);
   cin_bwd_dx_simt_kernel<<<(unsigned)ceil_div(B, TB), 256, smem, st>>>(x0, bs0, xk, bsk, W, ws.dF, (int)B, m, H, D, N,
                                                                       TB, dx0, dxk, dbsk);
   RM_LAUNCH_CHECK();

@@ -276,10 +276,10 @@ size_t cin_tc_fwd_workspace(int64_t B, int m, int H, int D, int N, int precision
 template <int MP4>
 static int launch_tc(const TcParams& P, bool split3, int grid, size_t smem, cudaStream_t st) {
   if (split3) {
-    RM_CUDA(cudaFuncSetAttribute(cin_fwd_tc_kernel<MP4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RM_SMEM_ATTR_ONCE(smem, cin_fwd_tc_kernel<MP4, true>);
     cin_fwd_tc_kernel<MP4, true><<<grid, TC_THREADS, smem, st>>>(P);
   } else {
-    RM_CUDA(cudaFuncSetAttribute(cin_fwd_tc_kernel<MP4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RM_SMEM_ATTR_ONCE(smem, cin_fwd_tc_kernel<MP4, false>);
     cin_fwd_tc_kernel<MP4, false><<<grid, TC_THREADS, smem, st>>>(P);
   }
   RM_LAUNCH_CHECK();

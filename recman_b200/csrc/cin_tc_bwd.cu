@@ -533,8 +533,8 @@ static TbLayout tb_layout(int64_t B, int m, int H, int D, int N, int precision) 
   const int64_t Mrows = B * (int64_t)D;
   // slab size: 384..640 rows (the TMEM accumulation truncates, so slabs stay short), chosen so that the grid
   // n_ktiles x slabs fills whole waves of 148 CTAs (1 CTA / SM) and the per-CTA prologue/epilogue is amortised
-  L.slab_rows = tune_variant("RM_TUNE_CIN_SLAB", 0) / 32 * 32;
-  if (L.slab_rows <= 0) {
+  L.slab_rows = 0;
+  {
     double best = -1.0;
     for (int cand = 384; cand <= 640; cand += 32) {
       const int64_t slabs = (Mrows + cand - 1) / cand;
@@ -572,10 +572,10 @@ size_t cin_tc_bwd_workspace(int64_t B, int m, int H, int D, int N, int precision
 template <int MP4>
 static int launch_dx(const TbParams& P, bool split3, int grid, size_t smem, cudaStream_t st) {
   if (split3) {
-    RM_CUDA(cudaFuncSetAttribute(cin_bwd_dx_tc_kernel<MP4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RM_SMEM_ATTR_ONCE(smem, cin_bwd_dx_tc_kernel<MP4, true>);
     cin_bwd_dx_tc_kernel<MP4, true><<<grid, TB_THREADS, smem, st>>>(P);
   } else {
-    RM_CUDA(cudaFuncSetAttribute(cin_bwd_dx_tc_kernel<MP4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RM_SMEM_ATTR_ONCE(smem, cin_bwd_dx_tc_kernel<MP4, false>);
     cin_bwd_dx_tc_kernel<MP4, false><<<grid, TB_THREADS, smem, st>>>(P);
   }
   RM_LAUNCH_CHECK();
@@ -640,10 +640,10 @@ int cin_bwd_tc(const float* x0, int64_t bs0, const float* xk, int64_t bsk, const
     RM_UNSUPPORTED(max_xrows * (KS / 4) <= 3 * 256, "staged slice too large for the dW kernel's prefetch registers");
     dim3 grid((unsigned)L.n_ktiles, (unsigned)L.slabs);
     if (split3) {
-      RM_CUDA(cudaFuncSetAttribute(cin_bwd_dw_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      RM_SMEM_ATTR_ONCE(smem, cin_bwd_dw_tc_kernel<true>);
       cin_bwd_dw_tc_kernel<true><<<grid, TB_THREADS_B, smem, st>>>(P);
     } else {
-      RM_CUDA(cudaFuncSetAttribute(cin_bwd_dw_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      RM_SMEM_ATTR_ONCE(smem, cin_bwd_dw_tc_kernel<false>);
       cin_bwd_dw_tc_kernel<false><<<grid, TB_THREADS_B, smem, st>>>(P);
     }
     RM_LAUNCH_CHECK();

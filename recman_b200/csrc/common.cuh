@@ -13,8 +13,6 @@ namespace rm {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
-// kernel-variant override for tuning runs: integer value of environment variable `name`, else `dflt`
-int tune_variant(const char* name, int dflt);
 
 #define RM_CHECK_ARG(cond, msg)                                       \
   do {                                                                \
@@ -49,6 +47,17 @@ int tune_variant(const char* name, int dflt);
       rm::set_error("%s: kernel launch -> %s", __func__, cudaGetErrorString(e__));      \
       return (int)e__;                                                                  \
     }                                                                                   \
+  } while (0)
+
+// opt a kernel in to `bytes` of dynamic shared memory: once per call site (and template instantiation), raised only
+// when a larger size is requested - a launch-time constant, not a per-call driver round trip
+#define RM_SMEM_ATTR_ONCE(bytes, ...)                                                                       \
+  do {                                                                                                      \
+    static int smem_attr_set__ = 0;                                                                         \
+    if (smem_attr_set__ < (int)(bytes)) {                                                                   \
+      RM_CUDA(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      smem_attr_set__ = (int)(bytes);                                                                       \
+    }                                                                                                       \
   } while (0)
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

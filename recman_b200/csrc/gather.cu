@@ -223,14 +223,10 @@ static int launch_gather_fm(const float* table, const float* bias_table, const f
                             int32_t* status, cudaStream_t st) {
   const int groups_per_cta = 256 / LPR;
   const int grid = grid_for(B, groups_per_cta, 8);
-  const int variant = tune_variant("RM_TUNE_GATHER_FM", 1);
 #define RM_GFM(UU, MB)                                                                                              \
   gather_fm_kernel<LPR, UU, MB><<<grid, 256, 0, st>>>(table, bias_table, lin_table, offs, ids, dense, lin_dense,     \
                                                       n_dense, B, m, k, x, ld, fm_out, lin_out, sum_out, status)
-  if (variant == 0) RM_GFM(8, 2);
-  else if (variant == 2) RM_GFM(4, 3);
-  else if (variant == 3) RM_GFM(2, 6);
-  else RM_GFM(4, 4);
+  RM_GFM(4, 4);  // 4 rows in flight per lane, 4 CTAs / SM: the measured best of (8,2) (4,3) (2,6) (4,4) on B200
 #undef RM_GFM
   RM_LAUNCH_CHECK();
   return 0;

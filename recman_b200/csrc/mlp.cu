@@ -272,11 +272,11 @@ static int linear_dx_launch(const float* g, int64_t B, int32_t N, const float* W
   dim3 grid((unsigned)ceil_div(B, DX_BM), (unsigned)ceil_div(ceil_div(d_ld, DX_BN), DX_CT));
   if (N <= 32) {
     const size_t smem = (size_t)3 * 32 * DX_LD * sizeof(float);
-    RM_CUDA(cudaFuncSetAttribute(linear_dx_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RM_SMEM_ATTR_ONCE(smem, linear_dx_kernel<32>);
     linear_dx_kernel<32><<<grid, 256, smem, st>>>(g, B, N, W, d, dx, d_ld, fx, fx_ld, fS, fg, fk);
   } else {
     const size_t smem = (size_t)3 * 64 * DX_LD * sizeof(float);
-    RM_CUDA(cudaFuncSetAttribute(linear_dx_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RM_SMEM_ATTR_ONCE(smem, linear_dx_kernel<64>);
     linear_dx_kernel<64><<<grid, 256, smem, st>>>(g, B, N, W, d, dx, d_ld, fx, fx_ld, fS, fg, fk);
   }
   RM_LAUNCH_CHECK();
@@ -336,7 +336,7 @@ int rm_linear_bwd_weight(const float* x, int64_t ld, const float* g, int64_t B, 
   if (L.NT == 32) {
     linear_dw_kernel<32><<<grid, 128, smem, st>>>(x, ld, g, B, K, N, L.slab_rows, partial, L.Kpad);
   } else {
-    RM_CUDA(cudaFuncSetAttribute(linear_dw_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RM_SMEM_ATTR_ONCE(smem, linear_dw_kernel<64>);
     linear_dw_kernel<64><<<grid, 128, smem, st>>>(x, ld, g, B, K, N, L.slab_rows, partial, L.Kpad);
   }
   RM_LAUNCH_CHECK();

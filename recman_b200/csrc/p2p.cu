@@ -112,164 +112,6 @@ __global__ void __launch_bounds__(256, MINB) gather_fm_p2p_kernel(
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Deep-queue variant (experiment, opt-in).  NVLink reads have several times the latency of local HBM; if the
-// register-staged kernel above (64 B in flight per thread) were latency bound, more bytes in flight would help.  Here
-// every lane requests its 16-byte piece of FCH rows at once with cp.async (LDGSTS) into a PRIVATE shared-memory slot
-// and reads the same slot back itself after cp.async.wait_group - no registers are held by loads in flight, no
-// block-level synchronisation is needed, and two chunks (double buffer) x FCH rows x 16 B are in flight per thread.
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-template <int LPR, int FCH>
-__global__ void __launch_bounds__(256, 2) gather_fm_p2p_async_kernel(
-    const PeerTables pt, int wshift, const int64_t* __restrict__ feat_sizes, const int64_t* __restrict__ local_offs,
-    const int64_t* __restrict__ ids, const float* __restrict__ dense, const float* __restrict__ lin_dense, int n_dense,
-    int64_t B, int m, int k, float* __restrict__ x, int64_t ld, float* __restrict__ fm_out, float* __restrict__ lin_out,
-    float* __restrict__ sum_out, int32_t* status) {
-  // k=1 lookups: field f belongs to lane (f % 4) % LPR - the same partition (and therefore the same fp32 summation
-  // order) as gather_fm_kernel, whose results this kernel reproduces bit for bit
-  constexpr int LQ = LPR < 4 ? LPR : 4;       // lanes of a group that carry k=1 lookups
-  constexpr int SPL = (FCH + LQ - 1) / LQ;    // lookups per such lane and chunk
-  constexpr int GPC = 256 / LPR;              // groups per CTA
-  extern __shared__ float4 slots[];           // [2][FCH][256] row pieces, then [2][SPL][GPC][LQ] float2 (bias, lin)
-  float2* sslots = reinterpret_cast<float2*>(slots + 2 * FCH * 256);
-  const int tid = threadIdx.x;
-  const int lir = tid % LPR;
-  const bool col_ok = lir < (k >> 2);
-  const int64_t wmask = ((int64_t)1 << wshift) - 1;
-  const bool has_bias = pt.bias[0] != nullptr, has_lin = pt.lin[0] != nullptr;
-  const int64_t group = ((int64_t)blockIdx.x * blockDim.x + tid) / LPR;
-  const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / LPR;
-  const int64_t iters = (B + n_groups - 1) / n_groups;  // the same for every lane of a warp (shuffles below)
-  const int NCH = (m + FCH - 1) / FCH;
-  const int64_t T = iters * NCH;
-  const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(slots) + (uint32_t)tid * 16u;
-  const int sidx = (tid / LPR) * LQ + (lir < LQ ? lir : 0);  // this lane's k=1 slot inside one [GPC][LQ] plane
-  const uint32_t sslot0 = (uint32_t)__cvta_generic_to_shared(sslots) + (uint32_t)sidx * 8u;
-
-  auto issue = [&](int64_t t) {
-    const int64_t it = t / NCH;
-    const int ch = (int)(t - it * NCH);
-    const int buf = (int)(t & 1);
-    const int64_t b = group + it * n_groups;
-    if (b < B) {
-      const int64_t* my_ids = ids + b * m;
-#pragma unroll
-      for (int j = 0; j < FCH; ++j) {
-        const int f = ch * FCH + j;
-        if (f < m) {
-          const int64_t id = my_ids[f];
-          const bool ok = (id >= 0) && (id < feat_sizes[f]);
-          const uint32_t dst = slot0 + (uint32_t)((buf * FCH + j) * 256) * 16u;
-          const bool mine = ((f & 3) % LPR) == lir;  // this lane also fetches the k=1 values of field f
-          const uint32_t sdst = sslot0 + (uint32_t)((buf * SPL + j / LQ) * (GPC * LQ)) * 8u;
-          if (ok) {
-            const int owner = (int)(id & wmask);
-            const int64_t row = local_offs[f] + (id >> wshift);
-            if (col_ok) cp_async16(dst, pt.tab[owner] + row * (int64_t)k + 4 * lir);
-            if (mine) {
-              if (has_bias) cp_async4(sdst, pt.bias[owner] + row);
-              if (has_lin) cp_async4(sdst + 4u, pt.lin[owner] + row);
-            }
-          } else {
-            slots[(buf * FCH + j) * 256 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (mine) sslots[(buf * SPL + j / LQ) * (GPC * LQ) + sidx] = make_float2(0.f, 0.f);
-            if (lir == 0 && status) atomicOr(status, 1);
-          }
-        }
-      }
-    }
-    cp_async_commit();  // possibly empty: keeps the group count uniform
-  };
-
-  float4 S = make_float4(0.f, 0.f, 0.f, 0.f), Q = make_float4(0.f, 0.f, 0.f, 0.f);
-  float bias_acc = 0.f, lin_acc = 0.f;
-  if (T > 0) issue(0);
-  for (int64_t t = 0; t < T; ++t) {
-    if (t + 1 < T) issue(t + 1);
-    else cp_async_commit();
-    cp_async_wait<1>();  // everything but the newest group has landed: chunk t is readable by its own lane
-    const int64_t it = t / NCH;
-    const int ch = (int)(t - it * NCH);
-    const int buf = (int)(t & 1);
-    const int64_t b = group + it * n_groups;
-    const bool live = b < B;
-    if (live) {
-      float* xrow = x + b * ld;
-#pragma unroll
-      for (int j = 0; j < FCH; ++j) {
-        const int f = ch * FCH + j;
-        if (f < m) {
-          if (col_ok) {
-            const float4 v = slots[(buf * FCH + j) * 256 + tid];
-            st4(xrow + (int64_t)f * k + 4 * lir, v);
-            S.x += v.x; S.y += v.y; S.z += v.z; S.w += v.w;
-            Q.x += v.x * v.x; Q.y += v.y * v.y; Q.z += v.z * v.z; Q.w += v.w * v.w;
-          }
-          if (((f & 3) % LPR) == lir) {
-            const float2 sv = sslots[(buf * SPL + j / LQ) * (GPC * LQ) + sidx];
-            if (has_bias) bias_acc += sv.x;
-            if (has_lin) lin_acc += sv.y;
-          }
-        }
-      }
-    }
-    if (ch == NCH - 1) {  // last chunk of the sample: dense tail, sums, logits
-      if (live) {
-        float* xrow = x + b * ld;
-        for (int j = lir; j < n_dense; j += LPR) {
-          const float dv = dense[b * n_dense + j];
-          xrow[(int64_t)m * k + j] = dv;
-          if (lin_dense) lin_acc += dv * lin_dense[j];
-        }
-        if (sum_out && col_ok) st4(sum_out + b * k + 4 * lir, S);
-      }
-      float second = 0.5f * (S.x * S.x - Q.x) + 0.5f * (S.y * S.y - Q.y) + 0.5f * (S.z * S.z - Q.z) +
-                     0.5f * (S.w * S.w - Q.w);
-      second = group_sum<LPR>(second);
-      bias_acc = group_sum<LPR>(bias_acc);
-      lin_acc = group_sum<LPR>(lin_acc);
-      if (live && lir == 0) {
-        if (fm_out) fm_out[b] = bias_acc + second;
-        if (lin_out) lin_out[b] = lin_acc;
-      }
-      S = make_float4(0.f, 0.f, 0.f, 0.f);
-      Q = make_float4(0.f, 0.f, 0.f, 0.f);
-      bias_acc = 0.f;
-      lin_acc = 0.f;
-    }
-  }
-}
-
-template <int LPR, int FCH>
-static int launch_gather_fm_p2p_async(const PeerTables& pt, int wshift, const int64_t* feat_sizes,
-                                      const int64_t* local_offsets, const int64_t* ids, const float* dense,
-                                      const float* lin_dense, int n_dense, int64_t B, int m, int k, float* x, int64_t ld,
-                                      float* fm_out, float* lin_out, float* sum_out, int32_t* status, cudaStream_t st) {
-  constexpr int LQ = LPR < 4 ? LPR : 4;
-  constexpr int SPL = (FCH + LQ - 1) / LQ;
-  const size_t smem = (size_t)2 * FCH * 256 * 16 + (size_t)2 * SPL * (256 / LPR) * LQ * 8;
-  RM_CUDA(cudaFuncSetAttribute(gather_fm_p2p_async_kernel<LPR, FCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem));
-  const int grid = grid_for(B, 256 / LPR, 2);
-  gather_fm_p2p_async_kernel<LPR, FCH><<<grid, 256, smem, st>>>(pt, wshift, feat_sizes, local_offsets, ids, dense,
-                                                                lin_dense, n_dense, B, m, k, x, ld, fm_out, lin_out,
-                                                                sum_out, status);
-  RM_LAUNCH_CHECK();
-  return 0;
-}
-
 static inline int pow2ceil_p(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -344,31 +186,12 @@ int rm_gather_fm_fwd_p2p(const float* const* tables, const float* const* bias_ta
     RM_CHECK_ARG(r >= W || !bias_tables || pt.bias[r], "null peer bias table");
     RM_CHECK_ARG(r >= W || !lin_tables || pt.lin[r], "null peer linear table");
   }
-  if (tune_variant("RM_TUNE_P2P_NOSCALAR", 0))  // timing experiment only: results lack the k=1 terms
-    for (int r = 0; r < RM_MAX_PEERS; ++r) pt.bias[r] = pt.lin[r] = nullptr;
   int wshift = 0;
   while ((1 << wshift) < W) ++wshift;
   cudaStream_t st = (cudaStream_t)stream;
   const int lpr = pow2ceil_p(k / 4);
-  // deep-queue (cp.async) variant: opt-in with RM_TUNE_P2P_ASYNC=1.  Measured at W = 2 (C5, half the rows over NVLink)
-  // it is SLOWER than the register-staged kernel (0.72 ms vs 0.54 ms): the NVLink reads are not bound by registers held
-  // per load in flight (profiles/README.md)
-  if (tune_variant("RM_TUNE_P2P_ASYNC", 0) && lpr <= 32) {
-#define RM_GA(L, F)                                                                                                  \
-  return launch_gather_fm_p2p_async<L, F>(pt, wshift, feat_sizes, local_offsets, ids, dense, lin_dense, n_dense, B, m, \
-                                          k, x, ld, fm_out, lin_out, sum_out, status, st)
-    // FCH = fields per chunk: half of m when that fits 13 (Criteo: 26 fields -> two chunks of 13), else 8 / 13
-    const bool f8 = m <= 8 || (m > 13 && m <= 16);
-    switch (lpr) {
-      case 1: if (f8) RM_GA(1, 8); else RM_GA(1, 13);
-      case 2: if (f8) RM_GA(2, 8); else RM_GA(2, 13);
-      case 4: if (f8) RM_GA(4, 8); else RM_GA(4, 13);
-      case 8: if (f8) RM_GA(8, 8); else RM_GA(8, 13);
-      case 16: if (f8) RM_GA(16, 8); else RM_GA(16, 13);
-      default: if (f8) RM_GA(32, 8); else RM_GA(32, 13);
-    }
-#undef RM_GA
-  }
+  // (a deep-queue cp.async variant of this kernel was measured SLOWER at W = 2 - 0.72 ms vs 0.54 ms: the NVLink reads are
+  // not bound by registers held per load in flight - and was removed; profiles/README.md)
   const int grid = grid_for(B, 256 / (lpr > 32 ? 32 : lpr), 8);
 #define RM_GP(L)                                                                                                      \
   case L:                                                                                                             \

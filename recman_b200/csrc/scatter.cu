@@ -526,7 +526,7 @@ template <int LPR, class Src>
 static int launch_segment_reduce(const Src& src, int k, int64_t N, const int32_t* sorted_pos, const int32_t* seg_start,
                                  const int32_t* n_unique, float* out_rows, float* out_bias, float* out_lin,
                                  const UpdateSink& sink, int dflt_variant, const LongWs& lw, cudaStream_t st) {
-  const int variant = tune_variant("RM_TUNE_SEGRED", dflt_variant);  // measured best on B200 (profiles/r1_kbench.json)
+  const int variant = dflt_variant;  // per entry point: the measured best on B200 (profiles/r1_call19_kbench_c5shape_10Mrows.json)
   // n_unique <= N lives on the device: the grid is sized for the worst case (a CTA iteration = 8 warps x 32 rows)
   const int grid = grid_for(N, 256, 8);
   if (lw.counters) RM_CUDA(cudaMemsetAsync(lw.counters, 0, 2 * sizeof(int32_t), st));

@@ -36,8 +36,20 @@ constexpr int BK_TILE = 128;
 constexpr int BK_NS = 3;    // gather stages
 constexpr int BK_DEPTH = 2; // tiles in flight per producer thread
 constexpr int BK_PRODUCERS = 128;
-constexpr bool BK_PREFETCH = false;  // request the next tile's per-sample operands one tile ahead
-constexpr int BK_NH = 2;              // epilogue threads per position (each owns 64 / BK_NH columns of the row)
+// Epilogue variants that were measured and lost at the C5 shape (kept switchable for other shapes):
+//   BK_FASTPATH: tiles of singleton segments release their gather stage before the update math and store rows straight
+//                from registers - 0.80 ms against 0.72 ms with the staged, coalesced write-back;
+//   BK_PREFETCH: next tile's S rows requested one tile ahead - the 32 extra live registers spill (0.88 ms);
+//   BK_NH = 4  : four threads per position - per-position bookkeeping replicated, 0.78 .. 1.06 ms.
+constexpr bool BK_FASTPATH = false;
+#ifndef RM_BK_PREFETCH
+#define RM_BK_PREFETCH 0
+#endif
+#ifndef RM_BK_NH
+#define RM_BK_NH 2
+#endif
+constexpr bool BK_PREFETCH = RM_BK_PREFETCH != 0;  // request the next tile's per-sample operands one tile ahead
+constexpr int BK_NH = RM_BK_NH;              // epilogue threads per position (each owns 64 / BK_NH columns of the row)
 constexpr int BK_EPI = 128 * BK_NH;
 constexpr int BK_THREADS = 128 + 32 + BK_EPI;  // 4 producer warps, 1 MMA warp, 4 * BK_NH epilogue warps
 constexpr int BK_DRAIN = 4;  // tiles per TMEM accumulation group of GEMM 2
@@ -147,6 +159,10 @@ struct TowerBwdParams {
   int m, upf, n_units, do_update;
 };
 
+__device__ __forceinline__ void atomicOr_shared(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 struct TileIter {
   int u, u_end, upf;
   const int32_t* ub;
@@ -254,8 +270,8 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
       mb = 0;
       if (tid < cnt) {
         mkey = P.keys[ti.p0 + tid];
-        mb = P.spos[ti.p0 + tid] / P.m;
-      }
+        mb = P.spos[ti.p0 + tid];  // raw position; divided by m when the meta is stored, one tile later, so that the
+      }                             // load's latency (keys / positions stream from HBM) is not exposed here
       if (tid == 0) mprev = ti.p0 > ti.rs ? P.keys[ti.p0 - 1] : TW_NONE;
       if (tid == 1) mnext = ti.p0 + cnt < ti.re ? P.keys[ti.p0 + cnt] : TW_NONE;
     };
@@ -268,12 +284,19 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
       const uint32_t mkey_cur = mkey;
       // key slots: [0] previous key, [1..cnt] the tile, [cnt+1] next key, the rest TW_NONE
       sts32(ms + 4u * (tid < cnt ? tid + 1 : tid + 2), mkey);
-      sts32(ms + 4u * (130 + tid), (uint32_t)mb);
+      sts32(ms + 4u * (130 + tid), (uint32_t)(mb / P.m));
       if (tid == 0) sts32(ms, mprev);
       if (tid == 1) sts32(ms + 4u * (cnt + 1), mnext);
+      if (tid == 2) sts32(ms + 4u * 258u, 0u);
       it_issue.next();
       if (it_issue.valid()) load_meta(it_issue);  // in flight while this tile's copies are issued
       named_bar_sync(2, BK_PRODUCERS);
+      {
+        // does any row of the tile appear twice (inside it, or across its borders)?  Tiles of singletons - nearly all of
+        // them under uniform ids - take the epilogue's fast path: no exchange, the gather stage is released early.
+        const bool dup = tid < cnt && (mkey_cur == lds32(ms + 4u * tid) || mkey_cur == lds32(ms + 4u * (tid + 2)));
+        if (__any_sync(0xffffffffu, dup) && (tid & 31) == 0) atomicOr_shared(ms + 4u * 258u, 1u);
+      }
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int r = rgx + 8 * i;
@@ -287,6 +310,20 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
       }
       ++X;
     };
+    float4 gn[8];
+    auto load_g = [&](const TileIter& ti, int Yt) {
+      const int cnt = ti.cnt();
+      const uint32_t mst = meta_base + (uint32_t)(Yt & 3) * BK_META;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rgg + 16 * i;
+        gn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < cnt) {
+          const int32_t b = (int32_t)lds32(mst + 4u * (130 + r));
+          gn[i] = __ldg(reinterpret_cast<const float4*>(P.g1 + (int64_t)b * BK_N1 + 4 * cg));
+        }
+      }
+    };
     if (it_issue.valid()) load_meta(it_issue);
     for (int d = 0; d < BK_DEPTH; ++d) {
       if (it_issue.valid()) issue();
@@ -295,20 +332,15 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
     for (int Y = 0; it_cons.valid(); ++Y) {
       cp_async_wait<BK_DEPTH - 1>();  // all but the newest BK_DEPTH-1 groups: tile Y has landed (this thread's chunks)
       const int s = Y % BK_NS;
-      // this thread's chunks of the tile's g1 rows (L2-resident), requested before the wait below
+      // this thread's chunks of the tile's g1 rows (L2-resident): requested one tile ahead (gn), used now (gv)
       float4 gv[8];
-      {
-        const int cnt = it_cons.cnt();
-        const uint32_t ms = meta_base + (uint32_t)(Y & 3) * BK_META;
+      if (Y == 0) load_g(it_cons, 0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = rgg + 16 * i;
-          gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (r < cnt) {
-            const int32_t b = (int32_t)lds32(ms + 4u * (130 + r));
-            gv[i] = __ldg(reinterpret_cast<const float4*>(P.g1 + (int64_t)b * BK_N1 + 4 * cg));
-          }
-        }
+      for (int i = 0; i < 8; ++i) gv[i] = gn[i];
+      {
+        TileIter nx = it_cons;
+        nx.next();
+        if (nx.valid()) load_g(nx, Y + 1);  // its meta was stored when the tile was issued (>= 1 iteration ago)
       }
       if (Y > 0) ok = ok && mbar_wait(lo_free, ((uint32_t)(Y - 1)) & 1u);
       // exact remainders of the truncated operands
@@ -472,6 +504,41 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
         gr[c].z = __uint_as_float(dr[4 * c + 2]) + gf * (Sv[c].z - xr[c].z);
         gr[c].w = __uint_as_float(dr[4 * c + 3]) + gf * (Sv[c].w - xr[c].w);
       }
+      if (BK_FASTPATH && lds32(ms + 4u * 258u) == 0u) {
+        // ---- fast path: every position of the tile is its own segment.  All this tile still needs sits in registers,
+        // so the gather stage goes back to the producers before the update math and the stores.
+        float2 sold = make_float2(0.f, 0.f);
+        if (h == 0 && valid && P.scal) sold = lds64f(scal_st + (uint32_t)s * 1024u + 8u * j);
+        mbar_arrive(empty(s));
+        if (valid) {
+          const int64_t opos = (int64_t)it.p0 + j;
+          if (P.out_rows) {
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) st4(P.out_rows + opos * BK_K + 4 * (h * CPT + c), gr[c]);
+          }
+          if (P.do_update) {
+            float* trow = P.table + (int64_t)key * BK_K + 4 * CPT * h;
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+              float4 nv;
+              nv.x = opt_update(xr[c].x, gr[c].x, P.o);
+              nv.y = opt_update(xr[c].y, gr[c].y, P.o);
+              nv.z = opt_update(xr[c].z, gr[c].z, P.o);
+              nv.w = opt_update(xr[c].w, gr[c].w, P.o);
+              st4(trow + 4 * c, nv);
+            }
+          }
+          if (h == 0) {
+            if (P.out_scal) *reinterpret_cast<float2*>(P.out_scal + 2 * opos) = make_float2(gf, gl);
+            if (P.scal && P.do_update) {
+              float2 nv;
+              nv.x = opt_update(sold.x, gf, P.o);
+              nv.y = P.g_lin ? opt_update(sold.y, gl, P.o) : sold.y;
+              *reinterpret_cast<float2*>(P.scal + 2 * (int64_t)key) = nv;
+            }
+          }
+        }
+      } else {
       float asf = gf, asl = gl;
       const bool single = is_head && is_tail;
       if (valid && !single) {  // members of longer segments exchange their rows through the (now dead) x tile
@@ -583,6 +650,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
         }
       }
       mbar_arrive(empty(s));
+      }
       ++tin;
       const bool unit_end = it.last_in_unit();
       if (tin == BK_DRAIN || unit_end) {  // drain the GEMM 2 accumulator (fp32 round-to-nearest adds)
@@ -793,11 +861,8 @@ int rm_tower_bwd_update(float* table, float* scal, const uint32_t* sorted_keys, 
   P.table = table; P.scal = scal; P.keys = sorted_keys; P.spos = sorted_pos; P.ub = unit_bounds; P.g1 = g1; P.S = S;
   P.g_fm = g_fm; P.g_lin = g_lin; P.wpack = wpack; P.slabs = slabs; P.out_rows = out_rows; P.out_scal = out_scal;
   P.status = status; P.m = m; P.upf = upf; P.n_units = m * upf;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RM_CUDA(cudaFuncSetAttribute(tower_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BK_SMEM));
-    attr_set = true;
-  }
+
+  RM_SMEM_ATTR_ONCE(BK_SMEM, tower_bwd_kernel);
   const int grid = P.n_units < RM_NUM_SMS ? P.n_units : RM_NUM_SMS;
   tower_bwd_kernel<<<grid, BK_THREADS, BK_SMEM, st>>>(P);
   RM_LAUNCH_CHECK();
@@ -810,12 +875,8 @@ int rm_umma_probe(const float* At, const float* Bt, int32_t K, int32_t variant, 
                   void* stream) {
   using namespace rm;
   RM_CHECK_ARG(At && Bt && D && K >= 8 && K <= 64 && K % 8 == 0, "bad probe arguments");
-  static bool attr_set = false;
   const int smem = 1024 + 65536 + 16384 + 64;
-  if (!attr_set) {
-    RM_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  RM_SMEM_ATTR_ONCE(smem, umma_probe_kernel);
   umma_probe_kernel<<<1, 160, smem, (cudaStream_t)stream>>>(At, Bt, K, variant, D, status);
   RM_LAUNCH_CHECK();
   return 0;

@@ -412,18 +412,11 @@ int rm_tower_fwd(const float* table, const float* scal, const int64_t* table_off
   P.tmem_cols = cols;
   const size_t smem = tower_fwd_smem(KB, m, n_dense, N1PAD);
   const int grid = (int)ceil_div(B, TF_ROWS);
-  static bool attr_set[3] = {false, false, false};
   if (KB == 1) {
-    if (!attr_set[1]) {
-      RM_CUDA(cudaFuncSetAttribute(tower_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set[1] = true;
-    }
+    RM_SMEM_ATTR_ONCE(smem, tower_fwd_kernel<1>);
     tower_fwd_kernel<1><<<grid, TF_THREADS, smem, st>>>(P);
   } else {
-    if (!attr_set[2]) {
-      RM_CUDA(cudaFuncSetAttribute(tower_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set[2] = true;
-    }
+    RM_SMEM_ATTR_ONCE(smem, tower_fwd_kernel<2>);
     tower_fwd_kernel<2><<<grid, TF_THREADS, smem, st>>>(P);
   }
   RM_LAUNCH_CHECK();
