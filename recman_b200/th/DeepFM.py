@@ -60,9 +60,10 @@ class DeepFM(DeepModel):
         """The layers of the fused tower path and its raw outputs (y1, fm, lin without w0), or None when the model /
         hyper-parameters are outside what the fused kernels cover."""
         hp = self.hparams
-        fm_dropout = hp["fm_dropout"] if training else (1.0,) * len(hp["fm_dropout"])
-        if not (self.use_fm and self.use_deep and all(p >= 1 for p in fm_dropout)
-                and (not training or hp["deep_dropout"][0] >= 1)):
+        # a per-model decision, NOT per call: the tower keeps the two k=1 tables interleaved in one array, a layout the
+        # separate kernels do not read - a model whose training step cannot use the tower (FM dropout, dropout on the DNN
+        # input) must not use it for inference either
+        if not (self.use_fm and self.use_deep and all(p >= 1 for p in hp["fm_dropout"]) and hp["deep_dropout"][0] >= 1):
             return None
         self.embeddings = self._embedding_layer(use_bias=True, l2_mode=hp["embedding_l2_mode"])
         linear_feats = list(self.feat_dict.values())

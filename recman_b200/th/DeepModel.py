@@ -149,6 +149,9 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
                     "row-sharded tables need the fused front end: every embedding feature one-hot (no multi-valued "
                     "fields), embedding_size % 4 == 0 and <= 128")
             return None
+        if "scal_storage" in self.__dict__.get("_cache", {}):
+            raise RuntimeError("this model's k=1 tables are interleaved for the fused tower kernels; the separate kernels "
+                               "cannot read that layout (hparams['tower'] must not change after the first forward)")
         layer._upsert_variables()
         table = self.variables[layer.table_name]
         bias_table = self.variables[layer.bias_name] if (layer.use_bias and want_fm) else None

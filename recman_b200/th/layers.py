@@ -52,6 +52,7 @@ __all__ = [
     "PredictionLayer",
     "BatchNormalization",
     "PaddedRows",
+    "set_dropout_mask_source",
     "glorot_normal",
     "glorot_uniform",
     "leaky_relu",
@@ -130,10 +131,25 @@ def _l2(w: torch.Tensor) -> torch.Tensor:
     return (w * w).sum() / 2  # tf.nn.l2_loss
 
 
+_dropout_mask_source = None  # callable(shape, keep_prob, device) -> 0/1 tensor | None (tests: injected Bernoulli masks)
+
+
+def set_dropout_mask_source(fn):
+    """Inject the Bernoulli keep-masks of every dropout site, in call order (``None`` restores the device RNG).  TF's
+    random stream cannot be reproduced, so parity tests of the reference's default keep-probs (hparams/xDeepFM.py:28:
+    0.8) feed the same masks to this path and to the oracle (oracle.tf_dropout)."""
+    global _dropout_mask_source
+    _dropout_mask_source = fn
+
+
 def _dropout(x, keep_prob, training=True):
     """tf.nn.dropout(x, rate=1-keep_prob): the reference's tuples are KEEP probabilities."""
     if keep_prob >= 1 or not training:
         return x
+    if _dropout_mask_source is not None:
+        mask = _dropout_mask_source(tuple(x.shape), float(keep_prob), x.device)
+        if mask is not None:
+            return x * mask.to(x.dtype) / float(keep_prob)
     return torch.nn.functional.dropout(x, p=1.0 - float(keep_prob), training=True)
 
 

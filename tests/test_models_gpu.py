@@ -396,3 +396,63 @@ def test_tower_inference_weight_override():
         torch.testing.assert_close(pred_train, base, rtol=1e-6, atol=1e-7)
         outs[tower] = pred
     torch.testing.assert_close(outs[True], outs[False], rtol=1e-5, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the reference's default keep-probabilities (dropout 0.8) with injected masks
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [16, 64])
+def test_deepfm_reference_default_dropout_with_injected_masks(k):
+    """deep_dropout = (0.8, 0.8, 0.8) (tf/core/DeepFM.py:38, hparams/xDeepFM.py:28): the same Bernoulli masks go to the
+    GPU path (layers.set_dropout_mask_source) and to the oracle's DNN (oracle.dnn(masks=...)); logit, loss and every
+    gradient at 1e-5."""
+    from recman_b200.th import DeepFM, layers
+    from recman_b200.th.input import DataInputs
+
+    fd = pu.make_feat_dict([40, 9, 300, 7], n_dense=3)
+    B = 333
+    X, y = pu.synth_batch(fd, B, seed=23)
+    keep = (0.8, 0.8, 0.8)
+    model = DeepFM(fd, embedding_size=k, deep_hidden_units=(32, 32), deep_dropout=keep, batch_size=B)
+    with torch.no_grad():
+        model._out(DataInputs("cuda").load(fd, X, y), training=False)
+    pu.randomize_variables(model)
+    d = 4 * k + 3
+    g = torch.Generator().manual_seed(99)
+    masks = [(torch.rand(B, n, generator=g) < p).float() for n, p in zip((d, 32, 32), keep)]
+    calls = []
+
+    def source(shape, keep_prob, device):
+        m = masks[len(calls)]
+        calls.append(shape)
+        assert tuple(shape) == tuple(m.shape) and keep_prob == 0.8
+        return m.to(device)
+
+    layers.set_dropout_mask_source(source)
+    try:
+        logit, loss, grads = pu.run_model_step(model, X, y)
+    finally:
+        layers.set_dropout_mask_source(None)
+    assert len(calls) == 3
+    # oracle with the same masks
+    st = pu.cpu_state(model, torch.float64)
+    layer = model.embeddings
+    tabs, biases = pu._split_tables(model, st, layer)
+    embeds, bias = oracle.feat_embedding_layer(tabs, pu._oracle_inputs(fd, layer, X), biases)
+    dense = torch.stack([torch.from_numpy(np.asarray(X[f.name], dtype=np.float32)).double() for f in fd.dense_feats], 1)
+    lin = pu._oracle_linear(fd, model.linear, st, X, torch.float64)
+    xin = oracle.dnn_combiner([embeds, dense])
+    dnn_l = oracle.dnn(xin, *pu._dnn_params(st, 2), activation=oracle.relu, dropout=keep, masks=[m.double() for m in masks])
+    o_logit = lin + oracle.fm_layer(embeds, bias) + dnn_l
+    hp = model.hparams
+    l2 = (hp["embedding_l2_reg"] * sum(oracle.l2_loss(t) for t in tabs) + hp["linear_l2_reg"] * oracle.l2_loss(st["linear_w"])
+          + hp["deep_l2_reg"] * (oracle.l2_loss(st["dnn_layer_0_weights"]) + oracle.l2_loss(st["dnn_layer_1_weights"])
+                                 + oracle.l2_loss(st["dnn_w"])))
+    o_loss = oracle.create_loss(torch.from_numpy(np.array(y, dtype=np.float32)).double(), oracle.prediction(o_logit), "classification") + l2
+    o_loss.backward()
+    torch.testing.assert_close(logit.reshape(-1).double(), o_logit.detach().reshape(-1), rtol=1e-5, atol=2e-6)
+    torch.testing.assert_close(loss.double().reshape(()), o_loss.detach().reshape(()), rtol=1e-5, atol=2e-6)
+    for name, gg in grads.items():
+        exp = st[name].grad if st[name].grad is not None else torch.zeros_like(st[name])
+        atol = 1e-5 * max(float(exp.abs().max()), 1e-30)
+        torch.testing.assert_close(gg.double().reshape(-1), exp.reshape(-1), rtol=1e-5, atol=atol, msg=lambda m: f"{name}: {m}")

@@ -319,3 +319,73 @@ def test_deepfm_head_forward_backward(act, task, B):
                            b3.cuda(), y.cuda(), _C.ACT_KINDS[act], 0 if task == "classification" else 1)
     for k in out:
         assert torch.equal(out[k], out2[k]), k
+
+
+def test_c5_shape_rows_indices_and_gradients():
+    """BASELINE config 5 shape: B = 65 536, 26 fields x 1 M rows, k = 64 (6.7 GB of tables; the kernels see the same
+    tile counts, unit cuts and id ranges as the timed workload).  Gathered rows and the sorted (row, position) indices
+    bit-exact; summed gradient rows, k=1 gradients and dW1 within 1e-5 of the fp64 reference on the touched rows."""
+    ops = _ops()
+    B, m, k, nd, N1, rows_per = 65536, 26, 64, 13, 32, 1_000_000
+    g = torch.Generator().manual_seed(2019)
+    dev = "cuda"
+    total = m * rows_per
+    table = torch.empty(total, k, device=dev).normal_(0.0, 0.05, generator=torch.Generator(device=dev).manual_seed(1))
+    scal = torch.empty(total, 2, device=dev).normal_(0.0, 0.05, generator=torch.Generator(device=dev).manual_seed(2))
+    offs = (torch.arange(m + 1) * rows_per).long()
+    ids = torch.randint(0, rows_per, (B, m), generator=g)
+    ids[:64, :] = 7          # a hot row per field: 64-position segments
+    ids[0] = 0
+    ids[-1] = rows_per - 1
+    dense = torch.randn(B, nd, generator=g)
+    W1 = torch.randn(m * k + nd, N1, generator=g) * 0.05
+    b1 = torch.randn(N1, generator=g) * 0.05
+    lin_dense = torch.randn(nd, generator=g) * 0.1
+    st = ops.new_status(dev)
+    y1, fm, lin, S, x = ops.tower_fwd(table, scal, offs.cuda(), ids.cuda(), dense.cuda(), lin_dense.cuda(), W1.cuda(),
+                                      b1.cuda(), want_x=True, status=st)
+    rows = oracle.global_rows(ids.numpy(), offs.numpy())  # [B, m]
+    rows_t = torch.from_numpy(rows).cuda()
+    gathered = table[rows_t.reshape(-1)].reshape(B, m * k)
+    assert torch.equal(x[:, : m * k], gathered)  # gathered rows: bit-exact
+    # forward values on a sample of the batch against fp64
+    sel = torch.arange(0, B, 257)
+    xs = gathered[sel.cuda()].double().cpu()
+    xin = torch.cat([xs, dense[sel].double()], 1)
+    assert_close(y1[sel.cuda()], xin @ W1.double() + b1.double(), msg="y1")
+    e = xs.reshape(len(sel), m, k)
+    sc = scal[rows_t[sel.cuda()].reshape(-1)].reshape(len(sel), m, 2).double().cpu()
+    assert_close(fm[sel.cuda()], sc[:, :, 0].sum(1) + 0.5 * ((e.sum(1) ** 2).sum(1) - (e ** 2).sum((1, 2))), msg="fm")
+    assert_close(lin[sel.cuda()], sc[:, :, 1].sum(1) + dense[sel].double() @ lin_dense.double(), msg="lin")
+    # sorted (row, position) pairs: bit-exact against a stable argsort
+    plan = ops.tower_plan(ids.cuda(), offs.cuda(), total, status=st)
+    torch.cuda.synchronize()
+    assert int(st.item()) == 0
+    keys = plan.sorted_keys.cpu().numpy().view(np.uint32).astype(np.int64)
+    order = np.argsort(rows.reshape(-1), kind="stable")
+    assert np.array_equal(plan.sorted_pos.cpu().numpy(), order.astype(np.int32))
+    assert np.array_equal(keys, rows.reshape(-1)[order])
+    # backward: gradients on the touched rows
+    g1 = torch.randn(B, N1, generator=g) * 1e-2
+    g_fm = torch.randn(B, generator=g) * 1e-2
+    g_lin = torch.randn(B, generator=g) * 1e-2
+    dW1, out_rows, out_scal = ops.tower_bwd_update(table, scal, plan, g1.cuda(), S, g_fm.cuda(), g_lin.cuda(), W1.cuda(),
+                                                   0, 1e-3, update=False, debug=True, status=st)
+    torch.cuda.synchronize()
+    assert int(st.item()) == 0
+    # fp64 reference of the per-position gradient rows, on the GPU in chunks (109 M values)
+    Sd = gathered.reshape(B, m, k).double().sum(1)
+    dx = (g1.cuda().double() @ W1.cuda().double()[: m * k].t()).reshape(B, m, k)
+    G = dx + g_fm.cuda().double()[:, None, None] * (Sd[:, None, :] - gathered.reshape(B, m, k).double())
+    closing = np.flatnonzero(np.append(keys[1:] != keys[:-1], True))
+    starts = np.concatenate([[0], closing[:-1] + 1])
+    Gs = G.reshape(-1, k)[torch.from_numpy(order).cuda()]  # per-position rows in sorted order
+    csum = torch.cat([torch.zeros(1, k, dtype=torch.float64, device=dev), Gs.cumsum(0)])
+    exp_rows = csum[torch.from_numpy(closing + 1).cuda()] - csum[torch.from_numpy(starts).cuda()]
+    got_rows = out_rows[torch.from_numpy(closing).cuda()]
+    assert_close(got_rows, exp_rows, atol_scale=1e-5, msg="summed gradient rows")
+    gsc = torch.stack([g_fm, g_lin], 1).double().cuda()[torch.from_numpy(order // m).cuda()]
+    cs2 = torch.cat([torch.zeros(1, 2, dtype=torch.float64, device=dev), gsc.cumsum(0)])
+    exp_sc = cs2[torch.from_numpy(closing + 1).cuda()] - cs2[torch.from_numpy(starts).cuda()]
+    assert_close(out_scal[torch.from_numpy(closing).cuda()], exp_sc, atol_scale=1e-5, msg="k=1 gradients")
+    assert_close(dW1, gathered.double().t() @ g1.cuda().double(), atol_scale=1e-5, msg="dW1")
