@@ -520,7 +520,7 @@ def sharded_parity_check(world, rank, dev, k=64, b=256):
     to_inputs = lambda t: DataInputs.from_tensors(fd, torch.from_numpy(t[0]).to(dev), torch.from_numpy(t[1]).to(dev),
                                                   torch.from_numpy(t[2]).to(dev))
     ref = DeepFM(fd, **dict(kw, batch_size=b * world))
-    ref.hparams["tower"] = False  # the sharded path runs the separate kernels: compare like with like first
+    ref.hparams["tower"] = False  # single GPU: the separate kernels; sharded: the fused tower (k = 64) over peer memory
     gi = to_inputs(glob)
     with torch.no_grad():
         ref._out(gi)

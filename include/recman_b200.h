@@ -389,6 +389,27 @@ int rm_tower_bwd_update(float* table, float* scal, const uint32_t* sorted_keys,
                         int64_t B, int32_t m, int32_t k, int32_t N1, int32_t unit, int32_t opt,
                         float lr, float l2, float* dW1, float* out_rows, float* out_scal,
                         int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+/* Row-sharded tables (row r of a table on rank r mod W at local row r div W) over NVLink peer memory:
+ * rm_tower_fwd_p2p = rm_tower_fwd with every row read from its owner (tables / scals: HOST arrays of W device
+ * pointers into the ranks' cudaIpc-mapped shards; feat_sizes [m] global sizes, local_offsets [m] owner-local first
+ * rows); rm_tower_shard_plan = the owner-side rm_tower_plan over the ids of ALL ranks (gids [W*b*m], rank-major):
+ * owned entries in ascending global position gp = src_rank*(b*m) + p, keyed by owner-local row, sorted, cut into
+ * units (capacity N_cap, *status |= 4 when exceeded; Bcap sizes the unit grid).  rm_tower_bwd_update then runs on the
+ * owner with B = Bcap and g1 / S / g_fm / g_lin holding the all-gathered per-sample operands of all W*b samples. */
+int rm_tower_fwd_p2p(const float* const* tables, const float* const* scals, int32_t W,
+                     const int64_t* feat_sizes, const int64_t* local_offsets, const int64_t* ids,
+                     const float* dense, const float* lin_dense, int32_t lin_dense_stride,
+                     int32_t n_dense, const float* W1, const float* b1, int32_t N1, int64_t B, int32_t m,
+                     int32_t k, float* y1, float* fm_out, float* lin_out, float* sum_out,
+                     int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+size_t rm_tower_shard_plan_workspace_bytes(int64_t Ntot, int64_t N_cap);
+int rm_tower_shard_plan(const int64_t* gids, int64_t Ntot, int32_t m, int32_t W, int32_t rank,
+                        const int64_t* feat_sizes, const int64_t* local_offsets, int64_t total_local,
+                        int64_t N_cap, int64_t Bcap, int32_t unit, void* workspace,
+                        size_t workspace_bytes, uint32_t* sorted_keys, int32_t* sorted_gpos,
+                        int32_t* field_bounds, int32_t* unit_bounds, int32_t* n_own, int32_t* status,
+                        void* stream);
+
 /* ------------------------------------------------------------------------- *
  * H   fused DeepFM head: everything between the first DNN layer's pre-activation y1 and
  *     the loss, forward and backward, for hidden_units = (32, 32).

@@ -114,6 +114,15 @@ _SIGS = {
         [P, P, P, P, P, P, P, P, P, P, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_float, P, P, P,
          P, P, c_size_t, P]),
     "rm_umma_probe": (ctypes.c_int, [P, P, c_int32, c_int32, P, P, P]),
+    "rm_tower_fwd_p2p": (
+        ctypes.c_int,
+        [P, P, c_int32, P, P, P, P, P, c_int32, c_int32, P, P, c_int32, c_int64, c_int32, c_int32, P, P, P, P, P, P,
+         c_size_t, P]),
+    "rm_tower_shard_plan_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "rm_tower_shard_plan": (
+        ctypes.c_int,
+        [P, c_int64, c_int32, c_int32, c_int32, P, P, c_int64, c_int64, c_int64, c_int32, P, c_size_t, P, P, P, P, P, P,
+         P]),
     "rm_deepfm_head_supported": (ctypes.c_int, [c_int32, c_int32]),
     "rm_deepfm_head_workspace_bytes": (c_size_t, [c_int64]),
     "rm_deepfm_head": (

@@ -437,11 +437,13 @@ class TowerFunction(Function):
 
     @staticmethod
     def forward(ctx, table, scal, scal_fwd, bias_param, W_lin, W1, b1, offsets, total_rows, status, ids, dense,
-                fused_opt):
+                fused_opt, grad_mode=True):
         k = table.shape[1]
         N1 = W1.shape[1]
         n_dense = 0 if dense is None else dense.shape[1]
-        need_grad = any(ctx.needs_input_grad)
+        # grad_mode: torch.is_grad_enabled() of the CALLER (inside forward() autograd is always off, and
+        # needs_input_grad ignores an enclosing no_grad())
+        need_grad = bool(grad_mode) and any(ctx.needs_input_grad)
         use_bk = need_grad and fused_opt is not None and ops.tower_bwd_supported(k, N1)
         lin_dense = scal_fwd[total_rows:, 1] if n_dense else None
         y1, fm, lin, S, x = ops.tower_fwd(table, scal_fwd[:total_rows], offsets, ids, dense, lin_dense, W1, b1,
@@ -480,7 +482,7 @@ class TowerFunction(Function):
             dW1[: m * k] = dW1_emb
             if ctx.n_dense:
                 torch.mm(dense.t(), g1, out=dW1[m * k :])
-            return (None, None, None, None, None, dW1, db1) + (None,) * 6
+            return (None, None, None, None, None, dW1, db1) + (None,) * 7
         d = m * k + ctx.n_dense
         ld = x.shape[1]
         if ops.narrow_linear_ok(N1):
@@ -495,7 +497,7 @@ class TowerFunction(Function):
         attach_sparse_grad(ctx.bias_param, ops.SparseGrad(plan.uniq_rows, ob, plan.n_unique))
         if g_lin is not None:
             attach_sparse_grad(ctx.W_lin, ops.SparseGrad(plan.uniq_rows, ol, plan.n_unique))
-        return (None, None, None, None, None, dW1, db1) + (None,) * 6
+        return (None, None, None, None, None, dW1, db1) + (None,) * 7
 
 
 class HeadFunction(Function):

@@ -24,6 +24,7 @@
 // Roofline: HBM.  Algorithmic bytes: per position 8 (key, position) + 4k (row read), per unique row 4k + 8 + 8
 // written / read-modify-written.
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include "optim.cuh"
 #include "tower_common.cuh"
@@ -97,11 +98,32 @@ __global__ void __launch_bounds__(1024) tower_bounds_kernel(const uint32_t* __re
     const int f = idx / (upf + 1), i = idx - f * (upf + 1);
     const int32_t lo = fb[f], hi = fb[f + 1];
     int64_t p64 = (int64_t)lo + (int64_t)i * unit;
-    int32_t p = p64 < hi ? (int32_t)p64 : hi;
+    int32_t p = (p64 < hi && i < upf) ? (int32_t)p64 : hi;  // the last cut is the field's end, whatever its length
     if (p > lo && p < hi && keys[p] == keys[p - 1]) {
       const uint32_t kv = keys[p];
       p = kv == 0xFFFFFFFFu ? hi : lower_bound_u32(keys, p, hi, kv + 1u);
     }
+    unit_bounds[idx] = p;
+  }
+}
+
+// the same with owner-local offsets [m] (no closing entry) and the total passed separately (row-sharded tables)
+__global__ void __launch_bounds__(1024) tower_bounds_local_kernel(const uint32_t* __restrict__ keys, int32_t N,
+                                                                  const int64_t* __restrict__ offs_m, uint32_t total, int m,
+                                                                  int unit, int upf, int32_t* __restrict__ field_bounds,
+                                                                  int32_t* __restrict__ unit_bounds) {
+  extern __shared__ int32_t fb[];
+  for (int f = threadIdx.x; f <= m; f += blockDim.x) {
+    fb[f] = lower_bound_u32(keys, 0, N, f < m ? (uint32_t)offs_m[f] : total);
+    field_bounds[f] = fb[f];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < m * (upf + 1); idx += blockDim.x) {
+    const int f = idx / (upf + 1), i = idx - f * (upf + 1);
+    const int32_t lo = fb[f], hi = fb[f + 1];
+    int64_t p64 = (int64_t)lo + (int64_t)i * unit;
+    int32_t p = (p64 < hi && i < upf) ? (int32_t)p64 : hi;
+    if (p > lo && p < hi && keys[p] == keys[p - 1]) p = lower_bound_u32(keys, p, hi, keys[p] + 1u);
     unit_bounds[idx] = p;
   }
 }
@@ -164,7 +186,7 @@ __device__ __forceinline__ void atomicOr_shared(uint32_t addr, uint32_t v) {
 }
 
 struct TileIter {
-  int u, u_end, upf;
+  int u, u_end, upf, stride;  // units u, u + stride, ... < u_end (strided: empty units spread evenly over the CTAs)
   const int32_t* ub;
   int32_t rs, re, p0;  // unit range, current tile start
   int f, t, nt;
@@ -178,7 +200,7 @@ struct TileIter {
       t = 0;
       p0 = rs;
       if (nt > 0) return;
-      ++u;
+      u += stride;
     }
   }
   __device__ __forceinline__ bool valid() const { return u < u_end; }
@@ -188,7 +210,7 @@ struct TileIter {
     ++t;
     p0 += BK_TILE;
     if (t >= nt) {
-      ++u;
+      u += stride;
       load_unit();
     }
   }
@@ -247,8 +269,9 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
   TileIter it;
   it.upf = P.upf;
   it.ub = P.ub;
-  it.u = (int)(((int64_t)blockIdx.x * P.n_units) / gridDim.x);
-  it.u_end = (int)(((int64_t)(blockIdx.x + 1) * P.n_units) / gridDim.x);
+  it.u = (int)blockIdx.x;
+  it.u_end = P.n_units;
+  it.stride = (int)gridDim.x;
   const int u_begin = it.u;
 
   if (warp < 4) {
@@ -442,7 +465,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
 #pragma unroll
     for (int i = 0; i < DWC; ++i) dwacc[i] = 0.f;
     // units without positions still own a slab: zero it
-    for (int u = u_begin; u < it.u_end; ++u) {
+    for (int u = u_begin; u < it.u_end; u += it.stride) {
       const int f = u / P.upf, i = u - f * P.upf;
       if (P.ub[f * (P.upf + 1) + i + 1] <= P.ub[f * (P.upf + 1) + i] && j < BK_K) {
         float* dst = P.slabs + ((int64_t)u * BK_K + j) * BK_N1 + DWC * h;
@@ -754,6 +777,40 @@ __global__ void __launch_bounds__(160, 1) umma_probe_kernel(const float* __restr
   }
 }
 
+// ---- owner-side plan for row-sharded tables: from the ids of ALL ranks (gids [W*b, m], rank-major) keep the entries
+// this rank owns (id mod W == rank) in ascending global position, key them by owner-local row, sort
+struct TowerOwned {
+  const int64_t* gids;
+  const int64_t* feat_sizes;
+  uint32_t m;
+  int64_t wmask, rank;
+  __host__ __device__ __forceinline__ bool operator()(const int32_t& i) const {
+    const int64_t id = gids[i];
+    return id >= 0 && id < feat_sizes[(uint32_t)i % m] && (id & wmask) == rank;
+  }
+};
+
+__global__ void __launch_bounds__(256) tower_shard_keys_kernel(const int64_t* __restrict__ gids,
+                                                               const int64_t* __restrict__ local_offs, uint32_t m,
+                                                               int wshift, const int32_t* __restrict__ own_gpos,
+                                                               const int32_t* __restrict__ n_own, int32_t N_cap,
+                                                               uint32_t sentinel, uint32_t* __restrict__ keys,
+                                                               int32_t* __restrict__ pos, int32_t* status) {
+  const int32_t n_all = *n_own;
+  const int32_t n = n_all < N_cap ? n_all : N_cap;
+  if (n_all > N_cap && blockIdx.x == 0 && threadIdx.x == 0 && status) atomicOr(status, 4);  // capacity exceeded
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N_cap; i += gridDim.x * blockDim.x) {
+    if (i < n) {
+      const int32_t gp = own_gpos[i];
+      keys[i] = (uint32_t)(local_offs[(uint32_t)gp % m] + (gids[gp] >> wshift));
+      pos[i] = gp;
+    } else {
+      keys[i] = sentinel;
+      pos[i] = 0;
+    }
+  }
+}
+
 struct TowerPlanWs {
   uint32_t* keys_in;
   int32_t* pos_in;
@@ -820,6 +877,71 @@ int rm_tower_plan(const int64_t* ids, const int64_t* table_offsets, int64_t B, i
   const int upf = rm_tower_units_per_field(B, unit);
   tower_bounds_kernel<<<1, 1024, (m + 1) * sizeof(int32_t), st>>>(sorted_keys, (int32_t)N, table_offsets, m, unit, upf,
                                                                   field_bounds, unit_bounds);
+  RM_LAUNCH_CHECK();
+  return 0;
+}
+
+size_t rm_tower_shard_plan_workspace_bytes(int64_t Ntot, int64_t N_cap) {
+  if (Ntot <= 0 || N_cap <= 0) return 256;
+  size_t sort_bytes = 0, sel_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)N_cap, 0, 32);
+  thrust::counting_iterator<int32_t> counting(0);
+  rm::TowerOwned own{nullptr, nullptr, 1, 0, 0};
+  cub::DeviceSelect::If(nullptr, sel_bytes, counting, (int32_t*)nullptr, (int32_t*)nullptr, (int)Ntot, own);
+  const size_t cubb = sort_bytes > sel_bytes ? sort_bytes : sel_bytes;
+  return rm::align_up((size_t)Ntot * 4, 256) + 2 * rm::align_up((size_t)N_cap * 4, 256) + rm::align_up(cubb, 256) + 256;
+}
+
+// Owner-side plan of the fused backward for row-sharded tables (see rm_shard_plan for the conventions): outputs as
+// rm_tower_plan with keys = owner-local rows and sorted_pos = GLOBAL positions gp = src_rank*(b*m) + p, over the fixed
+// capacity N_cap (entries past the owned count carry the sentinel key and sort last); n_own[1] = owned count.
+// `Bcap` = per-field capacity used to size the work units (rm_tower_units_per_field(Bcap, unit)).
+int rm_tower_shard_plan(const int64_t* gids, int64_t Ntot, int32_t m, int32_t W, int32_t rank, const int64_t* feat_sizes,
+                        const int64_t* local_offsets_m1, int64_t total_local, int64_t N_cap, int64_t Bcap, int32_t unit,
+                        void* workspace, size_t workspace_bytes, uint32_t* sorted_keys, int32_t* sorted_gpos,
+                        int32_t* field_bounds, int32_t* unit_bounds, int32_t* n_own, int32_t* status, void* stream) {
+  using namespace rm;
+  RM_CHECK_ARG(gids && feat_sizes && local_offsets_m1 && workspace && sorted_keys && sorted_gpos && field_bounds &&
+                   unit_bounds && n_own, "null pointer");
+  RM_CHECK_ARG(Ntot > 0 && m > 0 && N_cap > 0 && total_local > 0 && rank >= 0 && rank < W && unit >= BK_TILE && Bcap > 0,
+               "bad shape");
+  RM_UNSUPPORTED(W >= 1 && W <= 8 && (W & (W - 1)) == 0, "world size must be a power of two <= 8");
+  RM_UNSUPPORTED(Ntot < ((int64_t)1 << 31) - 1 && N_cap <= Ntot, "W*B*m must be < 2^31 - 1 and N_cap <= W*B*m");
+  RM_UNSUPPORTED(total_local < ((int64_t)1 << 31), "local rows must be < 2^31");
+  const size_t need = rm_tower_shard_plan_workspace_bytes(Ntot, N_cap);
+  if (workspace_bytes < need) {
+    set_error("rm_tower_shard_plan: workspace %zu < required %zu", workspace_bytes, need);
+    return RM_E_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  char* b = (char*)workspace;
+  int32_t* own_gpos = (int32_t*)b; b += align_up((size_t)Ntot * 4, 256);
+  uint32_t* keys_in = (uint32_t*)b; b += align_up((size_t)N_cap * 4, 256);
+  int32_t* pos_in = (int32_t*)b; b += align_up((size_t)N_cap * 4, 256);
+  void* cub_temp = (void*)b;
+  size_t cub_bytes = (size_t)((char*)workspace + workspace_bytes - b);
+  int wshift = 0;
+  while ((1 << wshift) < W) ++wshift;
+  thrust::counting_iterator<int32_t> counting(0);
+  TowerOwned own{gids, feat_sizes, (uint32_t)m, (int64_t)(W - 1), (int64_t)rank};
+  size_t bytes = cub_bytes;
+  RM_CUDA(cub::DeviceSelect::If(cub_temp, bytes, counting, own_gpos, n_own, (int)Ntot, own, st));
+  count_launch();
+  int end_bit = 1;
+  while (end_bit < 31 && ((int64_t)1 << end_bit) <= total_local) ++end_bit;
+  const uint32_t sentinel = (uint32_t)total_local;  // sorts behind every owned row
+  tower_shard_keys_kernel<<<grid_for(N_cap, 256, 8), 256, 0, st>>>(gids, local_offsets_m1, (uint32_t)m, wshift, own_gpos,
+                                                                  n_own, (int32_t)N_cap, sentinel, keys_in, pos_in, status);
+  RM_LAUNCH_CHECK();
+  bytes = cub_bytes;
+  RM_CUDA(cub::DeviceRadixSort::SortPairs(cub_temp, bytes, (const uint32_t*)keys_in, sorted_keys, (const int32_t*)pos_in,
+                                          sorted_gpos, (int)N_cap, 0, end_bit, st));
+  count_launch();
+  const int upf = rm_tower_units_per_field(Bcap, unit);
+  tower_bounds_local_kernel<<<1, 1024, (m + 1) * sizeof(int32_t), st>>>(sorted_keys, (int32_t)N_cap, local_offsets_m1,
+                                                                        (uint32_t)total_local, m, unit, upf, field_bounds,
+                                                                        unit_bounds);
   RM_LAUNCH_CHECK();
   return 0;
 }

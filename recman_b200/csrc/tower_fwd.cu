@@ -33,10 +33,16 @@ constexpr int TF_WSLOTS = 2;   // W1 field images in flight
 constexpr int TF_PRODUCERS = 256;
 constexpr int TF_THREADS = 320;
 
+constexpr int TF_MAX_PEERS = 8;
+constexpr uint32_t TF_ROW_BITS = 29;  // row code = owner rank << 29 | row inside the owner's table
+constexpr uint32_t TF_ROW_MASK = (1u << TF_ROW_BITS) - 1u;
+
 struct TowerFwdParams {
-  const float* table;
-  const float* scal;  // [rows, 2] = (bias, linear weight), nullable
-  const int64_t* offs;
+  const float* table[TF_MAX_PEERS];  // [rows, k] of every owner rank (W == 1: the one table); peer-mapped memory for W > 1
+  const float* scal[TF_MAX_PEERS];   // [rows, 2] = (bias, linear weight) per owner, nullable
+  const int64_t* offs;               // W == 1: [m+1] global row offsets; W > 1: [m] owner-local first rows
+  const int64_t* feat_sizes;         // W > 1: [m] global table sizes (range check)
+  int W, wshift;
   const int64_t* ids;
   const float* dense;
   const float* lin_dense;
@@ -131,9 +137,14 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tower_fwd_kernel(const TowerFwd
     uint32_t row = TW_NONE;
     if (b < P.B) {
       const int64_t id = P.ids[b * m + f];
-      const int64_t lo = P.offs[f], hi = P.offs[f + 1];
-      if (id >= 0 && id < hi - lo) row = (uint32_t)(lo + id);
-      else if (P.status) atomicOr(P.status, 1);
+      if (P.W == 1) {
+        const int64_t lo = P.offs[f], hi = P.offs[f + 1];
+        if (id >= 0 && id < hi - lo) row = (uint32_t)(lo + id);
+      } else if (id >= 0 && id < P.feat_sizes[f]) {
+        // row-sharded tables: global row id lives on rank id mod W at local row id div W
+        row = ((uint32_t)(id & (P.W - 1)) << TF_ROW_BITS) | (uint32_t)(P.offs[f] + (id >> P.wshift));
+      }
+      if (row == TW_NONE && P.status) atomicOr(P.status, 1);
     }
     sts32(rowidx_base + 4u * idx, row);
   }
@@ -171,15 +182,16 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tower_fwd_kernel(const TowerFwd
         const int r = rg + 32 * i;
         const uint32_t row = lds32(rowidx_base + 4u * (uint32_t)(r * m + f));
         const bool live = row != TW_NONE;
-        const float* src = P.table + (int64_t)(live ? row : 0u) * K + 4 * c8;
+        const float* src = P.table[live ? (row >> TF_ROW_BITS) : 0u] + (int64_t)(live ? (row & TF_ROW_MASK) : 0u) * K + 4 * c8;
 #pragma unroll
         for (int blk = 0; blk < KB; ++blk)
           cp_async16(xs + (uint32_t)blk * 16384u + (uint32_t)i * 4096u, src + 32 * blk, live ? 16u : 0u);
       }
-      if (P.scal && tid < TF_ROWS) {
+      if (P.scal[0] && tid < TF_ROWS) {
         const uint32_t row = lds32(rowidx_base + 4u * (uint32_t)(tid * m + f));
         const bool live = row != TW_NONE;
-        cp_async8(scal_base + (uint32_t)s * 1024u + 8u * tid, P.scal + 2 * (int64_t)(live ? row : 0u), live ? 8u : 0u);
+        cp_async8(scal_base + (uint32_t)s * 1024u + 8u * tid,
+                  P.scal[live ? (row >> TF_ROW_BITS) : 0u] + 2 * (int64_t)(live ? (row & TF_ROW_MASK) : 0u), live ? 8u : 0u);
       }
     };
 
@@ -212,7 +224,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tower_fwd_kernel(const TowerFwd
         fence_proxy_async_smem();
         mbar_arrive(lo_ready(ls));
       }
-      if (P.scal && tid < TF_ROWS) {
+      if (P.scal[0] && tid < TF_ROWS) {
         const float2 sv = lds64f(scal_base + (uint32_t)s * 1024u + 8u * tid);
         bias_acc += sv.x;
         lin_acc += sv.y;
@@ -373,23 +385,25 @@ size_t rm_tower_fwd_workspace_bytes(int32_t m, int32_t k, int32_t N1) {
   return 256 + (size_t)m * 2 * (k / 32) * rm::tower_n1pad(N1) * 128;
 }
 
-int rm_tower_fwd(const float* table, const float* scal, const int64_t* table_offsets, const int64_t* ids,
-                 const float* dense, const float* lin_dense, int32_t lin_dense_stride, int32_t n_dense,
-                 const float* W1, const float* b1, int32_t N1, int64_t B, int32_t m, int32_t k, float* x, int64_t ld,
-                 float* y1, float* fm_out, float* lin_out, float* sum_out, int32_t* status, void* workspace,
-                 size_t workspace_bytes, void* stream) {
+static int tower_fwd_impl(const float* const* tables, const float* const* scals, int W, const int64_t* feat_sizes,
+                          const int64_t* offs, const int64_t* ids, const float* dense, const float* lin_dense,
+                          int32_t lin_dense_stride, int32_t n_dense, const float* W1, const float* b1, int32_t N1,
+                          int64_t B, int32_t m, int32_t k, float* x, int64_t ld, float* y1, float* fm_out,
+                          float* lin_out, float* sum_out, int32_t* status, void* workspace, size_t workspace_bytes,
+                          void* stream, const char* who) {
   using namespace rm;
-  RM_CHECK_ARG(table && table_offsets && ids && W1 && b1 && y1 && workspace, "null pointer");
+  RM_CHECK_ARG(tables && offs && ids && W1 && b1 && y1 && workspace, "null pointer");
   RM_CHECK_ARG(B >= 0 && m > 0 && k > 0 && n_dense >= 0 && N1 > 0, "bad shape");
   RM_CHECK_ARG(n_dense == 0 || dense, "dense pointer missing");
   RM_CHECK_ARG(!x || ld >= (int64_t)m * k + n_dense, "ld smaller than m*k+n_dense");
   RM_UNSUPPORTED(rm_tower_supported(m, k, n_dense, N1), "tower kernels need k in {32, 64}, m <= 64, N1 <= 64");
-  RM_UNSUPPORTED(aligned16(table) && (!x || (aligned16(x) && ld % 4 == 0)) && (!sum_out || aligned16(sum_out)) &&
-                     (!scal || (reinterpret_cast<uintptr_t>(scal) & 7) == 0) && aligned16(workspace),
+  RM_UNSUPPORTED(W >= 1 && W <= TF_MAX_PEERS && (W & (W - 1)) == 0, "world size must be a power of two <= 8");
+  RM_CHECK_ARG(W == 1 || feat_sizes, "feat_sizes missing");
+  RM_UNSUPPORTED((!x || (aligned16(x) && ld % 4 == 0)) && (!sum_out || aligned16(sum_out)) && aligned16(workspace),
                  "tower forward needs 16-byte aligned rows");
   const size_t need = rm_tower_fwd_workspace_bytes(m, k, N1);
   if (workspace_bytes < need) {
-    set_error("rm_tower_fwd: workspace %zu < required %zu", workspace_bytes, need);
+    set_error("%s: workspace %zu < required %zu", who, workspace_bytes, need);
     return RM_E_WORKSPACE;
   }
   if (B == 0) return 0;
@@ -400,7 +414,18 @@ int rm_tower_fwd(const float* table, const float* scal, const int64_t* table_off
   tower_pack_w1t_kernel<<<grid_for((int64_t)m * 2 * KB * N1PAD * 8, 256, 8), 256, 0, st>>>(W1, m, k, N1, N1PAD, wpack);
   RM_LAUNCH_CHECK();
   TowerFwdParams P;
-  P.table = table; P.scal = scal; P.offs = table_offsets; P.ids = ids; P.dense = dense; P.lin_dense = lin_dense;
+  for (int r = 0; r < TF_MAX_PEERS; ++r) {
+    P.table[r] = r < W ? tables[r] : nullptr;
+    P.scal[r] = (r < W && scals) ? scals[r] : nullptr;
+    RM_CHECK_ARG(r >= W || (P.table[r] && aligned16(P.table[r])), "null / misaligned table");
+    RM_CHECK_ARG(r >= W || !scals || (P.scal[r] && (reinterpret_cast<uintptr_t>(P.scal[r]) & 7) == 0),
+                 "null / misaligned k=1 table");
+  }
+  P.W = W;
+  P.wshift = 0;
+  while ((1 << P.wshift) < W) ++P.wshift;
+  P.feat_sizes = feat_sizes;
+  P.offs = offs; P.ids = ids; P.dense = dense; P.lin_dense = lin_dense;
   P.lin_dense_stride = lin_dense_stride; P.wpack = wpack; P.W1 = W1; P.b1 = b1; P.x = x; P.ld = ld; P.y1 = y1;
   P.fm_out = fm_out; P.lin_out = lin_out; P.sum_out = sum_out; P.status = status; P.B = B; P.m = m; P.nd = n_dense;
   P.N1 = N1; P.N1PAD = N1PAD;
@@ -421,6 +446,30 @@ int rm_tower_fwd(const float* table, const float* scal, const int64_t* table_off
   }
   RM_LAUNCH_CHECK();
   return 0;
+}
+
+int rm_tower_fwd(const float* table, const float* scal, const int64_t* table_offsets, const int64_t* ids,
+                 const float* dense, const float* lin_dense, int32_t lin_dense_stride, int32_t n_dense,
+                 const float* W1, const float* b1, int32_t N1, int64_t B, int32_t m, int32_t k, float* x, int64_t ld,
+                 float* y1, float* fm_out, float* lin_out, float* sum_out, int32_t* status, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+  const float* tabs[1] = {table};
+  const float* scs[1] = {scal};
+  return tower_fwd_impl(tabs, scal ? scs : nullptr, 1, nullptr, table_offsets, ids, dense, lin_dense, lin_dense_stride,
+                        n_dense, W1, b1, N1, B, m, k, x, ld, y1, fm_out, lin_out, sum_out, status, workspace,
+                        workspace_bytes, stream, "rm_tower_fwd");
+}
+
+/* Row-sharded tables over NVLink peer memory: row `id` of field f is read from tables[id % W] +
+ * (local_offsets[f] + id / W) * k (scals alike).  tables / scals are HOST arrays of W device pointers. */
+int rm_tower_fwd_p2p(const float* const* tables, const float* const* scals, int32_t W, const int64_t* feat_sizes,
+                     const int64_t* local_offsets, const int64_t* ids, const float* dense, const float* lin_dense,
+                     int32_t lin_dense_stride, int32_t n_dense, const float* W1, const float* b1, int32_t N1, int64_t B,
+                     int32_t m, int32_t k, float* y1, float* fm_out, float* lin_out, float* sum_out, int32_t* status,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  return tower_fwd_impl(tables, scals, W, feat_sizes, local_offsets, ids, dense, lin_dense, lin_dense_stride, n_dense, W1,
+                        b1, N1, B, m, k, nullptr, 0, y1, fm_out, lin_out, sum_out, status, workspace, workspace_bytes,
+                        stream, "rm_tower_fwd_p2p");
 }
 
 }  // extern "C"

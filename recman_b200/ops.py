@@ -718,14 +718,17 @@ def tower_bwd_update(table, scal, plan: TowerPlan, g1, S, g_fm, g_lin, W1, opt: 
     k = S.shape[1]
     N1 = g1.shape[1]
     assert g1.is_contiguous() and S.is_contiguous() and g_fm.is_contiguous() and W1.is_contiguous()
-    assert g1.shape[0] == B and S.shape[0] == B and g_fm.numel() == B and W1.shape[0] >= m * k and W1.shape[1] == N1
-    assert g_lin is None or (g_lin.is_contiguous() and g_lin.numel() == B)
+    # single GPU: one row per sample of the batch; row-sharded: the all-gathered operands of all W*b samples
+    n_s = g1.shape[0]
+    assert (n_s == B or hasattr(plan, "n_own")) and S.shape[0] == n_s and g_fm.numel() == n_s
+    assert W1.shape[0] >= m * k and W1.shape[1] == N1
+    assert g_lin is None or (g_lin.is_contiguous() and g_lin.numel() == n_s)
     dev = g1.device
     dW1 = torch.empty(m * k, N1, dtype=torch.float32, device=dev)
     out_rows = out_scal = None
     if debug:
-        out_rows = torch.zeros(B * m, k, dtype=torch.float32, device=dev)
-        out_scal = torch.zeros(B * m, 2, dtype=torch.float32, device=dev)
+        out_rows = torch.zeros(plan.sorted_pos.numel(), k, dtype=torch.float32, device=dev)
+        out_scal = torch.zeros(plan.sorted_pos.numel(), 2, dtype=torch.float32, device=dev)
     ws_bytes = _C.lib.rm_tower_bwd_workspace_bytes(B, m, plan.unit)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     plan.wait()
@@ -781,3 +784,61 @@ def deepfm_head(y1, fm, lin, w0, W2, b2, w3, b3, labels, act: int, task: int, gr
             task, float(grad_scale), _p(logit), _p(pred), _p(out["loss"]), _p(out["g1"]), _p(out["g"]), _p(out["dW2"]),
             _p(out["db2"]), _p(out["dw3"]), _p(out["dscal"]), _p(out["db1"]), _p(ws), ws_bytes, _stream())
     return out
+
+
+# --------------------------------------------------------------------------- #
+# T'  fused tower over row-sharded tables (NVLink peer memory)
+# --------------------------------------------------------------------------- #
+def tower_fwd_p2p(tab_ptrs, scal_ptrs, k, feat_sizes, local_offs, ids, dense, lin_dense, W1, b1, status=None):
+    """rm_tower_fwd with every row read from its owner's shard.  Returns (y1, fm, lin, S)."""
+    _dev_check(ids)
+    assert ids.dtype == torch.int64 and ids.is_contiguous()
+    B, m = ids.shape
+    W = len(tab_ptrs)
+    n_dense = 0 if dense is None else dense.shape[1]
+    N1 = W1.shape[1]
+    assert W1.shape[0] == m * k + n_dense and W1.is_contiguous() and b1.is_contiguous()
+    dev = ids.device
+    y1 = torch.empty(B, N1, dtype=torch.float32, device=dev)
+    fm = torch.empty(B, dtype=torch.float32, device=dev)
+    lin = torch.empty(B, dtype=torch.float32, device=dev)
+    S = torch.empty(B, k, dtype=torch.float32, device=dev)
+    if dense is not None:
+        dense = _f32c(dense, "dense").contiguous()
+    ld_stride = 1
+    if lin_dense is not None:
+        assert lin_dense.dim() == 1 and lin_dense.numel() == n_dense
+        ld_stride = lin_dense.stride(0) if n_dense > 1 else 1
+    ws_bytes = _C.lib.rm_tower_fwd_workspace_bytes(m, k, N1)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _C.call(
+        "rm_tower_fwd_p2p", _ptr_array(tab_ptrs), None if scal_ptrs is None else _ptr_array(scal_ptrs), W,
+        _p(feat_sizes), _p(local_offs), _p(ids), _p(dense), _p(lin_dense), ld_stride, n_dense, _p(W1), _p(b1), N1, B, m, k,
+        _p(y1), _p(fm), _p(lin), _p(S), _p(status), _p(ws), ws_bytes, _stream(),
+    )
+    return y1, fm, lin, S
+
+
+def tower_shard_plan(gids, W, rank, feat_sizes, local_offs, total_local, n_cap, b_cap, unit: int = TOWER_UNIT,
+                     status=None, side: bool = False) -> TowerPlan:
+    """Owner-side plan of the fused backward over the ids of all ranks (gids [W*b, m])."""
+    _dev_check(gids)
+    assert gids.dtype == torch.int64 and gids.is_contiguous() and gids.dim() == 2
+    Ntot, m = gids.numel(), gids.shape[1]
+    n_cap = int(min(n_cap, Ntot))
+    dev = gids.device
+    upf = _C.lib.rm_tower_units_per_field(int(b_cap), unit)
+    ws_bytes = _C.lib.rm_tower_shard_plan_workspace_bytes(Ntot, n_cap)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    keys = torch.empty(n_cap, dtype=torch.int32, device=dev)
+    pos = torch.empty(n_cap, dtype=torch.int32, device=dev)
+    fb = torch.empty(m + 1, dtype=torch.int32, device=dev)
+    ub = torch.empty(m * (upf + 1), dtype=torch.int32, device=dev)
+    n_own = torch.empty(1, dtype=torch.int32, device=dev)
+    ev = _launch_maybe_side(side, lambda: _C.call(
+        "rm_tower_shard_plan", _p(gids), Ntot, m, W, rank, _p(feat_sizes), _p(local_offs), int(total_local), n_cap,
+        int(b_cap), unit, _p(ws), ws_bytes, _p(keys), _p(pos), _p(fb), _p(ub), _p(n_own), _p(status), _stream(),
+    ))
+    plan = TowerPlan(int(b_cap), m, unit, keys, pos, fb, ub, ws, ev)
+    plan.n_own = n_own
+    return plan

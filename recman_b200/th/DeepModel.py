@@ -222,8 +222,11 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
         every embedding feature one-hot, k in {32, 64}, first hidden layer <= 64 wide, linear features ==
         [sparse..., dense...], single GPU.  The two k=1 tables (``feat_bias_table``, ``linear_w``) then share ONE
         interleaved [rows + n_dense, 2] storage, so an id costs one 8-byte lookup instead of two sector fetches."""
-        if not self.hparams.get("tower", True) or self.shard is not None or inputs.sparse_ids is None:
+        if not self.hparams.get("tower", True) or inputs.sparse_ids is None:
             return None
+        sharded = self.shard is not None
+        if sharded and self.shard.peer is None:
+            return None  # the all-to-all exchange keeps the separate kernels
         k = layer.embedding_size
         if not layer.all_one_hot or not layer.use_bias:
             return None
@@ -233,6 +236,10 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
         hidden0 = dnn.hidden_units[0]
         if hidden0 is None or not ops.tower_supported(lay.m, k, n_dense, int(hidden0)):
             return None
+        if sharded and not (ops.tower_bwd_supported(k, int(hidden0)) and self._fused_opt_config() is not None
+                            and not layer.l2_reg and not linear.l2_reg
+                            and self.hparams.get("embedding_l2_mode", "dense") != "touched"):
+            return None  # sharded training runs only the in-kernel update: everything else keeps the separate kernels
         want = self.feat_dict.sparse_feats + self.feat_dict.dense_feats
         if [f.name for f in linear.linear_feats] != [f.name for f in want]:
             return None
@@ -242,7 +249,8 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
         if "scal_storage" not in cache:
             if bname in self.variables or wname in self.variables:
                 return None  # the k=1 tables already exist in the separate layout
-            st = torch.zeros(total + n_dense, 2, dtype=torch.float32, device=self.device)
+            st = (self.shard.alloc((total + n_dense, 2)) if sharded
+                  else torch.zeros(total + n_dense, 2, dtype=torch.float32, device=self.device))
             self.variables[bname] = torch.nn.Parameter(st[:total, 0], requires_grad=True)
             self.variables[wname] = torch.nn.Parameter(st[:, 1:2], requires_grad=True)
             cache["scal_storage"] = st
@@ -259,15 +267,27 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
         if not training:  # inference-time per-id weights (layers.py:338-345, 426-437) are added to linear_w
             extra = np.concatenate([np.asarray(f.weights, dtype=np.float32).reshape(-1) for f in linear.linear_feats])
             if np.any(extra != 0):
+                if sharded:
+                    raise NotImplementedError("row-sharded tables: inference-time feature weights are not supported")
                 scal_fwd = scal.clone()
                 scal_fwd[:, 1] += torch.from_numpy(extra).to(scal.device)
         fused = getattr(self, "_fused_opt", None)
         if fused is not None and (layer.l2_reg or linear.l2_reg or getattr(table, "rm_l2_touched", 0.0)):
             fused = None
+        if sharded:
+            from .dist import P2PTowerFunction
+
+            if scal_fwd is not scal:
+                raise NotImplementedError("row-sharded tables: inference-time feature weights are not supported")
+            y1, fm, lin = P2PTowerFunction.apply(table, scal, bias_param, W_lin, W1, b1, self.shard, self._status(),
+                                                 inputs.sparse_ids, dense, fused, torch.is_grad_enabled())
+            if add_w0:
+                lin = lin + self.variables[f"{linear.prefix}linear_w0"]
+            return y1, fm, lin
         from ..autograd import TowerFunction
 
         y1, fm, lin = TowerFunction.apply(table, scal, scal_fwd, bias_param, W_lin, W1, b1, lay.runs[0].offsets, total,
-                                          self._status(), inputs.sparse_ids, dense, fused)
+                                          self._status(), inputs.sparse_ids, dense, fused, torch.is_grad_enabled())
         if add_w0:
             lin = lin + self.variables[f"{linear.prefix}linear_w0"]
         return y1, fm, lin

@@ -38,7 +38,7 @@ import torch.distributed as dist
 from torch.autograd import Function
 
 __all__ = ["ShardPlan", "Exchange", "build_exchange", "shard_model", "ShardedFrontEndFunction", "allreduce_dense",
-           "PeerMemory", "P2PFrontEndFunction"]
+           "PeerMemory", "P2PFrontEndFunction", "P2PTowerFunction"]
 
 
 class _DevicePointer:
@@ -382,6 +382,86 @@ class P2PFrontEndFunction(Function):
         if want_lin:
             attach_sparse_grad(ctx.W_lin, ops.SparseGrad(sp.uniq_rows, ol, sp.n_unique))
         return (None,) * 11
+
+
+class P2PTowerFunction(Function):
+    """Row-sharded version of autograd.TowerFunction (fused DeepFM tower): ids -> (y1, fm, lin).
+
+    forward   all-gather of the ids (the step's cross-rank barrier) ; ONE kernel per rank (rm_tower_fwd_p2p) reads every
+              row from its owner - local HBM or NVLink - and runs FM + first-order + the first DNN layer on it
+    backward  all-gathers of the per-sample operands (g1 [b,32], S [b,64], g_fm, g_lin: 392 B per sample instead of
+              m gradient rows of 256 B) ; the owner forms the gradient rows of its own positions itself and applies the
+              update in place (rm_tower_bwd_update over rm_tower_shard_plan) ; dW1 partials join the dense all-reduce.
+    Training only with the in-kernel update (k = 64, first hidden layer 32)."""
+
+    @staticmethod
+    def forward(ctx, table, scal, bias_param, W_lin, W1, b1, plan: ShardPlan, status, ids, dense, fused_opt,
+                grad_mode=True):
+        from .. import ops
+
+        b, m = ids.shape
+        k = table.shape[1]
+        W, dev, peer = plan.world, table.device, plan.peer
+        total = plan.total_local
+        n_dense = 0 if dense is None else dense.shape[1]
+        ids = ids.contiguous()
+        need_grad = bool(grad_mode) and any(ctx.needs_input_grad)
+        if need_grad and (fused_opt is None or not ops.tower_bwd_supported(k, W1.shape[1])):
+            raise NotImplementedError("row-sharded fused tower: training needs the in-kernel sparse update "
+                                      "(fit_on_batch; no L2 on the tables) with k = 64 and a first hidden layer of 32")
+        gids = None
+        if need_grad:
+            # every rank has finished the previous step's table update once this returns (barrier for the peer reads)
+            gids = torch.empty(W * b, m, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(gids, ids, group=plan.group)
+        lin_dense = scal[total:, 1] if n_dense else None
+        y1, fm, lin, S = ops.tower_fwd_p2p(peer.ptrs_of(table), peer.ptrs_of(scal), k, plan.feat_sizes_on(dev),
+                                           plan.offsets_on(dev), ids, dense, lin_dense, W1, b1, status=status)
+        ctx.tp = None
+        if need_grad:
+            n_cap = plan.capacity(b)
+            ctx.tp = ops.tower_shard_plan(gids, W, plan.rank, plan.feat_sizes_on(dev), plan.offsets_on(dev), total, n_cap,
+                                          (n_cap + m - 1) // m, status=status, side=True)
+        ctx.plan, ctx.status, ctx.fused_opt = plan, status, fused_opt
+        ctx.table, ctx.scal, ctx.W_lin = table, scal, W_lin
+        ctx.n_dense = n_dense
+        ctx.save_for_backward(S, dense, W1)
+        ctx.b, ctx.m, ctx.k = b, m, k
+        ctx.set_materialize_grads(False)
+        return y1, fm.reshape(-1, 1), lin.reshape(-1, 1)
+
+    @staticmethod
+    def backward(ctx, dy1, dfm, dlin):
+        from .. import ops
+
+        S, dense, W1 = ctx.saved_tensors
+        plan: ShardPlan = ctx.plan
+        b, m, k = ctx.b, ctx.m, ctx.k
+        W, dev = plan.world, S.device
+        N1 = W1.shape[1]
+        g1 = torch.zeros(b, N1, dtype=torch.float32, device=dev) if dy1 is None else dy1.contiguous()
+        g_fm = torch.zeros(b, dtype=torch.float32, device=dev) if dfm is None else dfm.reshape(-1).contiguous()
+        g_lin = torch.zeros(b, dtype=torch.float32, device=dev) if dlin is None else dlin.reshape(-1).contiguous()
+        # per-sample operands of every rank: the owners form the gradient rows themselves
+        g1_all = torch.empty(W * b, N1, dtype=torch.float32, device=dev)
+        S_all = torch.empty(W * b, k, dtype=torch.float32, device=dev)
+        gfm_all = torch.empty(W * b, dtype=torch.float32, device=dev)
+        glin_all = torch.empty(W * b, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(g1_all, g1, group=plan.group)
+        dist.all_gather_into_tensor(S_all, S, group=plan.group)
+        dist.all_gather_into_tensor(gfm_all, g_fm, group=plan.group)
+        dist.all_gather_into_tensor(glin_all, g_lin, group=plan.group)
+        total = plan.total_local
+        if ctx.n_dense:
+            ctx.W_lin.rm_dense_tail = (total, dense.t() @ g_lin)  # replicated: all-reduced by the optimizer
+        kind, lr = ctx.fused_opt
+        tp, ctx.tp = ctx.tp, None
+        dW1 = torch.empty(W1.shape, dtype=torch.float32, device=dev)
+        dW1[: m * k] = ops.tower_bwd_update(ctx.table.data, ctx.scal[:total], tp, g1_all, S_all, gfm_all, glin_all, W1.data,
+                                            kind, lr, status=ctx.status)
+        if ctx.n_dense:
+            torch.mm(dense.t(), g1, out=dW1[m * k :])
+        return (None, None, None, None, dW1, g1.sum(0)) + (None,) * 6
 
 
 def allreduce_dense(grads: List[torch.Tensor], group=None) -> None:

@@ -33,6 +33,7 @@ def main():
 
     # ---- single-GPU reference on the global batch (same on every rank) ----
     ref = DeepFM(fd, **kw)
+    ref.hparams["tower"] = False  # gradient-level comparison: the separate kernels emit the sparse gradients
     batches = [pu.synth_batch(fd, b, seed=100 + r) for r in range(world)]
     Xg = {n: np.concatenate([bt[0][n] for bt in batches]) for n in Xr}
     yg = np.concatenate([bt[1] for bt in batches])
@@ -43,6 +44,7 @@ def main():
 
     # ---- sharded model ----
     model = DeepFM(fd, **kw)
+    model.hparams["tower"] = False
     mode = os.environ.get("DIST_MODE", "auto")
     rdist.shard_model(model, world, rank, mode=mode)
     with torch.no_grad():
@@ -114,9 +116,15 @@ def main():
         model.check_ids()
         assert torch.isfinite(l1).all() and torch.isfinite(l2).all() and float(l2) < float(l1) + 1e-3, (l1, l2)
         dist.barrier()
+    # the fused tower path (k = 64, peer memory): logits and every parameter after one step, sharded == single GPU
+    tower_msg = ""
+    if model.shard.peer is not None:
+        import bench
+
+        tower_msg = " | tower: " + bench.sharded_parity_check(world, rank, torch.device("cuda", local_rank))
     if rank == 0:
         print(f"dist_check ok: world={world} k={k} mode={'p2p' if model.shard.peer is not None else 'a2a'} "
-              f"sharded DeepFM == single-GPU on the global batch", flush=True)
+              f"sharded DeepFM == single-GPU on the global batch{tower_msg}", flush=True)
     dist.barrier()
     torch.cuda.synchronize()
     sys.stdout.flush()
