@@ -420,13 +420,15 @@ def measure(args, wname, world, rank, local_rank, dev, primary=True):
                        "optimizer": "adam (fresh per batch, as the reference)", "l2_flush":
                        "inputs larger than L2: tables %.1f GB, 8 rotating id batches" % (m * rows * k * 4 / 1e9),
                        "parallelism": ("single GPU" if world == 1 else f"row-sharded tables x{world} "
-                                       f"({'NVLink peer-memory gather/reduce' if model.shard.peer is not None else 'NCCL all-to-all'})"
+                                       f"({'NVLink peer-memory row reads, owner-side update' if model.shard.peer is not None else 'NCCL all-to-all'})"
                                        " + DP dense all-reduce"),
                        "step_launch": ("CUDA graph replay" if graphed else "eager"),
                        "timing": f"median of {blocks} blocks of {steps} steps; each block bracketed by barrier + "
                                  "synchronize, CUDA events, max over ranks",
-                       "front_end": ("fused tower: rm_tower_fwd / rm_tower_bwd_update (tcgen05)"
-                                     if "rm_tower_fwd" in kernels else "rm_gather_fm_fwd + separate backward kernels")},
+                       "front_end": ("fused tower: rm_tower_fwd / rm_tower_bwd_update (tcgen05)" if "rm_tower_fwd" in kernels
+                                     else "fused tower over peer memory: rm_tower_fwd_p2p / rm_tower_shard_plan / "
+                                          "rm_tower_bwd_update (tcgen05)" if "rm_tower_fwd_p2p" in kernels
+                                     else "rm_gather_fm_fwd + separate backward kernels")},
             "clocks": clocks,
             "block_ms": [round(v, 3) for v in block_ms],
             "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "ms_per_step": round(e2e_ms_step, 4),
@@ -547,10 +549,22 @@ def sharded_parity_check(world, rank, dev, k=64, b=256):
                 p.data[plan.total_local :] = gten[total:]
         else:
             p.data.copy_(gten)
+    # the no_grad forward below reads the peers' shards and has no collective in front of it: every rank must have
+    # filled its shard first (inside a training step the ids all-gather is that barrier)
+    torch.cuda.synchronize()
+    dist.barrier()
+    errs = []  # collected, not raised: a rank that leaves early would strand the others in the step's collectives
+
+    def check(what, got, exp, atol):
+        try:
+            torch.testing.assert_close(got, exp, rtol=1e-5, atol=atol)
+        except AssertionError as exc:
+            errs.append(f"{what}: " + " ".join(str(exc).split())[:200])
+
     with torch.no_grad():
         lg = ref._out(gi, training=True)
         ll = model._out(li, training=True)
-    torch.testing.assert_close(ll, lg[rank * b : (rank + 1) * b], rtol=1e-5, atol=2e-6)
+    check("logits", ll, lg[rank * b : (rank + 1) * b], 2e-6)
     ref.fit_on_batch(gi, None)
     model.fit_on_batch(li, None)
     torch.cuda.synchronize()
@@ -561,15 +575,16 @@ def sharded_parity_check(world, rank, dev, k=64, b=256):
             for f, rows in enumerate(rows_of):
                 lo = plan.local_offsets[f]
                 exp = gten[rows.to(dev)]
-                torch.testing.assert_close(p.data[lo : lo + rows.numel()], exp, rtol=1e-5,
-                                           atol=1e-5 * max(float(exp.abs().max()) if exp.numel() else 0.0, 1e-3),
-                                           msg=lambda m_: f"{name}[table {f}]: {m_}")
+                check(f"{name}[table {f}]", p.data[lo : lo + rows.numel()], exp,
+                      1e-5 * max(float(exp.abs().max()) if exp.numel() else 0.0, 1e-3))
         else:
-            torch.testing.assert_close(p.data, gten, rtol=1e-5, atol=1e-5 * max(float(gten.abs().max()), 1e-3),
-                                       msg=lambda m_: f"{name}: {m_}")
-    dist.barrier()
+            check(name, p.data, gten, 1e-5 * max(float(gten.abs().max()), 1e-3))
+    bad = torch.tensor([len(errs)], dtype=torch.int64, device=dev)
+    dist.all_reduce(bad)
     del model, ref
     torch.cuda.empty_cache()
+    if int(bad.item()):  # same verdict on every rank
+        raise AssertionError(f"sharded parity: {int(bad.item())} mismatches over all ranks; rank {rank}: {errs[:3]}")
     return f"ok: row-sharded DeepFM x{world} (k={k}, b={b}/rank) == single-GPU on the global batch: logits 1e-5, all parameters after one step 1e-5"
 
 

@@ -392,7 +392,7 @@ int rm_tower_bwd_update(float* table, float* scal, const uint32_t* sorted_keys,
 /* Row-sharded tables (row r of a table on rank r mod W at local row r div W) over NVLink peer memory:
  * rm_tower_fwd_p2p = rm_tower_fwd with every row read from its owner (tables / scals: HOST arrays of W device
  * pointers into the ranks' cudaIpc-mapped shards; feat_sizes [m] global sizes, local_offsets [m] owner-local first
- * rows); rm_tower_shard_plan = the owner-side rm_tower_plan over the ids of ALL ranks (gids [W*b*m], rank-major):
+ * rows); rm_tower_shard_plan = the owner-side rm_tower_plan over the ids of ALL ranks (gids [W*b*m] int32, rank-major):
  * owned entries in ascending global position gp = src_rank*(b*m) + p, keyed by owner-local row, sorted, cut into
  * units (capacity N_cap, *status |= 4 when exceeded; Bcap sizes the unit grid).  rm_tower_bwd_update then runs on the
  * owner with B = Bcap and g1 / S / g_fm / g_lin holding the all-gathered per-sample operands of all W*b samples. */
@@ -403,7 +403,7 @@ int rm_tower_fwd_p2p(const float* const* tables, const float* const* scals, int3
                      int32_t k, float* y1, float* fm_out, float* lin_out, float* sum_out,
                      int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 size_t rm_tower_shard_plan_workspace_bytes(int64_t Ntot, int64_t N_cap);
-int rm_tower_shard_plan(const int64_t* gids, int64_t Ntot, int32_t m, int32_t W, int32_t rank,
+int rm_tower_shard_plan(const int32_t* gids, int64_t Ntot, int32_t m, int32_t W, int32_t rank,
                         const int64_t* feat_sizes, const int64_t* local_offsets, int64_t total_local,
                         int64_t N_cap, int64_t Bcap, int32_t unit, void* workspace,
                         size_t workspace_bytes, uint32_t* sorted_keys, int32_t* sorted_gpos,

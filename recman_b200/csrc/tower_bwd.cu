@@ -780,7 +780,7 @@ __global__ void __launch_bounds__(160, 1) umma_probe_kernel(const float* __restr
 // ---- owner-side plan for row-sharded tables: from the ids of ALL ranks (gids [W*b, m], rank-major) keep the entries
 // this rank owns (id mod W == rank) in ascending global position, key them by owner-local row, sort
 struct TowerOwned {
-  const int64_t* gids;
+  const int32_t* gids;
   const int64_t* feat_sizes;
   uint32_t m;
   int64_t wmask, rank;
@@ -790,7 +790,7 @@ struct TowerOwned {
   }
 };
 
-__global__ void __launch_bounds__(256) tower_shard_keys_kernel(const int64_t* __restrict__ gids,
+__global__ void __launch_bounds__(256) tower_shard_keys_kernel(const int32_t* __restrict__ gids,
                                                                const int64_t* __restrict__ local_offs, uint32_t m,
                                                                int wshift, const int32_t* __restrict__ own_gpos,
                                                                const int32_t* __restrict__ n_own, int32_t N_cap,
@@ -802,7 +802,7 @@ __global__ void __launch_bounds__(256) tower_shard_keys_kernel(const int64_t* __
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N_cap; i += gridDim.x * blockDim.x) {
     if (i < n) {
       const int32_t gp = own_gpos[i];
-      keys[i] = (uint32_t)(local_offs[(uint32_t)gp % m] + (gids[gp] >> wshift));
+      keys[i] = (uint32_t)(local_offs[(uint32_t)gp % m] + ((int64_t)gids[gp] >> wshift));
       pos[i] = gp;
     } else {
       keys[i] = sentinel;
@@ -896,8 +896,9 @@ size_t rm_tower_shard_plan_workspace_bytes(int64_t Ntot, int64_t N_cap) {
 // Owner-side plan of the fused backward for row-sharded tables (see rm_shard_plan for the conventions): outputs as
 // rm_tower_plan with keys = owner-local rows and sorted_pos = GLOBAL positions gp = src_rank*(b*m) + p, over the fixed
 // capacity N_cap (entries past the owned count carry the sentinel key and sort last); n_own[1] = owned count.
+// gids are int32 (the all-gather moves half the bytes of the reference's int64 ids; table sizes are < 2^31).
 // `Bcap` = per-field capacity used to size the work units (rm_tower_units_per_field(Bcap, unit)).
-int rm_tower_shard_plan(const int64_t* gids, int64_t Ntot, int32_t m, int32_t W, int32_t rank, const int64_t* feat_sizes,
+int rm_tower_shard_plan(const int32_t* gids, int64_t Ntot, int32_t m, int32_t W, int32_t rank, const int64_t* feat_sizes,
                         const int64_t* local_offsets_m1, int64_t total_local, int64_t N_cap, int64_t Bcap, int32_t unit,
                         void* workspace, size_t workspace_bytes, uint32_t* sorted_keys, int32_t* sorted_gpos,
                         int32_t* field_bounds, int32_t* unit_bounds, int32_t* n_own, int32_t* status, void* stream) {

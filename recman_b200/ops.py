@@ -192,10 +192,12 @@ class SegmentPlan:
 _side_streams = {}
 
 
-def _launch_maybe_side(side: bool, launch):
+def _launch_maybe_side(side: bool, launch, tensors=()):
     """Run ``launch()`` (kernel launches only, every buffer already allocated) on the current stream, or - the plan
     depends on the ids alone - on a side stream forked from it, so that it overlaps the forward.  Returns the event to
-    wait for, or None."""
+    wait for, or None.  ``tensors``: every buffer the launch touches; each is recorded on the side stream so that the
+    caching allocator does not hand its memory to the main stream while the side stream still uses it (an all-gathered
+    id buffer dropped at the end of the caller's forward, a plan dropped without a backward)."""
     if not side:
         launch()
         return None
@@ -209,6 +211,9 @@ def _launch_maybe_side(side: bool, launch):
         launch()
         ev = torch.cuda.Event()
         ev.record(st)
+    for t in tensors:
+        if t is not None:
+            t.record_stream(st)
     return ev
 
 
@@ -230,7 +235,7 @@ def segment_plan(ids, table_offsets, total_rows, side: bool = False, status=None
     ev = _launch_maybe_side(side, lambda: _C.call(
         "rm_segment_plan", _p(ids), _p(table_offsets), N, m, int(total_rows), _p(ws), ws_bytes, _p(sorted_pos),
         _p(seg_start), _p(uniq_rows), _p(n_unique), _p(status), _stream(),
-    ))
+    ), (ids, table_offsets, ws, sorted_pos, seg_start, uniq_rows, n_unique, status))
     return SegmentPlan(N, m, sorted_pos, seg_start, uniq_rows, n_unique, ws, ev)
 
 
@@ -591,7 +596,7 @@ def shard_plan(gids, W, rank, feat_sizes, local_offs, total_local, n_cap, status
     ev = _launch_maybe_side(side, lambda: _C.call(
         "rm_shard_plan", _p(gids), Ntot, m, W, rank, _p(feat_sizes), _p(local_offs), int(total_local), n_cap, _p(ws),
         ws_bytes, _p(sorted_gpos), _p(seg_start), _p(uniq_rows), _p(n_unique), _p(n_own), _p(status), _stream(),
-    ))
+    ), (gids, feat_sizes, local_offs, ws, sorted_gpos, seg_start, uniq_rows, n_unique, n_own, status))
     plan = SegmentPlan(n_cap, 1, sorted_gpos, seg_start, uniq_rows, n_unique, ws, ev)
     plan.n_own = n_own
     return plan
@@ -705,7 +710,7 @@ def tower_plan(ids, table_offsets, total_rows, unit: int = TOWER_UNIT, status=No
     ev = _launch_maybe_side(side, lambda: _C.call(
         "rm_tower_plan", _p(ids), _p(table_offsets), B, m, int(total_rows), unit, _p(ws), ws_bytes, _p(keys), _p(pos),
         _p(fb), _p(ub), _p(status), _stream(),
-    ))
+    ), (ids, table_offsets, ws, keys, pos, fb, ub, status))
     return TowerPlan(B, m, unit, keys, pos, fb, ub, ws, ev)
 
 
@@ -823,7 +828,7 @@ def tower_shard_plan(gids, W, rank, feat_sizes, local_offs, total_local, n_cap, 
                      status=None, side: bool = False) -> TowerPlan:
     """Owner-side plan of the fused backward over the ids of all ranks (gids [W*b, m])."""
     _dev_check(gids)
-    assert gids.dtype == torch.int64 and gids.is_contiguous() and gids.dim() == 2
+    assert gids.dtype == torch.int32 and gids.is_contiguous() and gids.dim() == 2
     Ntot, m = gids.numel(), gids.shape[1]
     n_cap = int(min(n_cap, Ntot))
     dev = gids.device
@@ -838,7 +843,7 @@ def tower_shard_plan(gids, W, rank, feat_sizes, local_offs, total_local, n_cap, 
     ev = _launch_maybe_side(side, lambda: _C.call(
         "rm_tower_shard_plan", _p(gids), Ntot, m, W, rank, _p(feat_sizes), _p(local_offs), int(total_local), n_cap,
         int(b_cap), unit, _p(ws), ws_bytes, _p(keys), _p(pos), _p(fb), _p(ub), _p(n_own), _p(status), _stream(),
-    ))
+    ), (gids, feat_sizes, local_offs, ws, keys, pos, fb, ub, n_own, status))
     plan = TowerPlan(int(b_cap), m, unit, keys, pos, fb, ub, ws, ev)
     plan.n_own = n_own
     return plan

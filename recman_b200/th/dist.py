@@ -412,8 +412,11 @@ class P2PTowerFunction(Function):
         gids = None
         if need_grad:
             # every rank has finished the previous step's table update once this returns (barrier for the peer reads)
-            gids = torch.empty(W * b, m, dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(gids, ids, group=plan.group)
+            # (int32: half the bytes of the reference's int64 ids; a table has < 2^31 rows, and an id outside int32 is
+            # outside its table anyway - it is clamped to -1 = "invalid")
+            ids32 = torch.where((ids >= 0) & (ids < 2 ** 31), ids, torch.full_like(ids, -1)).to(torch.int32)
+            gids = torch.empty(W * b, m, dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(gids, ids32, group=plan.group)
         lin_dense = scal[total:, 1] if n_dense else None
         y1, fm, lin, S = ops.tower_fwd_p2p(peer.ptrs_of(table), peer.ptrs_of(scal), k, plan.feat_sizes_on(dev),
                                            plan.offsets_on(dev), ids, dense, lin_dense, W1, b1, status=status)

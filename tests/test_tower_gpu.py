@@ -389,3 +389,91 @@ def test_c5_shape_rows_indices_and_gradients():
     exp_sc = cs2[torch.from_numpy(closing + 1).cuda()] - cs2[torch.from_numpy(starts).cuda()]
     assert_close(out_scal[torch.from_numpy(closing).cuda()], exp_sc, atol_scale=1e-5, msg="k=1 gradients")
     assert_close(dW1, gathered.double().t() @ g1.cuda().double(), atol_scale=1e-5, msg="dW1")
+
+
+def _shard_tables(s, W):
+    """Cyclic row sharding of the test tables: rank r keeps rows r, r+W, ... of every table (local row = row // W)."""
+    m = s["m"]
+    sizes = [int(s["offs"][f + 1] - s["offs"][f]) for f in range(m)]
+    local_sizes = [(v + W - 1) // W for v in sizes]
+    loffs = np.concatenate([[0], np.cumsum(local_sizes)])
+    total_local = int(loffs[-1])
+    tabs, scals = [], []
+    for r in range(W):
+        T = torch.zeros(total_local, s["k"])
+        Sc = torch.zeros(total_local, 2)
+        for f in range(m):
+            rows = torch.arange(r, max(sizes[f], r), W)
+            T[loffs[f] : loffs[f] + rows.numel()] = s["table"][int(s["offs"][f]) + rows]
+            Sc[loffs[f] : loffs[f] + rows.numel()] = s["scal"][int(s["offs"][f]) + rows]
+        tabs.append(T.cuda())
+        scals.append(Sc.cuda())
+    return sizes, loffs, total_local, tabs, scals
+
+
+@pytest.mark.parametrize("W", [2, 4, 8])
+def test_tower_forward_sharded_rows_from_their_owners(W):
+    """rm_tower_fwd_p2p with the W shards living on one device: same outputs as the unsharded kernel, bit for bit
+    (the rows are the same rows, wherever they live), including tables with fewer rows than ranks."""
+    ops = _ops()
+    sizes, k, B, nd, N1 = [50, 7, 1000, 3, 200, 31, 2, 90, 1], 64, 300, 5, 32
+    s = _setup(sizes, k, B, nd, N1, seed=4)
+    szs, loffs, total_local, tabs, scals = _shard_tables(s, W)
+    dev = lambda t: None if t is None else t.cuda()
+    st = ops.new_status("cuda")
+    y1, fm, lin, S, _ = ops.tower_fwd(dev(s["table"]), dev(s["scal"]), dev(s["offs"]), dev(s["ids"]), dev(s["dense"]),
+                                      dev(s["lin_dense"]), dev(s["W1"]), dev(s["b1"]), status=st)
+    y1p, fmp, linp, Sp = ops.tower_fwd_p2p([t.data_ptr() for t in tabs], [t.data_ptr() for t in scals], k,
+                                           torch.tensor(szs, dtype=torch.int64).cuda(),
+                                           torch.tensor(loffs[:-1], dtype=torch.int64).cuda(), dev(s["ids"]),
+                                           dev(s["dense"]), dev(s["lin_dense"]), dev(s["W1"]), dev(s["b1"]), status=st)
+    torch.cuda.synchronize()
+    assert int(st.item()) == 0
+    assert torch.equal(y1p, y1) and torch.equal(fmp, fm) and torch.equal(linp, lin) and torch.equal(Sp, S)
+
+
+@pytest.mark.parametrize("W", [2, 4])
+def test_tower_backward_sharded_owner_view(W):
+    """Every owner runs rm_tower_shard_plan + rm_tower_bwd_update on its shard over the ids / per-sample operands of all
+    W ranks (here: one device); together the shards receive the update the unsharded kernel applies to the full table,
+    and the owners' dW1 partials add up to the unsharded dW1."""
+    from recman_b200 import _C
+
+    ops = _ops()
+    sizes, k, b, nd, N1 = [50, 7, 1000, 3, 200, 31, 2, 90, 1], 64, 200, 0, 32
+    B = W * b  # global batch: rank r owns samples [r*b, (r+1)*b)
+    s = _setup(sizes, k, B, nd, N1, seed=8)
+    m = s["m"]
+    szs, loffs, total_local, tabs, scals = _shard_tables(s, W)
+    g = torch.Generator().manual_seed(5)
+    g1 = (torch.randn(B, N1, generator=g) * 1e-2).cuda()
+    g_fm = (torch.randn(B, generator=g) * 1e-2).cuda()
+    g_lin = (torch.randn(B, generator=g) * 1e-2).cuda()
+    st = ops.new_status("cuda")
+    # unsharded reference run of the same kernels
+    table, scal = s["table"].cuda(), s["scal"].cuda()
+    _, _, _, S, _ = ops.tower_fwd(table, scal, s["offs"].cuda(), s["ids"].cuda(), None, None, s["W1"].cuda(), s["b1"].cuda(),
+                                  status=st)
+    plan = ops.tower_plan(s["ids"].cuda(), s["offs"].cuda(), s["total"], unit=256, status=st)
+    dW1 = ops.tower_bwd_update(table, scal, plan, g1, S, g_fm, g_lin, s["W1"].cuda(), _C.OPT_KINDS["gd"], 0.5, status=st)
+    # owners
+    gids = s["ids"].to(torch.int32).cuda()
+    dW1_sum = torch.zeros_like(dW1, dtype=torch.float64)
+    fs = torch.tensor(szs, dtype=torch.int64).cuda()
+    lo = torch.tensor(loffs[:-1], dtype=torch.int64).cuda()
+    for r in range(W):
+        n_cap = B * m
+        tp = ops.tower_shard_plan(gids, W, r, fs, lo, total_local, n_cap, B, unit=256, status=st)
+        dW1_r = ops.tower_bwd_update(tabs[r], scals[r], tp, g1, S, g_fm, g_lin, s["W1"].cuda(), _C.OPT_KINDS["gd"], 0.5,
+                                     status=st)
+        dW1_sum += dW1_r.double()
+    torch.cuda.synchronize()
+    assert int(st.item()) == 0
+    assert_close(dW1_sum, dW1.double(), atol_scale=1e-5, msg="dW1 partials")
+    for r in range(W):
+        for f in range(m):
+            rows = torch.arange(r, max(szs[f], r), W)
+            got = tabs[r][loffs[f] : loffs[f] + rows.numel()].cpu()
+            exp = table[int(s["offs"][f]) + rows.cuda()].cpu()
+            assert torch.equal(got, exp), (r, f)  # same positions, same order, same arithmetic: bit-identical rows
+            assert torch.equal(scals[r][loffs[f] : loffs[f] + rows.numel()].cpu(), scal[int(s["offs"][f]) + rows.cuda()].cpu())
