@@ -446,15 +446,17 @@ class TowerFunction(Function):
         need_grad = bool(grad_mode) and any(ctx.needs_input_grad)
         use_bk = need_grad and fused_opt is not None and ops.tower_bwd_supported(k, N1)
         lin_dense = scal_fwd[total_rows:, 1] if n_dense else None
+        ctx.plan = None
+        if need_grad:
+            # the plans need the ids only: forked onto the side stream BEFORE the forward kernel is enqueued (the side
+            # stream waits for what the main stream holds at the fork), so that the sort runs under the forward
+            ctx.plan = (ops.tower_plan(ids, offsets, total_rows, status=status, side=True) if use_bk
+                        else ops.segment_plan(ids, offsets, total_rows, side=True, status=status))
         y1, fm, lin, S, x = ops.tower_fwd(table, scal_fwd[:total_rows], offsets, ids, dense, lin_dense, W1, b1,
                                           want_x=need_grad and not use_bk, status=status)
         ctx.use_bk, ctx.fused_opt = use_bk, fused_opt
         ctx.table, ctx.scal, ctx.bias_param, ctx.W_lin = table, scal, bias_param, W_lin
         ctx.total_rows, ctx.n_dense, ctx.status = total_rows, n_dense, status
-        ctx.plan = None
-        if need_grad:  # the plans need the ids only: built on the side stream, under the forward
-            ctx.plan = (ops.tower_plan(ids, offsets, total_rows, status=status, side=True) if use_bk
-                        else ops.segment_plan(ids, offsets, total_rows, side=True, status=status))
         ctx.save_for_backward(x, S, ids, dense, W1)
         ctx.set_materialize_grads(False)
         return y1, fm.reshape(-1, 1), lin.reshape(-1, 1)

@@ -192,7 +192,17 @@ class SegmentPlan:
 _side_streams = {}
 
 
-def _launch_maybe_side(side: bool, launch, tensors=()):
+def side_stream() -> "torch.cuda.Stream":
+    """The side stream paired with the current stream (plans that depend on the ids alone run on it)."""
+    cur = torch.cuda.current_stream()
+    key = (cur.device.index, cur.cuda_stream)
+    st = _side_streams.get(key)
+    if st is None:
+        st = _side_streams[key] = torch.cuda.Stream(device=cur.device)
+    return st
+
+
+def _launch_maybe_side(side: bool, launch, tensors=(), fork: bool = True):
     """Run ``launch()`` (kernel launches only, every buffer already allocated) on the current stream, or - the plan
     depends on the ids alone - on a side stream forked from it, so that it overlaps the forward.  Returns the event to
     wait for, or None.  ``tensors``: every buffer the launch touches; each is recorded on the side stream so that the
@@ -202,11 +212,9 @@ def _launch_maybe_side(side: bool, launch, tensors=()):
         launch()
         return None
     cur = torch.cuda.current_stream()
-    key = (cur.device.index, cur.cuda_stream)
-    st = _side_streams.get(key)
-    if st is None:
-        st = _side_streams[key] = torch.cuda.Stream(device=cur.device)
-    st.wait_stream(cur)
+    st = side_stream()
+    if fork:  # fork=False: the caller already forked the side stream and queued work on it that `launch` depends on
+        st.wait_stream(cur)
     with torch.cuda.stream(st):
         launch()
         ev = torch.cuda.Event()
@@ -825,7 +833,7 @@ def tower_fwd_p2p(tab_ptrs, scal_ptrs, k, feat_sizes, local_offs, ids, dense, li
 
 
 def tower_shard_plan(gids, W, rank, feat_sizes, local_offs, total_local, n_cap, b_cap, unit: int = TOWER_UNIT,
-                     status=None, side: bool = False) -> TowerPlan:
+                     status=None, side: bool = False, fork: bool = True) -> TowerPlan:
     """Owner-side plan of the fused backward over the ids of all ranks (gids [W*b, m])."""
     _dev_check(gids)
     assert gids.dtype == torch.int32 and gids.is_contiguous() and gids.dim() == 2
@@ -843,7 +851,7 @@ def tower_shard_plan(gids, W, rank, feat_sizes, local_offs, total_local, n_cap, 
     ev = _launch_maybe_side(side, lambda: _C.call(
         "rm_tower_shard_plan", _p(gids), Ntot, m, W, rank, _p(feat_sizes), _p(local_offs), int(total_local), n_cap,
         int(b_cap), unit, _p(ws), ws_bytes, _p(keys), _p(pos), _p(fb), _p(ub), _p(n_own), _p(status), _stream(),
-    ), (gids, feat_sizes, local_offs, ws, keys, pos, fb, ub, n_own, status))
+    ), (gids, feat_sizes, local_offs, ws, keys, pos, fb, ub, n_own, status), fork)
     plan = TowerPlan(int(b_cap), m, unit, keys, pos, fb, ub, ws, ev)
     plan.n_own = n_own
     return plan

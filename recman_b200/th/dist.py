@@ -384,6 +384,18 @@ class P2PFrontEndFunction(Function):
         return (None,) * 11
 
 
+def _all_gather_many(pairs, group=None) -> None:
+    """Several all_gather_into_tensor calls as ONE grouped NCCL launch (ncclGroupStart/End) where torch offers it."""
+    cm = getattr(dist, "_coalescing_manager", None)
+    if cm is None:
+        for out, inp in pairs:
+            dist.all_gather_into_tensor(out, inp, group=group)
+        return
+    with cm(group=group):
+        for out, inp in pairs:
+            dist.all_gather_into_tensor(out, inp, group=group)
+
+
 class P2PTowerFunction(Function):
     """Row-sharded version of autograd.TowerFunction (fused DeepFM tower): ids -> (y1, fm, lin).
 
@@ -409,22 +421,28 @@ class P2PTowerFunction(Function):
         if need_grad and (fused_opt is None or not ops.tower_bwd_supported(k, W1.shape[1])):
             raise NotImplementedError("row-sharded fused tower: training needs the in-kernel sparse update "
                                       "(fit_on_batch; no L2 on the tables) with k = 64 and a first hidden layer of 32")
-        gids = None
+        ctx.tp = None
         if need_grad:
-            # every rank has finished the previous step's table update once this returns (barrier for the peer reads)
-            # (int32: half the bytes of the reference's int64 ids; a table has < 2^31 rows, and an id outside int32 is
-            # outside its table anyway - it is clamped to -1 = "invalid")
+            # Owner-side plan, entirely on the side stream and forked BEFORE the forward kernel is enqueued: the ids
+            # all-gather (int32: half the bytes of the reference's int64 ids; a table has < 2^31 rows, an id outside
+            # int32 is outside its table anyway and becomes -1 = "invalid") and the sort run under the forward's NVLink
+            # reads.  The forward needs no barrier of its own: the peers' rows it reads were last written by the
+            # previous step's update, and every rank's dense all-reduce of that step was enqueued behind its update -
+            # this rank's all-reduce could not complete before every rank had entered it.
             ids32 = torch.where((ids >= 0) & (ids < 2 ** 31), ids, torch.full_like(ids, -1)).to(torch.int32)
             gids = torch.empty(W * b, m, dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(gids, ids32, group=plan.group)
+            side = ops.side_stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                dist.all_gather_into_tensor(gids, ids32, group=plan.group)
+            ids32.record_stream(side)
+            gids.record_stream(side)
+            n_cap = plan.capacity(b)
+            ctx.tp = ops.tower_shard_plan(gids, W, plan.rank, plan.feat_sizes_on(dev), plan.offsets_on(dev), total, n_cap,
+                                          (n_cap + m - 1) // m, status=status, side=True, fork=False)
         lin_dense = scal[total:, 1] if n_dense else None
         y1, fm, lin, S = ops.tower_fwd_p2p(peer.ptrs_of(table), peer.ptrs_of(scal), k, plan.feat_sizes_on(dev),
                                            plan.offsets_on(dev), ids, dense, lin_dense, W1, b1, status=status)
-        ctx.tp = None
-        if need_grad:
-            n_cap = plan.capacity(b)
-            ctx.tp = ops.tower_shard_plan(gids, W, plan.rank, plan.feat_sizes_on(dev), plan.offsets_on(dev), total, n_cap,
-                                          (n_cap + m - 1) // m, status=status, side=True)
         ctx.plan, ctx.status, ctx.fused_opt = plan, status, fused_opt
         ctx.table, ctx.scal, ctx.W_lin = table, scal, W_lin
         ctx.n_dense = n_dense
@@ -450,10 +468,7 @@ class P2PTowerFunction(Function):
         S_all = torch.empty(W * b, k, dtype=torch.float32, device=dev)
         gfm_all = torch.empty(W * b, dtype=torch.float32, device=dev)
         glin_all = torch.empty(W * b, dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(g1_all, g1, group=plan.group)
-        dist.all_gather_into_tensor(S_all, S, group=plan.group)
-        dist.all_gather_into_tensor(gfm_all, g_fm, group=plan.group)
-        dist.all_gather_into_tensor(glin_all, g_lin, group=plan.group)
+        _all_gather_many([(S_all, S), (g1_all, g1), (gfm_all, g_fm), (glin_all, g_lin)], plan.group)
         total = plan.total_local
         if ctx.n_dense:
             ctx.W_lin.rm_dense_tail = (total, dense.t() @ g_lin)  # replicated: all-reduced by the optimizer
