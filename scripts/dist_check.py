@@ -102,6 +102,10 @@ def main():
             g = p.grad.clone()
             dist.all_reduce(g)
             close(name, g, exp)
+    # drop this script's autograd graph: it keeps the parameters' grad accumulators alive, and those were created on
+    # the default stream - a captured backward that reused them would make the legacy stream wait on the capture
+    del loss
+    model.final_logit = None
     # one full step through the public call (all-reduce of the dense bucket inside optimizer_step)
     model.fit_on_batch(Xr, yr)
     torch.cuda.synchronize()
