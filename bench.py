@@ -196,7 +196,7 @@ def algorithmic_bytes(kind, B, m, k, n_dense, n_unique=None):
     if kind == "rm_pack_grad_rows":
         # per (b,f): dx row + x row read, G row (k+4) written; S row + 2 scalars per sample
         return B * m * (8 * k + 4 * (k + 4)) + B * (4 * k + 8)
-    if kind == "rm_tower_fwd":
+    if kind in ("rm_tower_fwd", "rm_tower_fwd_p2p"):
         # per (b,f): id 8 + row read 4k + interleaved (bias, weight) 8; per sample: dense read, S + y1 + 2 logits written
         # (N1 = 32 at the bench shape; the row buffer is not written)
         return B * (m * (8 + 4 * k + 8) + 4 * n_dense + 4 * k + 4 * 32 + 8)
@@ -367,12 +367,21 @@ def measure(args, wname, world, rank, local_rank, dev, primary=True):
             ab = algorithmic_bytes(name, B, m, k, n_dense, n_unique)
             kernels[name] = {"avg_ms": round(avg, 4), "launches": count, "ms_per_step": round(total_ms / prof_steps, 4),
                              "alg_bytes": ab, "gbs": (round(ab / (avg * 1e-3) / 1e9, 1) if ab and avg > 0 else None)}
+            if world > 1 and name in ("rm_tower_fwd_p2p", "rm_gather_fm_fwd_p2p") and avg > 0:
+                # rows (and their (bias, weight) pairs) read from the W-1 peers over NVLink, per launch (uniform ids)
+                nv = B * m * (world - 1) / world * (4 * k + 8)
+                kernels[name]["nvlink_read_bytes"] = int(nv)
+                kernels[name]["nvlink_gbs"] = round(nv / (avg * 1e-3) / 1e9, 1)
+        if world > 1 and "rm_tower_bwd_update" in kernels:
+            # what the collectives of the step deliver to this rank: ids (int32) + per-sample operands (S, g1, g_fm, g_lin)
+            kernels["nccl_all_gather"] = {"avg_ms": None, "ms_per_step": None, "alg_bytes": None, "recv_bytes_per_step": int((world - 1) * B * (4 * m + 4 * k + 4 * 32 + 8)),
+                                          "note": "ids on the side stream under the forward; operands before the backward"}
         traffic = {}
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wname, {})
         except Exception:
             pass
-        cand = [(v["ms_per_step"], n) for n, v in kernels.items() if v["alg_bytes"]]
+        cand = [(v["ms_per_step"], n) for n, v in kernels.items() if v.get("alg_bytes")]
         roofline = None
         cin_f = cin_flops_per_step(w, B, k)
         if cin_f and "rm_cin_layer_bwd" in kernels:

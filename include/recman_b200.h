@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define RM_ABI_VERSION 3 /* 3: fused DeepFM tower entry points (rm_tower_*) */
+#define RM_ABI_VERSION 3 /* 3: fused DeepFM tower (rm_tower_*), head (rm_deepfm_head), CIN split-half/pool (rm_cin_pool_*) */
 
 #define RM_E_INVALID (-1)     /* bad argument (null pointer, negative size, ...) */
 #define RM_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
@@ -199,8 +199,10 @@ int rm_cross_bwd(const float* x, int64_t ld, const float* w, const float* b, con
  * x0[b*x0_bstride + p*D + d], xk[b*xk_bstride + q*D + d] (both may be views into
  * wider rows: x0 into the front-end row buffer, xk into the previous layer's
  * [B,N,D] output).  Z is never materialised.  `pre` (nullable) receives the pre-activation
- * [B,N,D] for the backward.  The split-half / sum-pool / cin_w head stay in
- * torch (views and a tiny GEMV).
+ * [B,N,D] for the backward.  Split-half + sum-pool: rm_cin_pool_fwd / _bwd below;
+ * the cin_w head is a [B, sum H] x [sum H, 1] GEMV left to torch.
+ * Parity mode (RM_CIN_3XTF32) accumulates at most 512 k'' per CTA in TMEM (the tensor core's fp32 accumulation
+ * rounds toward zero) and adds the splits in fp32 round-to-nearest, in order: 1e-5 of max|F| at any K.
  * ------------------------------------------------------------------------- */
 int rm_cin_layer_fwd(const float* x0, int64_t x0_bstride, const float* xk, int64_t xk_bstride, const float* W,
                      const float* bias, int64_t B, int32_t m, int32_t H, int32_t D, int32_t N,
@@ -219,6 +221,12 @@ int rm_cin_layer_bwd(const float* x0, int64_t x0_bstride, const float* xk, int64
                      size_t workspace_bytes, void* stream);
 size_t rm_cin_layer_bwd_workspace_bytes(int64_t B, int32_t m, int32_t H, int32_t D, int32_t N,
                                         int32_t precision);
+/* split-half + sum-pool of a layer's output (recman/tf/core/layers.py:738-751): feature maps n < n0 feed the next
+ * layer (out[:, :n0] is used in place), pooled[b, n - n0] = sum_d out[b, n, d] for n >= n0 (n0 = 0: last layer).
+ * Backward: dout[b,n,d] = n < n0 ? d_next[b*next_bstride + n*D + d] : d_pool[b, n - n0]; a null gradient is zero. */
+int rm_cin_pool_fwd(const float* out, int64_t B, int32_t N, int32_t D, int32_t n0, float* pooled, void* stream);
+int rm_cin_pool_bwd(const float* d_next, int64_t next_bstride, const float* d_pool, int64_t B, int32_t N, int32_t D,
+                    int32_t n0, float* dout, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * N1  optimizer step on K2's (rows, sums) output and on dense parameters.

@@ -72,6 +72,8 @@ _SIGS = {
          c_int64, P, c_size_t, P],
     ),
     "rm_cin_layer_bwd_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32, c_int32, c_int32]),
+    "rm_cin_pool_fwd": (ctypes.c_int, [P, c_int64, c_int32, c_int32, c_int32, P, P]),
+    "rm_cin_pool_bwd": (ctypes.c_int, [P, c_int64, P, c_int64, c_int32, c_int32, c_int32, P, P]),
     "rm_unpack_rows": (ctypes.c_int, [P, c_int64, c_int32, P, c_int32, c_int32, P, c_int64, P, P, P]),
     "rm_pack_grad_rows": (ctypes.c_int, [P, P, c_int64, P, P, P, c_int64, c_int32, P, c_int32, c_int32, P, P]),
     "rm_p2p_alloc": (ctypes.c_int, [c_size_t, P, P]),

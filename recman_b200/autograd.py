@@ -227,6 +227,34 @@ class CINLayerFunction(Function):
         return dx0, dxk, dW, dbias, None, None
 
 
+class CINLayerPoolFunction(Function):
+    """One CIN layer with its split-half + sum-pool (layers.py:711-751):
+    (x0, xk, W, bias) -> (next = out[:, :n0] [B,n0,D] feeding the next layer, pooled [B, N-n0] = sum_d out[:, n0:]).
+    n0 = 0 for the last layer (``next`` is then an empty tensor).  The backward builds dout in one pass from the two
+    gradients instead of autograd's zero-fill + slice-add + expand chain."""
+
+    @staticmethod
+    def forward(ctx, x0, xk, W, bias, act, precision, n0):
+        out, pre = ops.cin_layer_fwd(x0, xk, W, bias, act, precision, want_pre=True)
+        pooled = ops.cin_pool_fwd(out, n0)
+        ctx.save_for_backward(x0, xk, W, pre)
+        ctx.act, ctx.precision, ctx.n0 = act, precision, n0
+        ctx.set_materialize_grads(False)
+        return out[:, :n0], pooled
+
+    @staticmethod
+    def backward(ctx, d_next, d_pool):
+        x0, xk, W, pre = ctx.saved_tensors
+        B, N, D = pre.shape
+        if d_next is not None and (d_next.stride(2) != 1 or d_next.stride(1) != D):
+            d_next = d_next.contiguous()
+        dout = ops.cin_pool_bwd(d_next if ctx.n0 else None, d_pool, B, N, D, ctx.n0, pre.device)
+        dx0 = torch.zeros_like(x0, memory_format=torch.contiguous_format)
+        dxk = torch.empty(xk.shape, dtype=xk.dtype, device=xk.device)
+        dW, dbias = ops.cin_layer_bwd(x0, xk, W, pre, dout, ctx.act, ctx.precision, dx0, dxk)
+        return dx0, dxk, dW, dbias, None, None, None
+
+
 # --------------------------------------------------------------------------- #
 # fused DeepFM / DCN / xDeepFM front end (K1 + K3 + first-order, one launch)
 # --------------------------------------------------------------------------- #

@@ -22,6 +22,11 @@
 // holds 16 k'' of "hi" in its first 64 bytes and the same 16 k'' of "lo" in the last 64, so both modes use the
 // same SWIZZLE_128B tiles and descriptors.
 //
+// TMEM accumulation rounds toward zero - a bias that grows linearly with the number of accumulate steps (measured
+// 3.3e-5 of max|F| at k'' = 2800).  In parity mode the reduction is therefore cut into splits of <= TC_SPLIT_K k'':
+// CTA (tile, split) accumulates its k'' range in TMEM and writes the raw partial sums; cin_splitk_finish_kernel adds
+// the splits in order in fp32 round-to-nearest (deterministic), then bias + activation.  One split = the fused epilogue.
+//
 // Every mbarrier wait is bounded: a pipeline bug sets *status and lets the kernel drain instead of hanging.
 #include "tc_common.cuh"
 
@@ -31,6 +36,7 @@ constexpr int TC_BM = 256;          // rows per CTA (two M=128 accumulators)
 constexpr int TC_STAGES = 3;
 constexpr int TC_A_BYTES = TC_BM * 128;  // A tile: 256 rows x 128 B
 constexpr int TC_THREADS = 320;
+constexpr int TC_SPLIT_K = 512;     // parity mode: k'' accumulated in TMEM per CTA (truncation bias < 1e-5 of max|F|)
 
 // ------------------------------------------------------------------------------------------------ W packing
 // Stage image `it` = NPAD rows x 128 B, 16-byte chunk c of row n stored at chunk (c ^ (n & 7)).
@@ -74,9 +80,42 @@ struct TcParams {
   float* out;
   float* pre;
   int32_t* status;
-  int64_t Mrows;  // B*D
+  float* partial;  // n_split > 1: [n_split][B, N, D] raw partial sums (no bias / activation)
+  int64_t Mrows;   // B*D
   int m, H, D, N, NPAD, act, n_stages;
+  int n_split, stages_per_split;
 };
+
+// out = act(bias + sum over splits, in order) - fp32 round-to-nearest, fixed order
+__global__ void __launch_bounds__(256) cin_splitk_finish_kernel(const float* __restrict__ partial, int n_split,
+                                                                int64_t total, int N, int D,
+                                                                const float* __restrict__ bias, int act,
+                                                                float* __restrict__ out, float* __restrict__ pre) {
+  const int64_t total4 = total >> 2;  // D % 4 == 0 is not required: vector path only when total % 4 == 0 and D % 4 == 0
+  const bool vec = (total & 3) == 0 && (D & 3) == 0;
+  if (vec) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+      float4 acc = __ldcs(reinterpret_cast<const float4*>(partial) + i);
+      for (int s = 1; s < n_split; ++s) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(partial + (int64_t)s * total) + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      const float bv = __ldg(bias + (int)(((i << 2) / D) % N));
+      acc.x += bv; acc.y += bv; acc.z += bv; acc.w += bv;
+      if (pre) reinterpret_cast<float4*>(pre)[i] = acc;
+      reinterpret_cast<float4*>(out)[i] =
+          make_float4(tc_act(acc.x, act), tc_act(acc.y, act), tc_act(acc.z, act), tc_act(acc.w, act));
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      float acc = partial[i];
+      for (int s = 1; s < n_split; ++s) acc += partial[(int64_t)s * total + i];
+      acc += __ldg(bias + (int)((i / D) % N));
+      if (pre) pre[i] = acc;
+      out[i] = tc_act(acc, act);
+    }
+  }
+}
 
 template <int MP4, bool SPLIT3>
 __global__ void __launch_bounds__(TC_THREADS, 1) cin_fwd_tc_kernel(const TcParams P) {
@@ -116,7 +155,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cin_fwd_tc_kernel(const TcParam
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int n_stages = P.n_stages;
+  // this CTA's slice of the reduction: stages [stage0, stage0 + n_stages) of the whole K, tile blockIdx.x
+  const int split = (int)blockIdx.y;
+  const int stage0 = split * P.stages_per_split;
+  const int n_stages = min(P.stages_per_split, P.n_stages - stage0);
+  const int g0 = stage0 * CPS, g1 = (stage0 + n_stages) * CPS;  // 16-byte k-chunks [g0, g1) of a row (g = q*MP4 + c)
   bool ok = true;
 
   if (warp < 8) {
@@ -133,10 +176,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cin_fwd_tc_kernel(const TcParam
     const uint32_t row_off = (uint32_t)r * 128u;
     const uint32_t rx = (uint32_t)(r & 7);
     int cnt = 0;  // chunks produced so far (same value in every producer thread)
-    for (int q = 0; q < P.H; ++q) {
+    const int q_begin = g0 / MP4, q_end = min(P.H, (g1 + MP4 - 1) / MP4);
+    for (int q = q_begin; q < q_end; ++q) {
       const float xkv = valid ? __ldg(xkp + (int64_t)q * P.D) : 0.f;
 #pragma unroll
       for (int c = 0; c < MP4; ++c) {
+        const int g = q * MP4 + c;
+        if (g < g0 || g >= g1) continue;  // another split's chunk (only in the first / last q of the range)
         const int slot = cnt % CPS;
         const int it = cnt / CPS;
         const int s = it % TC_STAGES;
@@ -186,14 +232,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cin_fwd_tc_kernel(const TcParam
           : "r"(taddr0 + (uint32_t)col0));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (evalid) {
+        if (P.n_split > 1) {  // raw partial sums; cin_splitk_finish_kernel adds the splits, bias and activation
+          float* part = P.partial + (int64_t)split * P.Mrows * P.N;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = col0 + j;
-          if (n < P.N) {
-            const float v = __uint_as_float(a[j]) + __ldg(P.bias + n);
-            const int64_t o = obase + (int64_t)n * P.D;
-            if (P.pre) P.pre[o] = v;
-            P.out[o] = tc_act(v, P.act);
+          for (int j = 0; j < 16; ++j) {
+            const int n = col0 + j;
+            if (n < P.N) __stcs(part + obase + (int64_t)n * P.D, __uint_as_float(a[j]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = col0 + j;
+            if (n < P.N) {
+              const float v = __uint_as_float(a[j]) + __ldg(P.bias + n);
+              const int64_t o = obase + (int64_t)n * P.D;
+              if (P.pre) P.pre[o] = v;
+              P.out[o] = tc_act(v, P.act);
+            }
           }
         }
       }
@@ -236,8 +291,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cin_fwd_tc_kernel(const TcParam
         const int s = it % TC_STAGES;
         ok = mbar_wait(empty(s), (((uint32_t)(it / TC_STAGES)) & 1u) ^ 1u) && ok;
         mbar_arrive_expect_tx(full_b(s), b_bytes);
-        bulk_g2s(smem_base + (uint32_t)s * stage_bytes + TC_A_BYTES, P.wpack + (size_t)it * (b_bytes / 4), b_bytes,
-                 full_b(s));
+        bulk_g2s(smem_base + (uint32_t)s * stage_bytes + TC_A_BYTES,
+                 P.wpack + (size_t)(stage0 + it) * (b_bytes / 4), b_bytes, full_b(s));
       }
     }
   }
@@ -265,16 +320,29 @@ bool cin_tc_supported(int64_t B, int m, int H, int D, int N) {
   return m >= 1 && m <= 32 && N >= 1 && N <= 256;
 }
 
-// workspace: [status int32 x 64 (256 B)] [packed W stage images]
+// parity mode: number of k'' splits (one TMEM accumulation each) and stages per split
+static void tc_split_for(int n_stages, int split3, int* n_split, int* stages_per_split) {
+  const int k_per_stage = split3 ? 16 : 32;
+  int ns = split3 ? (n_stages * k_per_stage + TC_SPLIT_K - 1) / TC_SPLIT_K : 1;
+  if (ns < 1) ns = 1;
+  const int sps = (n_stages + ns - 1) / ns;
+  *n_split = (n_stages + sps - 1) / sps;
+  *stages_per_split = sps;
+}
+
+// workspace: [status int32 x 64 (256 B)] [packed W stage images] [split-K partial sums (parity mode, K > TC_SPLIT_K)]
 size_t cin_tc_fwd_workspace(int64_t B, int m, int H, int D, int N, int precision) {
-  (void)B;
-  (void)D;
   const int split3 = precision == RM_CIN_3XTF32;
-  return 256 + (size_t)tc_stages_for(m, H, split3) * tc_npad(N) * 128;
+  const int n_stages = tc_stages_for(m, H, split3);
+  int n_split, sps;
+  tc_split_for(n_stages, split3, &n_split, &sps);
+  size_t bytes = 256 + align_up((size_t)n_stages * tc_npad(N) * 128, 256);
+  if (n_split > 1) bytes += align_up((size_t)n_split * (size_t)B * N * D * sizeof(float), 256);
+  return bytes;
 }
 
 template <int MP4>
-static int launch_tc(const TcParams& P, bool split3, int grid, size_t smem, cudaStream_t st) {
+static int launch_tc(const TcParams& P, bool split3, dim3 grid, size_t smem, cudaStream_t st) {
   if (split3) {
     RM_SMEM_ATTR_ONCE(smem, cin_fwd_tc_kernel<MP4, true>);
     cin_fwd_tc_kernel<MP4, true><<<grid, TC_THREADS, smem, st>>>(P);
@@ -309,19 +377,28 @@ int cin_fwd_tc(const float* x0, int64_t bs0, const float* xk, int64_t bsk, const
   P.x0 = x0; P.bs0 = bs0; P.xk = xk; P.bsk = bsk; P.wpack = wpack; P.bias = bias; P.out = out; P.pre = pre;
   P.status = status; P.Mrows = B * (int64_t)D; P.m = m; P.H = H; P.D = D; P.N = N; P.NPAD = NPAD; P.act = act;
   P.n_stages = n_stages;
+  tc_split_for(n_stages, split3 ? 1 : 0, &P.n_split, &P.stages_per_split);
+  P.partial = P.n_split > 1 ? (float*)((char*)workspace + 256 + align_up((size_t)n_stages * NPAD * 128, 256)) : nullptr;
   const uint32_t stage_bytes = (uint32_t)((TC_A_BYTES + NPAD * 128 + 1023) / 1024 * 1024);
   const size_t smem = (size_t)TC_STAGES * stage_bytes + 8 * (3 * TC_STAGES + 2) + 1024;  // + alignment slack
-  const int grid = (int)ceil_div(P.Mrows, TC_BM);
+  const dim3 grid((unsigned)ceil_div(P.Mrows, TC_BM), (unsigned)P.n_split);
+  int rc;
   switch (MP4) {
-    case 1: return launch_tc<1>(P, split3, grid, smem, st);
-    case 2: return launch_tc<2>(P, split3, grid, smem, st);
-    case 3: return launch_tc<3>(P, split3, grid, smem, st);
-    case 4: return launch_tc<4>(P, split3, grid, smem, st);
-    case 5: return launch_tc<5>(P, split3, grid, smem, st);
-    case 6: return launch_tc<6>(P, split3, grid, smem, st);
-    case 7: return launch_tc<7>(P, split3, grid, smem, st);
-    default: return launch_tc<8>(P, split3, grid, smem, st);
+    case 1: rc = launch_tc<1>(P, split3, grid, smem, st); break;
+    case 2: rc = launch_tc<2>(P, split3, grid, smem, st); break;
+    case 3: rc = launch_tc<3>(P, split3, grid, smem, st); break;
+    case 4: rc = launch_tc<4>(P, split3, grid, smem, st); break;
+    case 5: rc = launch_tc<5>(P, split3, grid, smem, st); break;
+    case 6: rc = launch_tc<6>(P, split3, grid, smem, st); break;
+    case 7: rc = launch_tc<7>(P, split3, grid, smem, st); break;
+    default: rc = launch_tc<8>(P, split3, grid, smem, st); break;
   }
+  if (rc || P.n_split == 1) return rc;
+  const int64_t total = P.Mrows * N;
+  cin_splitk_finish_kernel<<<grid_for(total / 4 + 1, 256, 8), 256, 0, st>>>(P.partial, P.n_split, total, N, D, bias, act,
+                                                                            out, pre);
+  RM_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace rm

@@ -400,6 +400,29 @@ def cin_layer_fwd(x0, xk, W, bias, act: int, precision: int, want_pre=True):
 _last_cin_ws = None
 
 
+def cin_pool_fwd(out, n0: int):
+    """pooled[b, n - n0] = sum_d out[b, n, d] for n >= n0 (layers.py:738-751: the direct half, sum-pooled over D)."""
+    _dev_check(out)
+    B, N, D = out.shape
+    assert out.is_contiguous() and 0 <= n0 < N
+    pooled = torch.empty(B, N - n0, dtype=torch.float32, device=out.device)
+    _C.call("rm_cin_pool_fwd", _p(out), B, N, D, n0, _p(pooled), _stream())
+    return pooled
+
+
+def cin_pool_bwd(d_next, d_pool, B: int, N: int, D: int, n0: int, device):
+    """dout [B,N,D] of a layer from the gradients of its two consumers (either may be None = zero)."""
+    if d_next is not None:
+        assert d_next.shape == (B, n0, D) and d_next.stride(2) == 1 and d_next.stride(1) == D
+    if d_pool is not None:
+        d_pool = d_pool.contiguous()
+        assert d_pool.shape == (B, N - n0)
+    dout = torch.empty(B, N, D, dtype=torch.float32, device=device)
+    _C.call("rm_cin_pool_bwd", _p(d_next), 0 if d_next is None else d_next.stride(0), _p(d_pool), B, N, D, n0, _p(dout),
+            _stream())
+    return dout
+
+
 def cin_tc_status() -> int:
     """Status word of the last tensor-core CIN launch (0 = ok, 2 = a bounded pipeline wait expired). Host sync."""
     if _last_cin_ws is None:

@@ -25,7 +25,7 @@ import torch
 
 from .. import _C, ops
 from ..autograd import (
-    CINLayerFunction,
+    CINLayerFunction, CINLayerPoolFunction,
     CrossFunction,
     EmbeddingLayerFunction,
     EmbeddingLayout,
@@ -641,6 +641,14 @@ class CIN:
         n_layers = len(self.cross_layer_units)
         for i, size in enumerate(self.cross_layer_units):
             W = v[f"{p}cin_filter_{i}"][0]  # [m*H_i, N_i]
+            last = i == n_layers - 1
+            if not self.training or self.dropout[i + 1] is None or self.dropout[i + 1] >= 1:
+                # no dropout between the layer and its consumers: split-half + sum-pool ride with the layer kernel
+                assert last or size % 2 == 0, "tf.split needs an even layer size"
+                xk, pooled = CINLayerPoolFunction.apply(x0, xk, W, v[f"{p}cin_bias_{i}"], act, self.precision,
+                                                        0 if last else size // 2)
+                finals.append(pooled)
+                continue
             feat_map = CINLayerFunction.apply(x0, xk, W, v[f"{p}cin_bias_{i}"], act, self.precision)  # [B,N,D]
             feat_map = _dropout(feat_map, self.dropout[i + 1], self.training)
             if i != n_layers - 1:
