@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define RM_ABI_VERSION 3 /* 3: fused DeepFM tower (rm_tower_*), head (rm_deepfm_head), CIN split-half/pool (rm_cin_pool_*) */
+#define RM_ABI_VERSION 4 /* 3: fused DeepFM tower (rm_tower_*), head (rm_deepfm_head); 4: rm_cin_pool_*, dense-feature gradients in rm_deepfm_head */
 
 #define RM_E_INVALID (-1)     /* bad argument (null pointer, negative size, ...) */
 #define RM_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
@@ -429,16 +429,20 @@ int rm_tower_shard_plan(const int32_t* gids, int64_t Ntot, int32_t m, int32_t W,
  * labels == NULL: forward only (logit / pred, nullable).  Otherwise also loss[1] (batch
  * mean), g[B] = grad_scale * dL/dlogit (the FM and first-order gradient), g1[B,32] =
  * grad_scale * dL/dy1, dW2[32,32], db2[32], dw3[32], dscal[1] (= db3 = dw0), db1[32].
- * Batch reductions are CTA partials added in CTA order: run-to-run identical.
+ * dense [B, n_dense] (nullable): the samples' dense features; with it the kernel also emits the two
+ * gradients of the first layer / first-order term that involve them, dW1_dense[n_dense,32] =
+ * dense^T g1 and dlin_dense[n_dense] = dense^T g (layers.py:418-439, 589-602 autodiff).
+ * Batch reductions are CTA partials added in a fixed association: run-to-run identical.
  * ------------------------------------------------------------------------- */
 int rm_deepfm_head_supported(int32_t N1, int32_t N2);
-size_t rm_deepfm_head_workspace_bytes(int64_t B);
+size_t rm_deepfm_head_workspace_bytes(int64_t B, int32_t n_dense);
 int rm_deepfm_head(const float* y1, const float* fm, const float* lin, const float* w0,
                    const float* W2, const float* b2, const float* w3, const float* b3,
-                   const float* labels, int64_t B, int32_t N1, int32_t N2, int32_t act,
-                   int32_t task, float grad_scale, float* logit, float* pred, float* loss,
-                   float* g1, float* g, float* dW2, float* db2, float* dw3, float* dscal,
-                   float* db1, void* workspace, size_t workspace_bytes, void* stream);
+                   const float* labels, const float* dense, int32_t n_dense, int64_t B, int32_t N1,
+                   int32_t N2, int32_t act, int32_t task, float grad_scale, float* logit,
+                   float* pred, float* loss, float* g1, float* g, float* dW2, float* db2, float* dw3,
+                   float* dscal, float* db1, float* dW1_dense, float* dlin_dense, void* workspace,
+                   size_t workspace_bytes, void* stream);
 
 /* Test-only: D[128,32] = At^T @ Bt (At [K,128], Bt [K,32]) through the MN-major SWIZZLE_128B
  * operand layout of the tower backward's weight-gradient GEMM (variant 0 = the layout used). */

@@ -126,11 +126,11 @@ _SIGS = {
         [P, c_int64, c_int32, c_int32, c_int32, P, P, c_int64, c_int64, c_int64, c_int32, P, c_size_t, P, P, P, P, P, P,
          P]),
     "rm_deepfm_head_supported": (ctypes.c_int, [c_int32, c_int32]),
-    "rm_deepfm_head_workspace_bytes": (c_size_t, [c_int64]),
+    "rm_deepfm_head_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "rm_deepfm_head": (
         ctypes.c_int,
-        [P, P, P, P, P, P, P, P, P, c_int64, c_int32, c_int32, c_int32, c_int32, c_float, P, P, P, P, P, P, P, P, P, P, P,
-         c_size_t, P]),
+        [P, P, P, P, P, P, P, P, P, P, c_int32, c_int64, c_int32, c_int32, c_int32, c_int32, c_float, P, P, P, P, P, P, P,
+         P, P, P, P, P, P, c_size_t, P]),
 }
 
 EXPORTS = tuple(_SIGS)

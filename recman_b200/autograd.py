@@ -465,7 +465,7 @@ class TowerFunction(Function):
 
     @staticmethod
     def forward(ctx, table, scal, scal_fwd, bias_param, W_lin, W1, b1, offsets, total_rows, status, ids, dense,
-                fused_opt, grad_mode=True):
+                fused_opt, grad_mode=True, side=None):
         k = table.shape[1]
         N1 = W1.shape[1]
         n_dense = 0 if dense is None else dense.shape[1]
@@ -485,6 +485,7 @@ class TowerFunction(Function):
         ctx.use_bk, ctx.fused_opt = use_bk, fused_opt
         ctx.table, ctx.scal, ctx.bias_param, ctx.W_lin = table, scal, bias_param, W_lin
         ctx.total_rows, ctx.n_dense, ctx.status = total_rows, n_dense, status
+        ctx.side = side
         ctx.save_for_backward(x, S, ids, dense, W1)
         ctx.set_materialize_grads(False)
         return y1, fm.reshape(-1, 1), lin.reshape(-1, 1)
@@ -500,19 +501,25 @@ class TowerFunction(Function):
         g1 = torch.zeros(B, N1, dtype=torch.float32, device=dev) if dy1 is None else dy1.contiguous()
         g_fm = torch.zeros(B, dtype=torch.float32, device=dev) if dfm is None else dfm.reshape(-1).contiguous()
         g_lin = None if dlin is None else dlin.reshape(-1).contiguous()
-        db1 = g1.sum(0)
+        # the head kernel of the same step may already hold the gradients that need no embedding rows (TowerSide)
+        side_db1, side_dW1d, side_dlind = ctx.side.take() if ctx.side is not None else (None, None, None)
+        if dy1 is None or (ctx.n_dense and (side_dW1d is None or (g_lin is not None and side_dlind is None))):
+            side_db1 = side_dW1d = side_dlind = None
+        db1 = side_db1 if side_db1 is not None else g1.sum(0)
         total = ctx.total_rows
         if g_lin is not None and ctx.n_dense:
-            ctx.W_lin.rm_dense_tail = (total, dense.t() @ g_lin)
+            ctx.W_lin.rm_dense_tail = (total, side_dlind if side_db1 is not None else dense.t() @ g_lin)
         if ctx.use_bk:
             kind, lr = ctx.fused_opt
             dW1 = torch.empty(W1.shape, dtype=torch.float32, device=dev)
-            dW1_emb = ops.tower_bwd_update(ctx.table.data, ctx.scal[:total], plan, g1, S, g_fm, g_lin, W1.data, kind, lr,
-                                           status=ctx.status)
-            dW1[: m * k] = dW1_emb
+            ops.tower_bwd_update(ctx.table.data, ctx.scal[:total], plan, g1, S, g_fm, g_lin, W1.data, kind, lr,
+                                 status=ctx.status, out=dW1[: m * k])
             if ctx.n_dense:
-                torch.mm(dense.t(), g1, out=dW1[m * k :])
-            return (None, None, None, None, None, dW1, db1) + (None,) * 7
+                if side_db1 is not None:
+                    dW1[m * k :] = side_dW1d
+                else:
+                    torch.mm(dense.t(), g1, out=dW1[m * k :])
+            return (None, None, None, None, None, dW1, db1) + (None,) * 8
         d = m * k + ctx.n_dense
         ld = x.shape[1]
         if ops.narrow_linear_ok(N1):
@@ -527,20 +534,44 @@ class TowerFunction(Function):
         attach_sparse_grad(ctx.bias_param, ops.SparseGrad(plan.uniq_rows, ob, plan.n_unique))
         if g_lin is not None:
             attach_sparse_grad(ctx.W_lin, ops.SparseGrad(plan.uniq_rows, ol, plan.n_unique))
-        return (None, None, None, None, None, dW1, db1) + (None,) * 7
+        return (None, None, None, None, None, dW1, db1) + (None,) * 8
+
+
+class TowerSide:
+    """Side channel from the head kernel to the tower's backward (same step): the gradients of the first layer that do
+    not need the embedding rows - db1 = sum_b g1, dW1_dense = dense^T g1, dlin_dense = dense^T g - come out of
+    rm_deepfm_head's partial sums, so the tower's backward does not launch a reduce, a skinny GEMM and a GEMV for them.
+    Filled by HeadFunction, read (and cleared) by TowerFunction / P2PTowerFunction; empty = compute them from g1."""
+
+    __slots__ = ("db1", "dW1_dense", "dlin_dense")
+
+    def __init__(self):
+        self.clear()
+
+    def clear(self):
+        self.db1 = self.dW1_dense = self.dlin_dense = None
+
+    def take(self):
+        out = (self.db1, self.dW1_dense, self.dlin_dense)
+        self.clear()
+        return out
 
 
 class HeadFunction(Function):
     """DeepFM head in one kernel (rm_deepfm_head): (y1, fm, lin, w0, W2, b2, w3, b3, labels) -> (loss, logit, pred).
 
     The kernel computes the loss AND every gradient in the same pass; ``backward`` only scales them by the incoming
-    gradient of the loss (a scalar)."""
+    gradient of the loss (a scalar) - or not at all with ``unit_grad`` (the caller guarantees that it backpropagates
+    d(loss) = 1, as ``DeepModel._eager_step`` does on one GPU: saves six elementwise launches per step).
+    ``dense`` + ``side``: see TowerSide."""
 
     @staticmethod
-    def forward(ctx, y1, fm, lin, w0, W2, b2, w3, b3, labels, act, task):
+    def forward(ctx, y1, fm, lin, w0, W2, b2, w3, b3, labels, act, task, dense=None, side=None, unit_grad=False):
         out = ops.deepfm_head(y1.contiguous(), fm.reshape(-1).contiguous(), lin.reshape(-1).contiguous(), w0, W2, b2,
-                              w3.reshape(-1).contiguous(), b3, labels, act, task)
+                              w3.reshape(-1).contiguous(), b3, labels, act, task,
+                              dense=dense if side is not None else None)
         ctx.out = out
+        ctx.side, ctx.unit_grad = side, bool(unit_grad)
         ctx.w3_shape = w3.shape
         ctx.fm_shape, ctx.lin_shape = fm.shape, lin.shape
         ctx.mark_non_differentiable(out["logit"], out["pred"])
@@ -549,7 +580,19 @@ class HeadFunction(Function):
     @staticmethod
     def backward(ctx, gloss, _glogit, _gpred):
         o, ctx.out = ctx.out, None
+        side, ctx.side = ctx.side, None
+        tail = (None,) * 6
+        if ctx.unit_grad:
+            if side is not None:
+                side.db1, side.dW1_dense, side.dlin_dense = o["db1"], o.get("dW1_dense"), o.get("dlin_dense")
+            g = o["g"]
+            return (o["g1"], g.reshape(ctx.fm_shape), g.reshape(ctx.lin_shape), o["dscal"], o["dW2"], o["db2"],
+                    o["dw3"].reshape(ctx.w3_shape), o["dscal"]) + tail
+        if side is not None:
+            side.db1 = o["db1"] * gloss
+            side.dW1_dense = None if "dW1_dense" not in o else o["dW1_dense"] * gloss
+            side.dlin_dense = None if "dlin_dense" not in o else o["dlin_dense"] * gloss
         g = o["g"] * gloss
         ds = o["dscal"] * gloss
         return (o["g1"].mul_(gloss), g.reshape(ctx.fm_shape), g.reshape(ctx.lin_shape), ds, o["dW2"] * gloss,
-                o["db2"] * gloss, (o["dw3"] * gloss).reshape(ctx.w3_shape), ds, None, None, None)
+                o["db2"] * gloss, (o["dw3"] * gloss).reshape(ctx.w3_shape), ds) + tail

@@ -8,7 +8,9 @@
 //                                                                            create_loss utils.py:192-198 (Keras BCE)
 //          or mean((logit - y)^2) for regression
 //   and the gradients TensorFlow's autodiff would produce: g = dL/dlogit (= the FM and first-order gradients),
-//   g1 = dL/dy1, dW2, db2, dw3, db3, dw0, db1.
+//   g1 = dL/dy1, dW2, db2, dw3, db3, dw0, db1 - and, given the samples' dense features, the two products of the first
+//   layer / first-order term that involve them: dW1_dense = dense^T g1 [n_dense, 32], dlin_dense = dense^T g [n_dense]
+//   (what would otherwise be a reduce kernel, a skinny GEMM + split-K reduce and a GEMV per step).
 //
 // In the stock path these are ~100 tiny elementwise / reduce / GEMM launches on [B, 32] tensors - a third of a C5
 // step after the embedding kernels were fused.  One thread owns one sample (its two 32-wide hidden vectors live in
@@ -37,9 +39,10 @@ struct HeadParams {
   float* pred;
   float* g1;
   float* g;
-  float* partials;  // [grid, HD_PART]
+  float* partials;  // [grid, part_stride]: HD_PART + n_dense * (HD_N + 1) (dW1_dense rows | dlin_dense), padded
+  const float* dense;  // [B, nd] or nullptr
   int64_t B;
-  int act, task;
+  int act, task, nd, part_stride;
   float inv_B;
 };
 
@@ -132,7 +135,8 @@ __global__ void __launch_bounds__(HD_THREADS) head_kernel(const HeadParams P) {
     }
     P.g[b] = g;
   }
-  float* part = P.partials + (int64_t)blockIdx.x * HD_PART;
+  sD[tid][HD_N] = g;  // the pad column keeps dL/dlogit of the CTA's samples for the dense-feature products below
+  float* part = P.partials + (int64_t)blockIdx.x * P.part_stride;
   // ---- second layer backward: dy2 (kept in h2's registers), db2 / dw3 column sums by warp shuffle
 #pragma unroll
   for (int j = 0; j < HD_N; ++j) {
@@ -204,24 +208,74 @@ __global__ void __launch_bounds__(HD_THREADS) head_kernel(const HeadParams P) {
     part[HD_N * HD_N + 3 * HD_N + 2] = 0.f;
     part[HD_N * HD_N + 3 * HD_N + 3] = 0.f;
   }
+  if (P.dense) {
+    // dW1_dense[j][n] = sum_s dense[s][j] * g1[s][n],  dlin_dense[j] = sum_s dense[s][j] * g[s]: four interleaved
+    // partial sums over the CTA's samples, added in a fixed order
+    const int64_t b0 = (int64_t)blockIdx.x * HD_THREADS;
+    const int nlive = (int)(P.B - b0 < HD_THREADS ? P.B - b0 : HD_THREADS);
+    const float* dn = P.dense + b0 * P.nd;
+    const bool staged = P.nd <= HD_N;  // the CTA's dense rows fit the (dead) dy2 columns of sD
+    __syncthreads();
+    if (staged) {
+      for (int idx = tid; idx < HD_THREADS * P.nd; idx += HD_THREADS) {
+        const int sidx = idx / P.nd, j = idx - sidx * P.nd;
+        sD[sidx][j] = sidx < nlive ? __ldg(dn + idx) : 0.f;
+      }
+      __syncthreads();
+    }
+    for (int idx = tid; idx < P.nd * (HD_N + 1); idx += HD_THREADS) {
+      const int j = idx / (HD_N + 1), n = idx - j * (HD_N + 1);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      if (staged) {
+#pragma unroll 2
+        for (int sidx = 0; sidx < HD_THREADS; sidx += 4) {
+          a0 = fmaf(sD[sidx][j], n < HD_N ? sA[sidx][n] : sD[sidx][HD_N], a0);
+          a1 = fmaf(sD[sidx + 1][j], n < HD_N ? sA[sidx + 1][n] : sD[sidx + 1][HD_N], a1);
+          a2 = fmaf(sD[sidx + 2][j], n < HD_N ? sA[sidx + 2][n] : sD[sidx + 2][HD_N], a2);
+          a3 = fmaf(sD[sidx + 3][j], n < HD_N ? sA[sidx + 3][n] : sD[sidx + 3][HD_N], a3);
+        }
+      } else {
+        for (int sidx = 0; sidx < nlive; ++sidx)
+          a0 = fmaf(__ldg(dn + (int64_t)sidx * P.nd + j), n < HD_N ? sA[sidx][n] : sD[sidx][HD_N], a0);
+      }
+      part[HD_PART + idx] = (a0 + a1) + (a2 + a3);
+    }
+  }
 }
 
-// out[e] = sum over CTAs (ascending) of partials[cta][e];  out layout = HD_PART
-__global__ void __launch_bounds__(256) head_reduce_kernel(const float* __restrict__ partials, int n_part, float inv_B,
-                                                          float* __restrict__ dW2, float* __restrict__ db2,
-                                                          float* __restrict__ dw3, float* __restrict__ db1,
-                                                          float* __restrict__ loss, float* __restrict__ dscal) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= HD_PART) return;
+// out[e] = sum over the CTAs' partials, fixed association (run-to-run identical): CTA = 32 columns x 8 row groups,
+// group r adds rows r, r + 8, ... in order, then the 8 group sums are added in order.
+__global__ void __launch_bounds__(256) head_reduce_kernel(const float* __restrict__ partials, int n_part, int stride,
+                                                          int nd, float inv_B, float* __restrict__ dW2,
+                                                          float* __restrict__ db2, float* __restrict__ dw3,
+                                                          float* __restrict__ db1, float* __restrict__ loss,
+                                                          float* __restrict__ dscal, float* __restrict__ dW1_dense,
+                                                          float* __restrict__ dlin_dense) {
+  __shared__ float sm[8][33];
+  const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + c;
   float acc = 0.f;
-  for (int c = 0; c < n_part; ++c) acc += partials[(int64_t)c * HD_PART + e];
+  if (e < stride)
+    for (int p = r; p < n_part; p += 8) acc += partials[(int64_t)p * stride + e];
+  sm[r][c] = acc;
+  __syncthreads();
+  if (r != 0 || e >= stride) return;
+#pragma unroll
+  for (int q = 1; q < 8; ++q) acc += sm[q][c];
   if (e < HD_N * HD_N) dW2[e] = acc;
   else if (e < HD_N * HD_N + HD_N) db2[e - HD_N * HD_N] = acc;
   else if (e < HD_N * HD_N + 2 * HD_N) dw3[e - HD_N * HD_N - HD_N] = acc;
   else if (e < HD_N * HD_N + 3 * HD_N) db1[e - HD_N * HD_N - 2 * HD_N] = acc;
   else if (e == HD_N * HD_N + 3 * HD_N) loss[0] = acc * inv_B;
   else if (e == HD_N * HD_N + 3 * HD_N + 1) dscal[0] = acc;  // db3 = dw0 = sum_b g_b
+  else if (e >= HD_PART && e < HD_PART + nd * (HD_N + 1)) {
+    const int idx = e - HD_PART, j = idx / (HD_N + 1), n = idx - j * (HD_N + 1);
+    if (n < HD_N) dW1_dense[j * HD_N + n] = acc;
+    else dlin_dense[j] = acc;
+  }
 }
+
+static int head_part_stride(int nd) { return (HD_PART + nd * (HD_N + 1) + 3) & ~3; }
 
 }  // namespace rm
 
@@ -229,32 +283,38 @@ extern "C" {
 
 int rm_deepfm_head_supported(int32_t N1, int32_t N2) { return (N1 == rm::HD_N && N2 == rm::HD_N) ? 1 : 0; }
 
-size_t rm_deepfm_head_workspace_bytes(int64_t B) {
-  if (B <= 0) return 256;
-  return (size_t)rm::ceil_div(B, rm::HD_THREADS) * rm::HD_PART * sizeof(float);
+size_t rm_deepfm_head_workspace_bytes(int64_t B, int32_t n_dense) {
+  if (B <= 0 || n_dense < 0) return 256;
+  return (size_t)rm::ceil_div(B, rm::HD_THREADS) * rm::head_part_stride(n_dense) * sizeof(float);
 }
 
 int rm_deepfm_head(const float* y1, const float* fm, const float* lin, const float* w0, const float* W2,
-                   const float* b2, const float* w3, const float* b3, const float* labels, int64_t B, int32_t N1,
-                   int32_t N2, int32_t act, int32_t task, float grad_scale, float* logit, float* pred, float* loss,
-                   float* g1, float* g, float* dW2, float* db2, float* dw3, float* dscal, float* db1, void* workspace,
+                   const float* b2, const float* w3, const float* b3, const float* labels, const float* dense,
+                   int32_t n_dense, int64_t B, int32_t N1, int32_t N2, int32_t act, int32_t task, float grad_scale,
+                   float* logit, float* pred, float* loss, float* g1, float* g, float* dW2, float* db2, float* dw3,
+                   float* dscal, float* db1, float* dW1_dense, float* dlin_dense, void* workspace,
                    size_t workspace_bytes, void* stream) {
   using namespace rm;
   RM_CHECK_ARG(y1 && fm && lin && w0 && W2 && b2 && w3 && b3, "null pointer");
-  RM_CHECK_ARG(B >= 0 && (task == 0 || task == 1), "bad argument");
+  RM_CHECK_ARG(B >= 0 && (task == 0 || task == 1) && n_dense >= 0, "bad argument");
   RM_UNSUPPORTED(rm_deepfm_head_supported(N1, N2), "the fused head is built for hidden_units = (32, 32)");
   RM_UNSUPPORTED(act == RM_ACT_IDENTITY || act == RM_ACT_RELU || act == RM_ACT_LEAKY_RELU, "activation kind");
   RM_UNSUPPORTED(aligned16(y1) && (!g1 || aligned16(g1)), "rows must be 16-byte aligned");
   if (B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  const bool with_dense = labels && dense && n_dense > 0;
   HeadParams P;
   P.y1 = y1; P.fm = fm; P.lin = lin; P.w0 = w0; P.W2 = W2; P.b2 = b2; P.w3 = w3; P.b3 = b3; P.labels = labels;
   P.logit = logit; P.pred = pred; P.g1 = g1; P.g = g; P.partials = (float*)workspace; P.B = B; P.act = act; P.task = task;
+  P.dense = with_dense ? dense : nullptr;
+  P.nd = with_dense ? n_dense : 0;
+  P.part_stride = head_part_stride(P.nd);
   P.inv_B = grad_scale / (float)B;
   const int grid = (int)ceil_div(B, HD_THREADS);
   if (labels) {
     RM_CHECK_ARG(loss && g1 && g && dW2 && db2 && dw3 && dscal && db1 && workspace, "null output pointer");
-    const size_t need = rm_deepfm_head_workspace_bytes(B);
+    RM_CHECK_ARG(!with_dense || (dW1_dense && dlin_dense), "null output pointer (dense-feature gradients)");
+    const size_t need = (size_t)grid * P.part_stride * sizeof(float);
     if (workspace_bytes < need) {
       set_error("rm_deepfm_head: workspace %zu < required %zu", workspace_bytes, need);
       return RM_E_WORKSPACE;
@@ -265,8 +325,9 @@ int rm_deepfm_head(const float* y1, const float* fm, const float* lin, const flo
   else head_kernel<RM_ACT_IDENTITY><<<grid, HD_THREADS, 0, st>>>(P);
   RM_LAUNCH_CHECK();
   if (labels) {
-    head_reduce_kernel<<<(int)ceil_div(HD_PART, 256), 256, 0, st>>>((const float*)workspace, grid, 1.f / (float)B, dW2,
-                                                                    db2, dw3, db1, loss, dscal);
+    head_reduce_kernel<<<(int)ceil_div(P.part_stride, 32), 256, 0, st>>>((const float*)workspace, grid, P.part_stride,
+                                                                         P.nd, 1.f / (float)B, dW2, db2, dw3, db1, loss,
+                                                                         dscal, dW1_dense, dlin_dense);
     RM_LAUNCH_CHECK();
   }
   return 0;

@@ -746,7 +746,7 @@ def tower_plan(ids, table_offsets, total_rows, unit: int = TOWER_UNIT, status=No
 
 
 def tower_bwd_update(table, scal, plan: TowerPlan, g1, S, g_fm, g_lin, W1, opt: int, lr: float, l2: float = 0.0,
-                     update: bool = True, debug: bool = False, status=None):
+                     update: bool = True, debug: bool = False, status=None, out=None):
     """Fused sparse backward + optimizer update (in place on ``table`` / ``scal``).  Returns dW1[:m*k] [m*k, N1]
     (and, with ``debug``, the summed gradient rows / k=1 gradients at the sorted position closing each segment)."""
     _dev_check(g1)
@@ -760,7 +760,11 @@ def tower_bwd_update(table, scal, plan: TowerPlan, g1, S, g_fm, g_lin, W1, opt: 
     assert W1.shape[0] >= m * k and W1.shape[1] == N1
     assert g_lin is None or (g_lin.is_contiguous() and g_lin.numel() == n_s)
     dev = g1.device
-    dW1 = torch.empty(m * k, N1, dtype=torch.float32, device=dev)
+    if out is not None:  # write dW1[:m*k] straight into the caller's (contiguous) buffer
+        assert out.shape == (m * k, N1) and out.is_contiguous() and out.dtype == torch.float32
+        dW1 = out
+    else:
+        dW1 = torch.empty(m * k, N1, dtype=torch.float32, device=dev)
     out_rows = out_scal = None
     if debug:
         out_rows = torch.zeros(plan.sorted_pos.numel(), k, dtype=torch.float32, device=dev)
@@ -796,9 +800,10 @@ def deepfm_head_supported(N1: int, N2: int) -> bool:
     return bool(_C.lib.rm_deepfm_head_supported(int(N1), int(N2)))
 
 
-def deepfm_head(y1, fm, lin, w0, W2, b2, w3, b3, labels, act: int, task: int, grad_scale: float = 1.0):
+def deepfm_head(y1, fm, lin, w0, W2, b2, w3, b3, labels, act: int, task: int, grad_scale: float = 1.0, dense=None):
     """labels None: forward only -> (logit, pred).  Otherwise -> dict with logit, pred, loss [1] and the gradients
-    g1 [B,N1], g [B], dW2, db2, dw3, dscal [1] (= db3 = dw0), db1 - all scaled by ``grad_scale``."""
+    g1 [B,N1], g [B], dW2, db2, dw3, dscal [1] (= db3 = dw0), db1 - all scaled by ``grad_scale`` - and, with the
+    samples' ``dense`` features [B, n_dense], dW1_dense [n_dense, N1] = dense^T g1 and dlin_dense [n_dense] = dense^T g."""
     _dev_check(y1)
     B, N1 = y1.shape
     N2 = W2.shape[1]
@@ -808,17 +813,26 @@ def deepfm_head(y1, fm, lin, w0, W2, b2, w3, b3, labels, act: int, task: int, gr
         assert t.is_contiguous() and t.dtype == torch.float32
     logit, pred = f(B), f(B)
     if labels is None:
-        _C.call("rm_deepfm_head", _p(y1), _p(fm), _p(lin), _p(w0), _p(W2), _p(b2), _p(w3), _p(b3), None, B, N1, N2, act,
-                task, 1.0, _p(logit), _p(pred), None, None, None, None, None, None, None, None, None, 0, _stream())
+        _C.call("rm_deepfm_head", _p(y1), _p(fm), _p(lin), _p(w0), _p(W2), _p(b2), _p(w3), _p(b3), None, None, 0, B, N1, N2,
+                act, task, 1.0, _p(logit), _p(pred), None, None, None, None, None, None, None, None, None, None, None, 0,
+                _stream())
         return logit, pred
     labels = labels.to(torch.float32).contiguous()
+    nd = 0
+    if dense is not None:
+        dense = _f32c(dense, "dense").contiguous()
+        assert dense.dim() == 2 and dense.shape[0] == B
+        nd = dense.shape[1]
     out = dict(logit=logit, pred=pred, loss=f(1), g1=f(B, N1), g=f(B), dW2=f(N1, N2), db2=f(N2), dw3=f(N2), dscal=f(1),
                db1=f(N1))
-    ws_bytes = _C.lib.rm_deepfm_head_workspace_bytes(B)
+    if nd:
+        out["dW1_dense"], out["dlin_dense"] = f(nd, N1), f(nd)
+    ws_bytes = _C.lib.rm_deepfm_head_workspace_bytes(B, nd)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    _C.call("rm_deepfm_head", _p(y1), _p(fm), _p(lin), _p(w0), _p(W2), _p(b2), _p(w3), _p(b3), _p(labels), B, N1, N2, act,
-            task, float(grad_scale), _p(logit), _p(pred), _p(out["loss"]), _p(out["g1"]), _p(out["g"]), _p(out["dW2"]),
-            _p(out["db2"]), _p(out["dw3"]), _p(out["dscal"]), _p(out["db1"]), _p(ws), ws_bytes, _stream())
+    _C.call("rm_deepfm_head", _p(y1), _p(fm), _p(lin), _p(w0), _p(W2), _p(b2), _p(w3), _p(b3), _p(labels),
+            _p(dense) if nd else None, nd, B, N1, N2, act, task, float(grad_scale), _p(logit), _p(pred), _p(out["loss"]),
+            _p(out["g1"]), _p(out["g"]), _p(out["dW2"]), _p(out["db2"]), _p(out["dw3"]), _p(out["dscal"]), _p(out["db1"]),
+            _p(out.get("dW1_dense")), _p(out.get("dlin_dense")), _p(ws), ws_bytes, _stream())
     return out
 
 

@@ -187,7 +187,9 @@ class DeepFM(DeepModel):
                 y1, fm_logit, lin_raw = tower
                 w0, W2, b2, w3, b3, act = head
                 loss, logit, _ = HeadFunction.apply(y1, fm_logit, lin_raw, w0, W2, b2, w3, b3, inputs.y, act,
-                                                    0 if self.task == "classification" else 1)
+                                                    0 if self.task == "classification" else 1, inputs.dense,
+                                                    getattr(self, "_tower_side", None),
+                                                    getattr(self, "_unit_loss_grad", False))
                 self.final_logit = logit.reshape(-1, 1)
                 for t in self._l2_terms():
                     loss = loss + t

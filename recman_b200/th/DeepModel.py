@@ -274,20 +274,25 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
         fused = getattr(self, "_fused_opt", None)
         if fused is not None and (layer.l2_reg or linear.l2_reg or getattr(table, "rm_l2_touched", 0.0)):
             fused = None
+        # side channel head kernel -> tower backward of this step (autograd.TowerSide); the model's loss hands it to
+        # HeadFunction when the fused head runs
+        from ..autograd import TowerSide
+
+        side = self._tower_side = TowerSide() if torch.is_grad_enabled() else None
         if sharded:
             from .dist import P2PTowerFunction
 
             if scal_fwd is not scal:
                 raise NotImplementedError("row-sharded tables: inference-time feature weights are not supported")
             y1, fm, lin = P2PTowerFunction.apply(table, scal, bias_param, W_lin, W1, b1, self.shard, self._status(),
-                                                 inputs.sparse_ids, dense, fused, torch.is_grad_enabled())
+                                                 inputs.sparse_ids, dense, fused, torch.is_grad_enabled(), side)
             if add_w0:
                 lin = lin + self.variables[f"{linear.prefix}linear_w0"]
             return y1, fm, lin
         from ..autograd import TowerFunction
 
         y1, fm, lin = TowerFunction.apply(table, scal, scal_fwd, bias_param, W_lin, W1, b1, lay.runs[0].offsets, total,
-                                          self._status(), inputs.sparse_ids, dense, fused, torch.is_grad_enabled())
+                                          self._status(), inputs.sparse_ids, dense, fused, torch.is_grad_enabled(), side)
         if add_w0:
             lin = lin + self.variables[f"{linear.prefix}linear_w0"]
         return y1, fm, lin
@@ -514,6 +519,9 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
 
     def _eager_step(self, inputs: DataInputs):
         self._fused_opt = self._fused_opt_config()
+        # one GPU: this method backpropagates d(loss) = 1 itself, so a loss kernel that already holds its gradients
+        # (HeadFunction) need not scale them
+        self._unit_loss_grad = self.shard is None
         try:
             loss = self._loss(inputs)
             if self.shard is not None:
@@ -522,6 +530,7 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
                 loss.backward()
         finally:
             self._fused_opt = None
+            self._unit_loss_grad = False
         self.optimizer_step()
         return loss.detach()
 

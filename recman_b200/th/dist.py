@@ -408,7 +408,7 @@ class P2PTowerFunction(Function):
 
     @staticmethod
     def forward(ctx, table, scal, bias_param, W_lin, W1, b1, plan: ShardPlan, status, ids, dense, fused_opt,
-                grad_mode=True):
+                grad_mode=True, side=None):
         from .. import ops
 
         b, m = ids.shape
@@ -446,6 +446,7 @@ class P2PTowerFunction(Function):
         ctx.plan, ctx.status, ctx.fused_opt = plan, status, fused_opt
         ctx.table, ctx.scal, ctx.W_lin = table, scal, W_lin
         ctx.n_dense = n_dense
+        ctx.side = side
         ctx.save_for_backward(S, dense, W1)
         ctx.b, ctx.m, ctx.k = b, m, k
         ctx.set_materialize_grads(False)
@@ -470,16 +471,23 @@ class P2PTowerFunction(Function):
         glin_all = torch.empty(W * b, dtype=torch.float32, device=dev)
         _all_gather_many([(S_all, S), (g1_all, g1), (gfm_all, g_fm), (glin_all, g_lin)], plan.group)
         total = plan.total_local
-        if ctx.n_dense:
-            ctx.W_lin.rm_dense_tail = (total, dense.t() @ g_lin)  # replicated: all-reduced by the optimizer
+        # gradients that need no embedding rows: from the head kernel of the same step when it left them (TowerSide)
+        side_db1, side_dW1d, side_dlind = ctx.side.take() if ctx.side is not None else (None, None, None)
+        if dy1 is None or dlin is None or (ctx.n_dense and (side_dW1d is None or side_dlind is None)):
+            side_db1 = None
+        if ctx.n_dense:  # replicated: all-reduced by the optimizer
+            ctx.W_lin.rm_dense_tail = (total, side_dlind if side_db1 is not None else dense.t() @ g_lin)
         kind, lr = ctx.fused_opt
         tp, ctx.tp = ctx.tp, None
         dW1 = torch.empty(W1.shape, dtype=torch.float32, device=dev)
-        dW1[: m * k] = ops.tower_bwd_update(ctx.table.data, ctx.scal[:total], tp, g1_all, S_all, gfm_all, glin_all, W1.data,
-                                            kind, lr, status=ctx.status)
+        ops.tower_bwd_update(ctx.table.data, ctx.scal[:total], tp, g1_all, S_all, gfm_all, glin_all, W1.data, kind, lr,
+                             status=ctx.status, out=dW1[: m * k])
         if ctx.n_dense:
-            torch.mm(dense.t(), g1, out=dW1[m * k :])
-        return (None, None, None, None, dW1, g1.sum(0)) + (None,) * 6
+            if side_db1 is not None:
+                dW1[m * k :] = side_dW1d
+            else:
+                torch.mm(dense.t(), g1, out=dW1[m * k :])
+        return (None, None, None, None, dW1, side_db1 if side_db1 is not None else g1.sum(0)) + (None,) * 7
 
 
 def allreduce_dense(grads: List[torch.Tensor], group=None) -> None:

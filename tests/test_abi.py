@@ -41,7 +41,7 @@ def test_ctypes_binding_covers_the_header(built_lib):
     from recman_b200 import _C
 
     assert sorted(_C.EXPORTS) == declared_symbols()
-    assert _C.lib.rm_version() == 3
+    assert _C.lib.rm_version() == 4
 
 
 def test_argument_validation_without_a_gpu(built_lib):

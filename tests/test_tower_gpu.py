@@ -319,6 +319,15 @@ def test_deepfm_head_forward_backward(act, task, B):
                            b3.cuda(), y.cuda(), _C.ACT_KINDS[act], 0 if task == "classification" else 1)
     for k in out:
         assert torch.equal(out[k], out2[k]), k
+    # with the samples' dense features: the first layer's / first-order term's gradients that involve them
+    nd = 13
+    dense = torch.randn(B, nd, generator=g)
+    out3 = ops.deepfm_head(y1.cuda(), fm.cuda(), lin.cuda(), w0.cuda(), W2.cuda(), b2.cuda(), w3.reshape(-1).cuda(),
+                           b3.cuda(), y.cuda(), _C.ACT_KINDS[act], 0 if task == "classification" else 1, dense=dense.cuda())
+    for k in out:
+        assert torch.equal(out[k], out3[k]), k
+    assert_close(out3["dW1_dense"], dense.double().t() @ Y1.grad, atol_scale=1e-5, msg="dW1_dense")
+    assert_close(out3["dlin_dense"], dense.double().t() @ FM.grad, atol_scale=1e-5, msg="dlin_dense")
 
 
 def test_c5_shape_rows_indices_and_gradients():
