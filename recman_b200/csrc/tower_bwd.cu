@@ -265,7 +265,8 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
   tc_fence_after();
   const uint32_t tmem_base = lds32(tmem_slot);
   bool ok = true;
-  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+  // (L2 eviction hints were measured and dropped: evict_first on the row stream costs 2-3 % at every world size, with
+  // or without evict_last on the per-sample operands)
 
   TileIter it;
   it.upf = P.upf;
@@ -326,8 +327,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
         const int r = rgx + 8 * i;
         const bool live = r < cnt;
         const uint32_t key = live ? lds32(ms + 4u * (r + 1)) : 0u;
-        cp_async16_hint(x_hi(s) + xoff + (uint32_t)i * 1024u, P.table + (int64_t)key * BK_K + 4 * cx, live ? 16u : 0u,
-                        pol_stream);
+        cp_async16(x_hi(s) + xoff + (uint32_t)i * 1024u, P.table + (int64_t)key * BK_K + 4 * cx, live ? 16u : 0u);
       }
       if (P.scal) {  // the row's (bias, weight) pair rides with the gather instead of stalling the epilogue
         const bool live = tid < cnt;
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
         gn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < cnt) {
           const int32_t b = (int32_t)lds32(mst + 4u * (130 + r));
-          gn[i] = ldg128_hint(P.g1 + (int64_t)b * BK_N1 + 4 * cg, pol_keep);
+          gn[i] = __ldg(reinterpret_cast<const float4*>(P.g1 + (int64_t)b * BK_N1 + 4 * cg));
         }
       }
     };
@@ -492,9 +492,9 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
         const int32_t b = (int32_t)lds32(mst + 4u * (130 + j));
         const float4* Sp = reinterpret_cast<const float4*>(P.S + (int64_t)b * BK_K + 4 * CPT * h);
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) Sv[c] = ldg128_hint(Sp + c, pol_keep);
-        gf = ldg32_hint(P.g_fm + b, pol_keep);
-        if (h == 0 && P.g_lin) gl = ldg32_hint(P.g_lin + b, pol_keep);
+        for (int c = 0; c < CPT; ++c) Sv[c] = __ldg(Sp + c);
+        gf = __ldg(P.g_fm + b);
+        if (h == 0 && P.g_lin) gl = __ldg(P.g_lin + b);
       }
     };
     int Y = 0, G = 0, tin = 0;
@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
           const uint32_t wk = lds32(wb + 4u * (uint32_t)(r0 + (BK_EPI / 16) * i));
           if (wk != TW_NONE) {
             const float4 v = lds128(xs + so0 + (uint32_t)i * ((BK_EPI / 16) * 128u));
-            stg128_hint(P.table + (int64_t)wk * BK_K + 4 * qc, v, pol_stream);
+            st4(P.table + (int64_t)wk * BK_K + 4 * qc, v);
           }
         }
       }

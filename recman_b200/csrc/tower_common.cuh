@@ -12,40 +12,6 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, u
 __device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
 }
-// L2 eviction policies: the gathered table rows stream through once per kernel (evict_first), the per-sample operands
-// of the backward (S, g1, g_fm, g_lin: ~25 MB re-read once per field) must survive that stream (evict_last)
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ void cp_async16_hint(uint32_t dst_smem, const void* src, uint32_t src_bytes, uint64_t pol) {
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst_smem), "l"(src),
-               "r"(src_bytes), "l"(pol)
-               : "memory");
-}
-__device__ __forceinline__ float4 ldg128_hint(const void* p, uint64_t pol) {
-  float4 v;
-  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ float ldg32_hint(const void* p, uint64_t pol) {
-  float v;
-  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ void stg128_hint(void* p, float4 v, uint64_t pol) {
-  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
-               "f"(v.w), "l"(pol)
-               : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

@@ -431,12 +431,12 @@ class P2PTowerFunction(Function):
             # this rank's all-reduce could not complete before every rank had entered it.
             ids32 = torch.where((ids >= 0) & (ids < 2 ** 31), ids, torch.full_like(ids, -1)).to(torch.int32)
             gids = torch.empty(W * b, m, dtype=torch.int32, device=dev)
-            side = ops.side_stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
+            sst = ops.side_stream()
+            sst.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(sst):
                 dist.all_gather_into_tensor(gids, ids32, group=plan.group)
-            ids32.record_stream(side)
-            gids.record_stream(side)
+            ids32.record_stream(sst)
+            gids.record_stream(sst)
             n_cap = plan.capacity(b)
             ctx.tp = ops.tower_shard_plan(gids, W, plan.rank, plan.feat_sizes_on(dev), plan.offsets_on(dev), total, n_cap,
                                           (n_cap + m - 1) // m, status=status, side=True, fork=False)
