@@ -41,7 +41,9 @@ constexpr int BK_PRODUCERS = 128;
 //   BK_FASTPATH: tiles of singleton segments release their gather stage before the update math and store rows straight
 //                from registers - 0.80 ms against 0.72 ms with the staged, coalesced write-back;
 //   BK_PREFETCH: next tile's S rows requested one tile ahead - the 32 extra live registers spill (0.88 ms);
-//   BK_NH = 4  : four threads per position - per-position bookkeeping replicated, 0.78 .. 1.06 ms.
+//   BK_NH = 4  : four threads per position - per-position bookkeeping replicated, 0.78 .. 1.06 ms;
+//   (not kept) a register-free `prefetch.global.L1` of the next tile's S rows: 0.714 vs 0.705 ms - the ~28 KB of L1 left
+//   beside 227 KB of shared memory do not hold a tile's 32 KB of S rows.
 constexpr bool BK_FASTPATH = false;
 #ifndef RM_BK_PREFETCH
 #define RM_BK_PREFETCH 0
