@@ -223,6 +223,31 @@ def cin_flops_per_step(w, B, k):
     return total
 
 
+def measure_tf32_peak(dev, n=8192, iters=20):
+    """Dense TF32 tensor-core throughput of this GPU, measured live: cuBLAS TF32 GEMM n^3 (a library call used ONLY as
+    the denominator of the CIN kernels' issued-MMA fraction; BASELINE.md section 2 promised a measured figure)."""
+    a = torch.randn(n, n, device=dev)
+    b = torch.randn(n, n, device=dev)
+    c = torch.empty(n, n, device=dev)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        for _ in range(3):
+            torch.mm(a, b, out=c)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            torch.mm(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    del a, b, c
+    return 2.0 * n ** 3 * iters / (ms * 1e-3) / 1e12
+
+
 def measure(args, wname, world, rank, local_rank, dev, primary=True):
     """Build the workload's model, time it (device-resident and end-to-end) and return the JSON-able record.
     `primary` adds the CPU / library baselines; secondary workloads (other_workloads) are timed more briefly."""
@@ -396,12 +421,17 @@ def measure(args, wname, world, rank, local_rank, dev, primary=True):
             passes = 3 if args.cin_precision == "3xtf32" else 1
             dom = "rm_cin_layer_bwd" if bwd_ms >= fwd_ms else "rm_cin_layer_fwd"
             ach = kernels[dom]["tflops"]
+            try:
+                tf32_peak, tf32_src = measure_tf32_peak(dev), "measured in this run: cuBLAS TF32 GEMM 8192^3 x 20"
+            except Exception as exc:  # the denominator only: fall back to half the bf16 figure
+                tf32_peak, tf32_src = tpeak / 2, f"assumed = bf16 / 2 ({type(exc).__name__})"
             roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s",
                         "frac": round(ach / tpeak, 4), "peak_source": "measured dense bf16, sustained (MEASURED_PEAKS.json)"
                         if peaks else "fallback 1376 TFLOP/s", "traffic": (traffic.get(dom) or {}).get("bytes"),
                         "traffic_source": (traffic.get(dom) or {}).get("source"),
                         "mma_passes": passes, "issued_tflops": round(ach * passes, 1),
-                        "frac_of_tf32_peak_issued": round(ach * passes / (tpeak / 2), 4),
+                        "tf32_peak_tflops": round(tf32_peak, 1), "tf32_peak_source": tf32_src,
+                        "frac_of_tf32_peak_issued": round(ach * passes / tf32_peak, 4),
                         "avg_launch_ms": kernels[dom]["avg_ms"], "alg_flops_per_step": kernels[dom]["alg_flops_per_step"]}
         elif cand:
             _, dom = max(cand)

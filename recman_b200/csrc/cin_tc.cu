@@ -27,6 +27,10 @@
 // CTA (tile, split) accumulates its k'' range in TMEM and writes the raw partial sums; cin_splitk_finish_kernel adds
 // the splits in order in fp32 round-to-nearest (deterministic), then bias + activation.  One split = the fused epilogue.
 //
+// (Measured alternative: one CTA running its tile's splits one after the other, adding each drained accumulator to an
+// L2-resident running sum - no partial tensors through HBM, but the producer warps are also the epilogue warps, so
+// synthesis and MMAs stall at every split boundary: forward 3.12 ms per C3 step against 2.04 ms with (tile, split) CTAs.)
+//
 // Every mbarrier wait is bounded: a pipeline bug sets *status and lets the kernel drain instead of hanging.
 #include "tc_common.cuh"
 
