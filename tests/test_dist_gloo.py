@@ -93,6 +93,91 @@ def _worker(rank, world, port, sizes, k, b, out_dir):
         dist.destroy_process_group()
 
 
+def _tower_worker(rank, world, port, sizes, k, N1, b, out_dir):
+    """The data flow of the row-sharded fused tower (th/dist.py:P2PTowerFunction) restated on CPU: ids and the
+    per-SAMPLE operands (g1, S, g_fm) are all-gathered, every owner forms the gradient rows of the positions it owns
+    itself (dx = g1 . W1_f^T, FM term from S and its own row) and sums duplicates - no gradient row crosses ranks.
+    Must equal this rank's shard of the dense gradient of the concatenated global batch."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from recman_b200.th.dist import ShardPlan, _all_gather_many
+
+    try:
+        m = len(sizes)
+        g = torch.Generator().manual_seed(0)  # same on every rank
+        tables = [torch.randn(v, k, generator=g, dtype=torch.float64) for v in sizes]
+        W1 = torch.randn(m * k, N1, generator=g, dtype=torch.float64) * 0.1
+        plan = ShardPlan(sizes, world, rank)
+        local = torch.zeros(plan.total_local, k, dtype=torch.float64)
+        for f in range(m):
+            rows = plan.local_rows_of(f)
+            local[plan.local_offsets[f] : plan.local_offsets[f] + rows.numel()] = tables[f][rows]
+        gi = torch.Generator().manual_seed(100 + rank)
+        ids = torch.stack([torch.randint(0, v, (b,), generator=gi) for v in sizes], 1)
+        ids[:3] = 0  # duplicates inside a batch and across ranks
+        x = torch.stack([tables[f][ids[:, f]] for f in range(m)], 1)  # [b, m, k] (the forward reads rows from their owners)
+        S = x.sum(1)
+        g1 = torch.randn(b, N1, generator=gi, dtype=torch.float64)
+        g_fm = torch.randn(b, generator=gi, dtype=torch.float64)
+        # the step's collectives: ids as int32 + one grouped all-gather of the per-sample operands
+        ids32 = ids.to(torch.int32)
+        gids = torch.empty(world * b, m, dtype=torch.int32)
+        S_all, g1_all, gfm_all = (torch.empty(world * b, k, dtype=torch.float64), torch.empty(world * b, N1, dtype=torch.float64),
+                                  torch.empty(world * b, dtype=torch.float64))
+        dist.all_gather_into_tensor(gids, ids32)
+        _all_gather_many([(S_all, S), (g1_all, g1), (gfm_all, g_fm)])
+        assert torch.equal(gids[rank * b : (rank + 1) * b], ids32) and torch.equal(S_all[rank * b : (rank + 1) * b], S)
+        # owner side: positions in ascending global position gp = sample * m + f (rank-major samples)
+        shard_grad = np.zeros((plan.total_local, k))
+        dW1_part = np.zeros((m * k, N1))
+        gid = gids.numpy().astype(np.int64)
+        for sample in range(world * b):
+            for f in range(m):
+                i = gid[sample, f]
+                if i % world != rank:
+                    continue
+                lr = plan.local_offsets[f] + i // world
+                row = local[lr].numpy()
+                dx = g1_all[sample].numpy() @ W1[f * k : (f + 1) * k].numpy().T
+                shard_grad[lr] += dx + gfm_all[sample].item() * (S_all[sample].numpy() - row)
+                dW1_part[f * k : (f + 1) * k] += np.outer(row, g1_all[sample].numpy())
+        # reference: dense gradient of the global tables over the concatenated batch
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        dense = np.zeros((int(offs[-1]), k))
+        dW1_ref = np.zeros((m * k, N1))
+        for r in range(world):
+            gr = torch.Generator().manual_seed(100 + r)
+            ids_r = torch.stack([torch.randint(0, v, (b,), generator=gr) for v in sizes], 1)
+            ids_r[:3] = 0
+            x_r = torch.stack([tables[f][ids_r[:, f]] for f in range(m)], 1)
+            S_r = x_r.sum(1)
+            g1_r = torch.randn(b, N1, generator=gr, dtype=torch.float64)
+            gfm_r = torch.randn(b, generator=gr, dtype=torch.float64)
+            dx_r = (g1_r @ W1.T).reshape(b, m, k) + gfm_r[:, None, None] * (S_r[:, None, :] - x_r)
+            for f in range(m):
+                np.add.at(dense, offs[f] + ids_r[:, f].numpy(), dx_r[:, f].numpy())
+            dW1_ref += x_r.reshape(b, m * k).numpy().T @ g1_r.numpy()
+        for f in range(m):
+            rows_f = plan.local_rows_of(f).numpy()
+            np.testing.assert_allclose(shard_grad[plan.local_offsets[f] : plan.local_offsets[f] + len(rows_f)],
+                                       dense[offs[f] + rows_f], rtol=1e-10, atol=1e-10)
+        # the owners' dW1 partials add up to the global dW1 (they join the dense all-reduce)
+        t = torch.from_numpy(dW1_part)
+        dist.all_reduce(t)
+        np.testing.assert_allclose(t.numpy(), dW1_ref, rtol=1e-10, atol=1e-10)
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_tower_dataflow_gloo(tmp_path, world):
+    sizes = [11, 1, 40, 3]
+    mp.spawn(_tower_worker, args=(world, _free_port(), sizes, 4, 3, 9, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_routing_gloo(tmp_path, world):
     sizes = [11, 1, 40, 7]
