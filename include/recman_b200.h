@@ -375,6 +375,10 @@ int rm_segment_reduce_p2p_update(const float* const* G, const float* gscal, int3
  * dW1[:m*k] = x^T @ g1.  k = 64, N1 = 32.  out_rows / out_scal (nullable): summed
  * gradient row / (bias, weight) gradient written at the sorted position that closes its
  * segment (tests); opt == RM_OPT_NONE skips the update.
+ * unit_bounds holds m*(upf+1) cuts (upf = rm_tower_units_per_field(B, unit)) followed by ONE flag
+ * word the plan sets when some row collects more than 32 positions of the batch (skewed ids): the
+ * backward then runs its variant that sums long runs warp-cooperatively (same ascending order:
+ * bit-identical results, ~2x faster under Zipf ids).  Allocate m*(upf+1) + 1 int32.
  * ------------------------------------------------------------------------- */
 int rm_tower_supported(int32_t m, int32_t k, int32_t n_dense, int32_t N1);
 size_t rm_tower_fwd_workspace_bytes(int32_t m, int32_t k, int32_t N1);

@@ -56,6 +56,7 @@ constexpr int BK_NH = RM_BK_NH;              // epilogue threads per position (e
 constexpr int BK_EPI = 128 * BK_NH;
 constexpr int BK_THREADS = 128 + 32 + BK_EPI;  // 4 producer warps, 1 MMA warp, 4 * BK_NH epilogue warps
 constexpr int BK_DRAIN = 4;  // tiles per TMEM accumulation group of GEMM 2
+constexpr int BK_WALK = 6;   // positions a segment leader adds by itself before the warp takes the run over
 constexpr uint32_t BK_XT = 32768, BK_GT = 16384, BK_STAGE = BK_XT;  // a gather stage holds the x tile only
 constexpr uint32_t BK_META = 1088;  // key[130] (prev, 128, next) + b[128], padded
 
@@ -86,6 +87,22 @@ __device__ __forceinline__ int32_t lower_bound_u32(const uint32_t* a, int32_t lo
 
 // field_bounds[f] = first sorted position of field f (field_bounds[m] = number of valid positions);
 // unit_bounds[f*(upf+1) + i] = the i-th cut of field f moved forward to the next segment head.
+// *flag = 1 when some table row collects more than BK_HOT_RUN positions of the batch (skewed ids: "hot rows"), found by
+// comparing sorted keys BK_HOT_RUN apart; the backward then runs its variant with warp-cooperative run summation.
+// Both variants add a run's positions in the same ascending order: the flag selects speed, never results.
+constexpr int BK_HOT_RUN = 32;
+// launched behind the bounds kernel (which zeroes the flag): n_valid = field_bounds[m], the entries before the sentinels
+__global__ void __launch_bounds__(256) tower_hot_flag_kernel(const uint32_t* __restrict__ keys,
+                                                             const int32_t* __restrict__ field_bounds, int m,
+                                                             int32_t* __restrict__ flag) {
+  const int32_t n_valid = field_bounds[m];
+  bool hot = false;
+  for (int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * BK_HOT_RUN; p + BK_HOT_RUN < n_valid;
+       p += (int64_t)gridDim.x * blockDim.x * BK_HOT_RUN)
+    hot = hot || keys[p] == keys[p + BK_HOT_RUN];
+  if (__any_sync(0xffffffffu, hot) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
 __global__ void __launch_bounds__(1024) tower_bounds_kernel(const uint32_t* __restrict__ keys, int32_t N,
                                                             const int64_t* __restrict__ offs, int m, int unit, int upf,
                                                             int32_t* __restrict__ field_bounds,
@@ -107,6 +124,7 @@ __global__ void __launch_bounds__(1024) tower_bounds_kernel(const uint32_t* __re
     }
     unit_bounds[idx] = p;
   }
+  if (threadIdx.x == 0) unit_bounds[m * (upf + 1)] = 0;  // hot-row flag: set by tower_hot_flag_kernel
 }
 
 // the same with owner-local offsets [m] (no closing entry) and the total passed separately (row-sharded tables)
@@ -128,6 +146,7 @@ __global__ void __launch_bounds__(1024) tower_bounds_local_kernel(const uint32_t
     if (p > lo && p < hi && keys[p] == keys[p - 1]) p = lower_bound_u32(keys, p, hi, keys[p] + 1u);
     unit_bounds[idx] = p;
   }
+  if (threadIdx.x == 0) unit_bounds[m * (upf + 1)] = 0;  // hot-row flag: set by tower_hot_flag_kernel
 }
 
 // W1 field images for GEMM 1: B operand = W1_f (rows c < 64, K = n < 32), K-major.  Per field [hi|lo][64][128 B].
@@ -218,7 +237,59 @@ struct TileIter {
   }
 };
 
+// Long runs of one table row inside a tile (hot rows: thousands of positions of one batch on one row under skewed ids)
+// are summed by the whole warp: lane l owns column 32 h + l of the row (one 128-byte shared-memory row per position:
+// conflict-free), positions added in ascending order - bit-identical to the leader thread's walk, ~15x fewer cycles per
+// position.  `lm`: lanes whose position leads such a run and has already added the first BK_WALK members into its slot of
+// the x tile; on return that slot holds the sum over the run's part inside this tile, jj the first position behind it.
+__device__ __noinline__ void bk_sum_long_runs(uint32_t lm, uint32_t xs, uint32_t ms, uint32_t sc_base, int cnt, int h,
+                                              int q, int lane, uint32_t key, int& jj, float& asf, float& asl) {
+  while (lm) {
+    const int src = __ffs(lm) - 1;
+    lm &= lm - 1;
+    const int j0 = 32 * q + src;
+    const uint32_t key0 = __shfl_sync(0xffffffffu, key, src);
+    const int jb = __shfl_sync(0xffffffffu, jj, src);  // first position not yet added
+    __syncwarp();
+    int je = cnt;  // end of the run inside this tile
+    for (int base = jb; base < cnt; base += 32) {
+      const int pj = base + lane;
+      const uint32_t kk = pj < cnt ? lds32(ms + 4u * (pj + 1)) : TW_NONE;
+      const uint32_t mism = __ballot_sync(0xffffffffu, kk != key0);
+      if (mism) {
+        je = base + __ffs(mism) - 1;
+        break;
+      }
+    }
+    const uint32_t colb = xs + (uint32_t)h * 16384u + (uint32_t)(lane & 3) * 4u;
+    const uint32_t cq = (uint32_t)lane >> 2;
+    float acc = __uint_as_float(lds32(colb + (uint32_t)j0 * 128u + sw32b_chunk(cq, (uint32_t)j0)));
+    const float sf0 = __shfl_sync(0xffffffffu, asf, src), sl0 = __shfl_sync(0xffffffffu, asl, src);
+    float sacc = lane == 0 ? sf0 : sl0;  // lane 0: bias-gradient sum, lane 1: weight-gradient sum (h == 0 only)
+#pragma unroll 4
+    for (int p2 = jb; p2 < je; ++p2) {
+      acc += __uint_as_float(lds32(colb + (uint32_t)p2 * 128u + sw32b_chunk(cq, (uint32_t)p2)));
+      if (h == 0 && lane < 2) sacc += __uint_as_float(lds32(sc_base + 8u * p2 + 4u * lane));
+    }
+    sts32(colb + (uint32_t)j0 * 128u + sw32b_chunk(cq, (uint32_t)j0), __float_as_uint(acc));
+    const float sf = __shfl_sync(0xffffffffu, sacc, 0), sl = __shfl_sync(0xffffffffu, sacc, 1);
+    __syncwarp();
+    if (lane == src) {
+      if (h == 0) {
+        asf = sf;
+        asl = sl;
+      }
+      jj = je;
+    }
+  }
+}
+
+// COOP: the variant for batches with hot rows (flag behind the unit bounds, tower_hot_flag).  Both variants are launched;
+// the one the flag does not select returns at once.  (Compiled into one kernel the cooperative block costs the
+// uniform-id path 10 % although it never runs there.)
+template <bool COOP>
 __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwdParams P) {
+  if (BK_NH == 2 && (P.ub[P.m * (P.upf + 1)] != 0) != COOP) return;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   auto x_hi = [&](int s) { return base + (uint32_t)s * BK_STAGE; };
@@ -592,7 +663,10 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
       }
       named_bar_sync(3, BK_EPI);
       uint32_t wkey = TW_NONE;  // table row this position finished (its new values sit in the x tile)
-      if (valid && (is_head || j == 0)) {  // leader of a segment (or of its part inside this tile)
+      const bool leader = valid && (is_head || j == 0);  // leader of a segment (or of its part inside this tile)
+      int jj = j + 1;
+      bool long_run = false;
+      if (leader) {
         if (!is_head) {  // continues from the previous tile: the carried partial sum comes first (position order)
           const uint32_t cb = carry_base + (uint32_t)((Y + 1) & 1) * 256u + (uint32_t)(h * CPT) * 16u;
 #pragma unroll
@@ -606,9 +680,15 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
             asl = cs.y + asl;
           }
         }
-        int jj = j + 1;
         if (!is_tail) {
+          // short runs (the common case) are walked by their leader thread; a run that goes on past BK_WALK positions
+          // is summed by the whole warp below - same ascending order, one column per lane instead of 32 per thread
+          int steps = 0;
           while (jj < cnt && lds32(ms + 4u * (jj + 1)) == key) {
+            if (COOP && steps == BK_WALK) {
+              long_run = true;
+              break;
+            }
 #pragma unroll
             for (int c = 0; c < CPT; ++c) {
               const uint32_t cq = (uint32_t)(h * CPT + c);
@@ -621,8 +701,30 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
               asl += sv.y;
             }
             ++jj;
+            ++steps;
+          }
+          if (long_run) {  // hand the running sum to the warp through this position's slot of the (dead) x tile
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) sts128(xs + xo[c], gr[c]);
           }
         }
+      }
+      if (COOP && lds32(ms + 4u * 258u) != 0u) {  // the tile repeats a row somewhere (flag set by the producers)
+        const uint32_t lm = __ballot_sync(0xffffffffu, long_run);
+        if (lm) {  // rare: kept out of line so that the common path's register allocation is unaffected
+          int jj_io = jj;
+          float asf_io = asf, asl_io = asl;
+          bk_sum_long_runs(lm, xs, ms, sc_base, cnt, h, q, lane, key, jj_io, asf_io, asl_io);
+          if (long_run) {
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) gr[c] = lds128(xs + xo[c]);
+            jj = jj_io;
+            asf = asf_io;
+            asl = asl_io;
+          }
+        }
+      }
+      if (leader) {
         const bool closed = lds32(ms + 4u * (jj + 1)) != key;
         if (closed) {
           const int64_t opos = (int64_t)it.p0 + jj - 1;  // sorted position that closes the segment
@@ -851,7 +953,7 @@ size_t rm_tower_plan_workspace_bytes(int64_t N) {
 }
 
 // Sort the (table row, position) pairs of one batch and cut every field's range into work units.
-//   sorted_keys [N] uint32, sorted_pos [N] int32, field_bounds [m+1] int32, unit_bounds [m*(upf+1)] int32
+//   sorted_keys [N] uint32, sorted_pos [N] int32, field_bounds [m+1] int32, unit_bounds [m*(upf+1) + 1] int32 (cuts + hot-row flag)
 int rm_tower_plan(const int64_t* ids, const int64_t* table_offsets, int64_t B, int32_t m, int64_t total_rows,
                   int32_t unit, void* workspace, size_t workspace_bytes, uint32_t* sorted_keys, int32_t* sorted_pos,
                   int32_t* field_bounds, int32_t* unit_bounds, int32_t* status, void* stream) {
@@ -881,6 +983,9 @@ int rm_tower_plan(const int64_t* ids, const int64_t* table_offsets, int64_t B, i
   const int upf = rm_tower_units_per_field(B, unit);
   tower_bounds_kernel<<<1, 1024, (m + 1) * sizeof(int32_t), st>>>(sorted_keys, (int32_t)N, table_offsets, m, unit, upf,
                                                                   field_bounds, unit_bounds);
+  RM_LAUNCH_CHECK();
+  tower_hot_flag_kernel<<<grid_for(N / BK_HOT_RUN + 1, 256, 4), 256, 0, st>>>(sorted_keys, field_bounds, m,
+                                                                             unit_bounds + (size_t)m * (upf + 1));
   RM_LAUNCH_CHECK();
   return 0;
 }
@@ -948,6 +1053,9 @@ int rm_tower_shard_plan(const int32_t* gids, int64_t Ntot, int32_t m, int32_t W,
                                                                         (uint32_t)total_local, m, unit, upf, field_bounds,
                                                                         unit_bounds);
   RM_LAUNCH_CHECK();
+  tower_hot_flag_kernel<<<grid_for(N_cap / BK_HOT_RUN + 1, 256, 4), 256, 0, st>>>(sorted_keys, field_bounds, m,
+                                                                                 unit_bounds + (size_t)m * (upf + 1));
+  RM_LAUNCH_CHECK();
   return 0;
 }
 
@@ -989,10 +1097,16 @@ int rm_tower_bwd_update(float* table, float* scal, const uint32_t* sorted_keys, 
   P.g_fm = g_fm; P.g_lin = g_lin; P.wpack = wpack; P.slabs = slabs; P.out_rows = out_rows; P.out_scal = out_scal;
   P.status = status; P.m = m; P.upf = upf; P.n_units = m * upf;
 
-  RM_SMEM_ATTR_ONCE(BK_SMEM, tower_bwd_kernel);
+  RM_SMEM_ATTR_ONCE(BK_SMEM, tower_bwd_kernel<false>);
+  RM_SMEM_ATTR_ONCE(BK_SMEM, tower_bwd_kernel<true>);
   const int grid = P.n_units < RM_NUM_SMS ? P.n_units : RM_NUM_SMS;
-  tower_bwd_kernel<<<grid, BK_THREADS, BK_SMEM, st>>>(P);
+  // the plan's hot-row flag (device side) picks the variant: the other launch returns at once
+  tower_bwd_kernel<false><<<grid, BK_THREADS, BK_SMEM, st>>>(P);
   RM_LAUNCH_CHECK();
+  if (BK_NH == 2) {
+    tower_bwd_kernel<true><<<grid, BK_THREADS, BK_SMEM, st>>>(P);
+    RM_LAUNCH_CHECK();
+  }
   tower_dw_reduce_kernel<<<grid_for((int64_t)m * BK_K * BK_N1, 256, 8), 256, 0, st>>>(slabs, m, upf, dW1);
   RM_LAUNCH_CHECK();
   return 0;

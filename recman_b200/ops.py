@@ -737,7 +737,7 @@ def tower_plan(ids, table_offsets, total_rows, unit: int = TOWER_UNIT, status=No
     keys = torch.empty(N, dtype=torch.int32, device=dev)
     pos = torch.empty(N, dtype=torch.int32, device=dev)
     fb = torch.empty(m + 1, dtype=torch.int32, device=dev)
-    ub = torch.empty(m * (upf + 1), dtype=torch.int32, device=dev)
+    ub = torch.empty(m * (upf + 1) + 1, dtype=torch.int32, device=dev)  # + the hot-row flag
     ev = _launch_maybe_side(side, lambda: _C.call(
         "rm_tower_plan", _p(ids), _p(table_offsets), B, m, int(total_rows), unit, _p(ws), ws_bytes, _p(keys), _p(pos),
         _p(fb), _p(ub), _p(status), _stream(),
@@ -883,7 +883,7 @@ def tower_shard_plan(gids, W, rank, feat_sizes, local_offs, total_local, n_cap, 
     keys = torch.empty(n_cap, dtype=torch.int32, device=dev)
     pos = torch.empty(n_cap, dtype=torch.int32, device=dev)
     fb = torch.empty(m + 1, dtype=torch.int32, device=dev)
-    ub = torch.empty(m * (upf + 1), dtype=torch.int32, device=dev)
+    ub = torch.empty(m * (upf + 1) + 1, dtype=torch.int32, device=dev)  # + the hot-row flag
     n_own = torch.empty(1, dtype=torch.int32, device=dev)
     ev = _launch_maybe_side(side, lambda: _C.call(
         "rm_tower_shard_plan", _p(gids), Ntot, m, W, rank, _p(feat_sizes), _p(local_offs), int(total_local), n_cap,

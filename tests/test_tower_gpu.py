@@ -187,9 +187,13 @@ def test_tower_backward(case, opt):
     assert np.array_equal(pos, order.astype(np.int32)) and np.array_equal(keys, rows.reshape(-1)[order])
     fb = plan.field_bounds.cpu().numpy()
     assert np.array_equal(fb, np.arange(m + 1) * B)
-    ub = plan.unit_bounds.cpu().numpy()
+    ub_all = plan.unit_bounds.cpu().numpy()
+    ub, hot = ub_all[:-1], int(ub_all[-1])
     for p in ub:  # every cut sits on a segment head
         assert p in fb or keys[p] != keys[p - 1]
+    # the hot-row flag behind the cuts: some row holds more than 32 positions (sorted keys compared 32 apart)
+    probe = np.arange(0, len(keys) - 32, 32)
+    assert hot == int(np.any(keys[probe] == keys[probe + 32]))
 
     lr = 0.5 if opt == "gd" else 1e-3
     kind = _C.OPT_KINDS[opt]
