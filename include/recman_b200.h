@@ -48,6 +48,11 @@ extern "C" {
 #define RM_OPT_ADAGRAD 1
 #define RM_OPT_GD 2
 #define RM_OPT_NONE (-1) /* rm_tower_bwd_update only: compute gradients, leave the tables untouched */
+/* rm_tower_bwd_update `variant`: AUTO launches both kernel variants and lets the plan's hot-row flag pick one on the
+ * device; PLAIN / HOT launch one only (a caller that knows its id distribution).  Same results either way. */
+#define RM_TOWER_BWD_AUTO 0
+#define RM_TOWER_BWD_PLAIN 1
+#define RM_TOWER_BWD_HOT 2
 
 /* activation kinds for rm_cin_* : hparams/xDeepFM.py:29,33 (tf.nn.leaky_relu, alpha 0.2) */
 #define RM_ACT_IDENTITY 0
@@ -399,7 +404,7 @@ int rm_tower_bwd_update(float* table, float* scal, const uint32_t* sorted_keys,
                         const int32_t* sorted_pos, const int32_t* unit_bounds, const float* g1,
                         const float* S, const float* g_fm, const float* g_lin, const float* W1,
                         int64_t B, int32_t m, int32_t k, int32_t N1, int32_t unit, int32_t opt,
-                        float lr, float l2, float* dW1, float* out_rows, float* out_scal,
+                        float lr, float l2, int32_t variant, float* dW1, float* out_rows, float* out_scal,
                         int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 /* Row-sharded tables (row r of a table on rank r mod W at local row r div W) over NVLink peer memory:
  * rm_tower_fwd_p2p = rm_tower_fwd with every row read from its owner (tables / scals: HOST arrays of W device

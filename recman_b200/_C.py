@@ -113,8 +113,8 @@ _SIGS = {
     "rm_tower_bwd_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "rm_tower_bwd_update": (
         ctypes.c_int,
-        [P, P, P, P, P, P, P, P, P, P, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_float, P, P, P,
-         P, P, c_size_t, P]),
+        [P, P, P, P, P, P, P, P, P, P, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_float, c_int32,
+         P, P, P, P, P, c_size_t, P]),
     "rm_umma_probe": (ctypes.c_int, [P, P, c_int32, c_int32, P, P, P]),
     "rm_tower_fwd_p2p": (
         ctypes.c_int,

@@ -510,10 +510,12 @@ class TowerFunction(Function):
         if g_lin is not None and ctx.n_dense:
             ctx.W_lin.rm_dense_tail = (total, side_dlind if side_db1 is not None else dense.t() @ g_lin)
         if ctx.use_bk:
-            kind, lr = ctx.fused_opt
+            kind, lr = ctx.fused_opt[:2]
+            variant = ctx.fused_opt[2] if len(ctx.fused_opt) > 2 else 0
+            ctx.table.rm_hot_flag = plan.unit_bounds[-1:]  # device flag: does the batch hold hot rows (DeepModel reads it)
             dW1 = torch.empty(W1.shape, dtype=torch.float32, device=dev)
             ops.tower_bwd_update(ctx.table.data, ctx.scal[:total], plan, g1, S, g_fm, g_lin, W1.data, kind, lr,
-                                 status=ctx.status, out=dW1[: m * k])
+                                 status=ctx.status, out=dW1[: m * k], variant=variant)
             if ctx.n_dense:
                 if side_db1 is not None:
                     dW1[m * k :] = side_dW1d

@@ -200,6 +200,7 @@ struct TowerBwdParams {
   int32_t* status;
   OptParams o;
   int m, upf, n_units, do_update;
+  int force;  // run whatever the plan's hot-row flag says (the caller launched this variant only)
 };
 
 __device__ __forceinline__ void atomicOr_shared(uint32_t addr, uint32_t v) {
@@ -289,7 +290,7 @@ __device__ __noinline__ void bk_sum_long_runs(uint32_t lm, uint32_t xs, uint32_t
 // uniform-id path 10 % although it never runs there.)
 template <bool COOP>
 __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwdParams P) {
-  if (BK_NH == 2 && (P.ub[P.m * (P.upf + 1)] != 0) != COOP) return;
+  if (!P.force && (P.ub[P.m * (P.upf + 1)] != 0) != COOP) return;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   auto x_hi = [&](int s) { return base + (uint32_t)s * BK_STAGE; };
@@ -663,6 +664,80 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
       }
       named_bar_sync(3, BK_EPI);
       uint32_t wkey = TW_NONE;  // table row this position finished (its new values sit in the x tile)
+      if constexpr (!COOP) {
+      // ---- common variant (no hot rows in the batch): every segment leader walks its run itself
+      if (valid && (is_head || j == 0)) {  // leader of a segment (or of its part inside this tile)
+        if (!is_head) {  // continues from the previous tile: the carried partial sum comes first (position order)
+          const uint32_t cb = carry_base + (uint32_t)((Y + 1) & 1) * 256u + (uint32_t)(h * CPT) * 16u;
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) {
+            const float4 cv = lds128(cb + 16u * c);
+            gr[c].x = cv.x + gr[c].x; gr[c].y = cv.y + gr[c].y; gr[c].z = cv.z + gr[c].z; gr[c].w = cv.w + gr[c].w;
+          }
+          if (h == 0) {
+            const float2 cs = lds64f(carry_sc + (uint32_t)((Y + 1) & 1) * 8u);
+            asf = cs.x + asf;
+            asl = cs.y + asl;
+          }
+        }
+        int jj = j + 1;
+        if (!is_tail) {
+          while (jj < cnt && lds32(ms + 4u * (jj + 1)) == key) {
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+              const uint32_t cq = (uint32_t)(h * CPT + c);
+              const float4 v = lds128(xs + (cq >> 3) * 16384u + (uint32_t)jj * 128u + sw32b_chunk(cq & 7u, (uint32_t)jj));
+              gr[c].x += v.x; gr[c].y += v.y; gr[c].z += v.z; gr[c].w += v.w;
+            }
+            if (h == 0) {
+              const float2 sv = lds64f(sc_base + 8u * jj);
+              asf += sv.x;
+              asl += sv.y;
+            }
+            ++jj;
+          }
+        }
+        const bool closed = lds32(ms + 4u * (jj + 1)) != key;
+        if (closed) {
+          const int64_t opos = (int64_t)it.p0 + jj - 1;  // sorted position that closes the segment
+          if (P.out_rows) {
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) st4(P.out_rows + opos * BK_K + 4 * (h * CPT + c), gr[c]);
+          }
+          if (P.do_update) {  // new row -> this thread's slot of the (dead) x tile; stored 256 B at a time below
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+              float4 nv;
+              nv.x = opt_update(xr[c].x, gr[c].x, P.o);
+              nv.y = opt_update(xr[c].y, gr[c].y, P.o);
+              nv.z = opt_update(xr[c].z, gr[c].z, P.o);
+              nv.w = opt_update(xr[c].w, gr[c].w, P.o);
+              sts128(xs + xo[c], nv);
+            }
+            wkey = key;
+          }
+          if (h == 0) {
+            if (P.out_scal) *reinterpret_cast<float2*>(P.out_scal + 2 * opos) = make_float2(asf, asl);
+            if (P.scal && P.do_update) {
+              const float2 sold = lds64f(scal_st + (uint32_t)s * 1024u + 8u * j);
+              float2 nv;
+              nv.x = opt_update(sold.x, asf, P.o);
+              nv.y = P.g_lin ? opt_update(sold.y, asl, P.o) : sold.y;
+              *reinterpret_cast<float2*>(P.scal + 2 * (int64_t)key) = nv;
+            }
+          }
+        } else {
+          const uint32_t cb = carry_base + (uint32_t)(Y & 1) * 256u + (uint32_t)(h * CPT) * 16u;
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) sts128(cb + 16u * c, gr[c]);
+          if (h == 0) {
+            sts32(carry_sc + (uint32_t)(Y & 1) * 8u, __float_as_uint(asf));
+            sts32(carry_sc + (uint32_t)(Y & 1) * 8u + 4u, __float_as_uint(asl));
+          }
+        }
+      }
+      } else {
+      // ---- hot-row variant: runs longer than BK_WALK are handed to the whole warp
       const bool leader = valid && (is_head || j == 0);  // leader of a segment (or of its part inside this tile)
       int jj = j + 1;
       bool long_run = false;
@@ -724,7 +799,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
           }
         }
       }
-      if (leader) {
+            if (leader) {
         const bool closed = lds32(ms + 4u * (jj + 1)) != key;
         if (closed) {
           const int64_t opos = (int64_t)it.p0 + jj - 1;  // sorted position that closes the segment
@@ -763,6 +838,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) tower_bwd_kernel(const TowerBwd
             sts32(carry_sc + (uint32_t)(Y & 1) * 8u + 4u, __float_as_uint(asl));
           }
         }
+      }
       }
       if (P.do_update) {
         // coalesced write-back: 16 lanes per finished row store its 256 bytes contiguously
@@ -1068,11 +1144,12 @@ size_t rm_tower_bwd_workspace_bytes(int64_t B, int32_t m, int32_t unit) {
 int rm_tower_bwd_update(float* table, float* scal, const uint32_t* sorted_keys, const int32_t* sorted_pos,
                         const int32_t* unit_bounds, const float* g1, const float* S, const float* g_fm,
                         const float* g_lin, const float* W1, int64_t B, int32_t m, int32_t k, int32_t N1, int32_t unit,
-                        int32_t opt, float lr, float l2, float* dW1, float* out_rows, float* out_scal, int32_t* status,
-                        void* workspace, size_t workspace_bytes, void* stream) {
+                        int32_t opt, float lr, float l2, int32_t variant, float* dW1, float* out_rows, float* out_scal,
+                        int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace rm;
   RM_CHECK_ARG(table && sorted_keys && sorted_pos && unit_bounds && g1 && S && g_fm && W1 && dW1 && workspace,
                "null pointer");
+  RM_CHECK_ARG(variant >= RM_TOWER_BWD_AUTO && variant <= RM_TOWER_BWD_HOT, "unknown variant");
   RM_CHECK_ARG(B > 0 && m > 0 && unit >= BK_TILE, "bad shape");
   RM_UNSUPPORTED(k == BK_K && N1 == BK_N1, "the fused tower backward is built for k = 64, first hidden layer = 32");
   RM_UNSUPPORTED(aligned16(table) && aligned16(g1) && aligned16(S) && aligned16(workspace) &&
@@ -1100,10 +1177,15 @@ int rm_tower_bwd_update(float* table, float* scal, const uint32_t* sorted_keys, 
   RM_SMEM_ATTR_ONCE(BK_SMEM, tower_bwd_kernel<false>);
   RM_SMEM_ATTR_ONCE(BK_SMEM, tower_bwd_kernel<true>);
   const int grid = P.n_units < RM_NUM_SMS ? P.n_units : RM_NUM_SMS;
-  // the plan's hot-row flag (device side) picks the variant: the other launch returns at once
-  tower_bwd_kernel<false><<<grid, BK_THREADS, BK_SMEM, st>>>(P);
-  RM_LAUNCH_CHECK();
-  if (BK_NH == 2) {
+  // AUTO: both variants are launched and the plan's hot-row flag (device side) picks one - the other returns at once
+  // (~14 us).  A caller that knows what its ids look like (e.g. from the previous steps' flags) launches one variant only;
+  // either variant is correct on any input, they differ in speed.
+  P.force = variant != RM_TOWER_BWD_AUTO || BK_NH != 2;
+  if (variant != RM_TOWER_BWD_HOT || BK_NH != 2) {
+    tower_bwd_kernel<false><<<grid, BK_THREADS, BK_SMEM, st>>>(P);
+    RM_LAUNCH_CHECK();
+  }
+  if (variant != RM_TOWER_BWD_PLAIN && BK_NH == 2) {
     tower_bwd_kernel<true><<<grid, BK_THREADS, BK_SMEM, st>>>(P);
     RM_LAUNCH_CHECK();
   }

@@ -746,8 +746,10 @@ def tower_plan(ids, table_offsets, total_rows, unit: int = TOWER_UNIT, status=No
 
 
 def tower_bwd_update(table, scal, plan: TowerPlan, g1, S, g_fm, g_lin, W1, opt: int, lr: float, l2: float = 0.0,
-                     update: bool = True, debug: bool = False, status=None, out=None):
-    """Fused sparse backward + optimizer update (in place on ``table`` / ``scal``).  Returns dW1[:m*k] [m*k, N1]
+                     update: bool = True, debug: bool = False, status=None, out=None, variant: int = 0):
+    """Fused sparse backward + optimizer update (in place on ``table`` / ``scal``).  ``variant``: 0 = both kernel variants
+    launched, the plan's hot-row flag picks one on the device; 1 = plain only; 2 = hot-row variant only (same results).
+    Returns dW1[:m*k] [m*k, N1]
     (and, with ``debug``, the summed gradient rows / k=1 gradients at the sorted position closing each segment)."""
     _dev_check(g1)
     B, m = plan.B, plan.m
@@ -775,7 +777,8 @@ def tower_bwd_update(table, scal, plan: TowerPlan, g1, S, g_fm, g_lin, W1, opt: 
     _C.call(
         "rm_tower_bwd_update", _p(table), _p(scal), _p(plan.sorted_keys),
         _p(plan.sorted_pos), _p(plan.unit_bounds), _p(g1), _p(S), _p(g_fm), _p(g_lin), _p(W1), B, m, k, N1, plan.unit,
-        opt if update else -1, float(lr), float(l2), _p(dW1), _p(out_rows), _p(out_scal), _p(status), _p(ws), ws_bytes,
+        opt if update else -1, float(lr), float(l2), int(variant), _p(dW1), _p(out_rows), _p(out_scal), _p(status), _p(ws),
+        ws_bytes,
         _stream(),
     )
     if debug:

@@ -274,6 +274,8 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
         fused = getattr(self, "_fused_opt", None)
         if fused is not None and (layer.l2_reg or linear.l2_reg or getattr(table, "rm_l2_touched", 0.0)):
             fused = None
+        if fused is not None:  # + which variant(s) of the backward kernel to launch (compile_step sets a hint)
+            fused = tuple(fused[:2]) + (int(getattr(self, "_bk_variant", 0)),)
         # side channel head kernel -> tower backward of this step (autograd.TowerSide); the model's loss hands it to
         # HeadFunction when the fused head runs
         from ..autograd import TowerSide
@@ -500,10 +502,22 @@ class DeepModel(BaseEstimator, TransformerMixin, ABC):
                 self._eager_step(st)
         cur.wait_stream(side)
         torch.cuda.synchronize()
+        # fused tower backward: the eager steps launch both kernel variants and the plan's device flag picks one; the
+        # captured step launches only the one the warm-up batch needed (hot rows under skewed ids or not).  Either variant
+        # is correct for any batch - a later change of the id distribution costs speed, not results.
+        self._bk_variant = 0
+        for p_ in self.variables.values():
+            flag = getattr(p_, "rm_hot_flag", None)
+            if flag is not None:
+                self._bk_variant = 2 if int(flag.item()) else 1
+                break
         graph = torch.cuda.CUDAGraph()
         before = _ops.launch_count()
-        with torch.cuda.graph(graph):
-            loss = self._eager_step(st)
+        try:
+            with torch.cuda.graph(graph):
+                loss = self._eager_step(st)
+        finally:
+            self._bk_variant = 0
         self._graph_launches = _ops.launch_count() - before
         self._graph, self._graph_inputs, self._graph_loss = graph, st, loss
         return self

@@ -477,11 +477,13 @@ class P2PTowerFunction(Function):
             side_db1 = None
         if ctx.n_dense:  # replicated: all-reduced by the optimizer
             ctx.W_lin.rm_dense_tail = (total, side_dlind if side_db1 is not None else dense.t() @ g_lin)
-        kind, lr = ctx.fused_opt
+        kind, lr = ctx.fused_opt[:2]
+        variant = ctx.fused_opt[2] if len(ctx.fused_opt) > 2 else 0
         tp, ctx.tp = ctx.tp, None
+        ctx.table.rm_hot_flag = tp.unit_bounds[-1:]
         dW1 = torch.empty(W1.shape, dtype=torch.float32, device=dev)
         ops.tower_bwd_update(ctx.table.data, ctx.scal[:total], tp, g1_all, S_all, gfm_all, glin_all, W1.data, kind, lr,
-                             status=ctx.status, out=dW1[: m * k])
+                             status=ctx.status, out=dW1[: m * k], variant=variant)
         if ctx.n_dense:
             if side_db1 is not None:
                 dW1[m * k :] = side_dW1d
