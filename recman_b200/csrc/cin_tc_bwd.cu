@@ -20,7 +20,6 @@ namespace rm {
 constexpr int TB_STAGES = 3;
 constexpr int TB_THREADS = 320;   // kernel A: 8 producer/epilogue warps + MMA warp + W loader warp
 constexpr int TB_THREADS_B = 544;  // kernel B: 8 A-producer/epilogue warps + 8 B-producer warps + MMA warp
-constexpr int TB_SLAB_DEFAULT = 512;  // rows of (b,d) accumulated in TMEM per CTA in kernel B (RM_TUNE_CIN_SLAB)
 
 // ------------------------------------------------------------------------------------------------ pack W'' (kernel A)
 // image (qg, st): NMMA rows (j -> k'' = qg*NMMA + j) x 128 B; chunk c of row j at (c ^ (j&7)).

@@ -26,10 +26,8 @@ def timeit(fn, n=20):
 
 res = {}
 fwd_bytes = B * (m * (8 + 8 * k + 8) + 8 * nd + 4 * k + 8)
-for var in os.environ.get("KB_GATHER_VARIANTS", "0,1,2,3").split(","):
-    os.environ["RM_TUNE_GATHER_FM"] = var
-    t = timeit(lambda i: ops.gather_fm_fwd(table, bias_t, lin_t, offs, ids_pool[i % 4], dense, lin_dense, status=st))
-    res[f"gather_fm_fwd v{var}"] = (round(t, 4), round(fwd_bytes / t / 1e6, 1))
+t = timeit(lambda i: ops.gather_fm_fwd(table, bias_t, lin_t, offs, ids_pool[i % 4], dense, lin_dense, status=st))
+res["gather_fm_fwd"] = (round(t, 4), round(fwd_bytes / t / 1e6, 1))
 t = timeit(lambda i: ops.gather(table, offs, ids_pool[i % 4], status=st))
 res["gather_fwd"] = (round(t, 4), round(B * m * (8 + 8 * k) / t / 1e6, 1))
 t = timeit(lambda i: ops.segment_plan(ids_pool[i % 4], offs, m * rows))
@@ -40,16 +38,15 @@ x, fm, lin, S = ops.gather_fm_fwd(table, bias_t, lin_t, offs, ids_pool[0], dense
 ld = x.shape[1]
 dx = torch.randn(B, ld, device=dev); g_fm = torch.randn(B, device=dev); g_lin = torch.randn(B, device=dev)
 bwd_bytes = B * m * (4 + 8 * k) + B * (4 * k + 8) + nu * (4 * k + 8)
-for var in os.environ.get("KB_SEG_VARIANTS", "1,2,3,4").split(","):
-    os.environ["RM_TUNE_SEGRED"] = var
+for var in ("",):  # (the kernel variants once swept here through environment knobs are gone: one configuration each)
     t = timeit(lambda i: ops.emb_fm_bwd(dx, x, ld, S, g_fm, g_lin, plans[i % 4], k, True, True, True))
-    res[f"emb_fm_bwd seg{var}"] = (round(t, 4), round(bwd_bytes / t / 1e6, 1))
+    res["emb_fm_bwd"] = (round(t, 4), round(bwd_bytes / t / 1e6, 1))
     grad = dx[:, : m * k].contiguous()
     t = timeit(lambda i: ops.segment_reduce(grad, plans[i % 4], k, ld=m * k))
-    res[f"segment_reduce seg{var}"] = (round(t, 4), round((B * m * (4 + 4 * k) + nu * (4 * k + 8)) / t / 1e6, 1))
+    res["segment_reduce"] = (round(t, 4), round((B * m * (4 + 4 * k) + nu * (4 * k + 8)) / t / 1e6, 1))
     upd_bytes = bwd_bytes - nu * (4 * k + 8) + nu * (8 + 8 * k + 16)  # uniq id + row r/w + bias/lin r/w per unique row
     t = timeit(lambda i: ops.emb_fm_bwd_update(dx, x, ld, S, g_fm, g_lin, plans[i % 4], k, table, bias_t, lin_t, 0, 1e-3))
-    res[f"emb_fm_bwd_update seg{var}"] = (round(t, 4), round(upd_bytes / t / 1e6, 1))
+    res["emb_fm_bwd_update"] = (round(t, 4), round(upd_bytes / t / 1e6, 1))
 rows_out, ob, ol = ops.emb_fm_bwd(dx, x, ld, S, g_fm, g_lin, plans[0], k, True, True, True)
 sg = ops.SparseGrad(plans[0].uniq_rows, rows_out, plans[0].n_unique)
 t = timeit(lambda i: ops.sparse_opt_step(table, sg, 0, 1e-3, 0.0))

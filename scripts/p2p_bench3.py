@@ -54,7 +54,6 @@ def main():
 
         def fm(tab, idt, fsz, loff, smode):
             def f():
-                os.environ["RM_TUNE_P2P_SCALAR"] = str(smode)
                 ops.gather_fm_fwd_p2p([tab], None, None, k, fsz, loff, idt, None, None)
             return f
 

@@ -30,14 +30,12 @@ def _shard(full, sizes, W):
 SIZES26 = [50, 7, 1000, 3, 200, 31, 2, 90, 1, 17, 400, 5, 64, 9, 300, 12, 77, 4, 128, 33, 6, 250, 19, 8, 500, 41]
 
 
-@pytest.mark.parametrize("variant", [0, 1])  # 0 = register-staged loads (default), 1 = cp.async deep queue
 @pytest.mark.parametrize("SIZES", [SIZES, SIZES26], ids=["m9", "m26"])
 @pytest.mark.parametrize("W", [1, 2, 4, 8])
 @pytest.mark.parametrize("k", [16, 64])
-def test_p2p_front_end_equals_single_table_front_end(W, k, SIZES, variant, monkeypatch):
+def test_p2p_front_end_equals_single_table_front_end(W, k, SIZES):
     from recman_b200 import ops
 
-    monkeypatch.setenv("RM_TUNE_P2P_ASYNC", str(variant))
     g = torch.Generator().manual_seed(W * 100 + k)
     total = sum(SIZES)
     m, B, n_dense = len(SIZES), 333, 5
