@@ -299,8 +299,8 @@ int rm_linear_bwd_weight(const float* x, int64_t ld, const float* g, int64_t B, 
                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------- *
- * (e') row-sharded tables over NVLink PEER MEMORY (W a power of two <= 8, one
- * NVSwitch box): the lookup and the gradient reduction read their rows straight
+ * (e') row-sharded tables over NVLink PEER MEMORY (any W <= 8, one NVSwitch box;
+ * powers of two use mask / shift, other sizes one integer division per id): the lookup and the gradient reduction read their rows straight
  * from the owning rank - no all-to-all, no pack/unpack pass, no host sync.
  *
  * rm_p2p_alloc: cudaMalloc + cudaIpcGetMemHandle (handle64: 64 host bytes to be

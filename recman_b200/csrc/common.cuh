@@ -61,6 +61,24 @@ void count_launch(int n = 1);
   } while (0)
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Row-sharded tables: global row `id` of a table lives on rank id mod W at local row id div W.  wshift >= 0: W is the
+// power of two 1 << wshift (mask / shift); wshift < 0: any other W (one integer division per id).
+inline int world_shift(int W) {
+  int s = 0;
+  while ((1 << s) < W) ++s;
+  return (1 << s) == W ? s : -1;
+}
+__host__ __device__ __forceinline__ void shard_of(int64_t id, int W, int wshift, int& owner, int64_t& local) {
+  if (wshift >= 0) {
+    owner = (int)(id & (((int64_t)1 << wshift) - 1));
+    local = id >> wshift;
+  } else {
+    const uint64_t q = (uint64_t)id / (uint32_t)W;
+    owner = (int)((uint64_t)id - q * (uint32_t)W);
+    local = (int64_t)q;
+  }
+}
 inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 

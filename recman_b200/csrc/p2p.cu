@@ -24,14 +24,13 @@ struct PeerTables {
 // one row group (LPR lanes) per sample; identical to gather_fm_kernel (gather.cu) except for the row address
 template <int LPR, int U, int MINB>
 __global__ void __launch_bounds__(256, MINB) gather_fm_p2p_kernel(
-    const PeerTables pt, int wshift, const int64_t* __restrict__ feat_sizes, const int64_t* __restrict__ local_offs,
+    const PeerTables pt, int W, int wshift, const int64_t* __restrict__ feat_sizes, const int64_t* __restrict__ local_offs,
     const int64_t* __restrict__ ids, const float* __restrict__ dense, const float* __restrict__ lin_dense, int n_dense,
     int64_t B, int m, int k, float* __restrict__ x, int64_t ld, float* __restrict__ fm_out, float* __restrict__ lin_out,
     float* __restrict__ sum_out, int32_t* status) {
   const int lir = threadIdx.x % LPR;
   const int k4 = k >> 2;
   const bool col_ok = lir < k4;
-  const int64_t wmask = ((int64_t)1 << wshift) - 1;
   const bool has_bias = pt.bias[0] != nullptr, has_lin = pt.lin[0] != nullptr;
   const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
   const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / LPR;
@@ -59,8 +58,9 @@ __global__ void __launch_bounds__(256, MINB) gather_fm_p2p_kernel(
             const int64_t id = my_ids[f];
             ok[u] = (id >= 0) && (id < feat_sizes[f]);
             if (ok[u]) {
-              owner[u] = (int)(id & wmask);
-              row[u] = local_offs[f] + (id >> wshift);
+              int64_t lr;
+              shard_of(id, W, wshift, owner[u], lr);
+              row[u] = local_offs[f] + lr;
             } else if (lir == 0 && status) {
               atomicOr(status, 1);
             }
@@ -171,7 +171,7 @@ int rm_gather_fm_fwd_p2p(const float* const* tables, const float* const* bias_ta
   RM_CHECK_ARG(B >= 0 && m > 0 && k > 0 && n_dense >= 0, "bad shape");
   RM_CHECK_ARG(n_dense == 0 || dense, "dense pointer missing");
   RM_CHECK_ARG(ld >= (int64_t)m * k + n_dense, "ld smaller than m*k+n_dense");
-  RM_UNSUPPORTED(W >= 1 && W <= RM_MAX_PEERS && (W & (W - 1)) == 0, "world size must be a power of two <= 8");
+  RM_UNSUPPORTED(W >= 1 && W <= RM_MAX_PEERS && true, "world size must be <= 8");
   RM_UNSUPPORTED(k % 4 == 0 && k <= 128, "fused front end needs k % 4 == 0 and k <= 128");
   RM_UNSUPPORTED(ld % 4 == 0 && aligned16(x) && (!sum_out || aligned16(sum_out)),
                  "fused front end needs 16-byte aligned rows (ld % 4 == 0)");
@@ -186,8 +186,7 @@ int rm_gather_fm_fwd_p2p(const float* const* tables, const float* const* bias_ta
     RM_CHECK_ARG(r >= W || !bias_tables || pt.bias[r], "null peer bias table");
     RM_CHECK_ARG(r >= W || !lin_tables || pt.lin[r], "null peer linear table");
   }
-  int wshift = 0;
-  while ((1 << wshift) < W) ++wshift;
+  const int wshift = world_shift(W);
   cudaStream_t st = (cudaStream_t)stream;
   const int lpr = pow2ceil_p(k / 4);
   // (a deep-queue cp.async variant of this kernel was measured SLOWER at W = 2 - 0.72 ms vs 0.54 ms: the NVLink reads are
@@ -195,7 +194,7 @@ int rm_gather_fm_fwd_p2p(const float* const* tables, const float* const* bias_ta
   const int grid = grid_for(B, 256 / (lpr > 32 ? 32 : lpr), 8);
 #define RM_GP(L)                                                                                                      \
   case L:                                                                                                             \
-    gather_fm_p2p_kernel<L, 4, 4><<<grid, 256, 0, st>>>(pt, wshift, feat_sizes, local_offsets, ids, dense, lin_dense,  \
+    gather_fm_p2p_kernel<L, 4, 4><<<grid, 256, 0, st>>>(pt, W, wshift, feat_sizes, local_offsets, ids, dense, lin_dense,  \
                                                         n_dense, B, m, k, x, ld, fm_out, lin_out, sum_out, status);        \
     break
   switch (lpr) {
@@ -205,7 +204,7 @@ int rm_gather_fm_fwd_p2p(const float* const* tables, const float* const* bias_ta
     RM_GP(8);
     RM_GP(16);
     default:
-      gather_fm_p2p_kernel<32, 4, 4><<<grid, 256, 0, st>>>(pt, wshift, feat_sizes, local_offsets, ids, dense, lin_dense,
+      gather_fm_p2p_kernel<32, 4, 4><<<grid, 256, 0, st>>>(pt, W, wshift, feat_sizes, local_offsets, ids, dense, lin_dense,
                                                            n_dense, B, m, k, x, ld, fm_out, lin_out, sum_out, status);
   }
 #undef RM_GP

@@ -584,15 +584,19 @@ struct OwnedBy {
   const int64_t* gids;
   const int64_t* feat_sizes;
   uint32_t m;
-  int64_t wmask, rank;
+  int W, wshift, rank;
   __host__ __device__ __forceinline__ bool operator()(const int32_t& i) const {
     const int64_t id = gids[i];
-    return id >= 0 && id < feat_sizes[(uint32_t)i % m] && (id & wmask) == rank;
+    if (!(id >= 0 && id < feat_sizes[(uint32_t)i % m])) return false;
+    int owner;
+    int64_t lr;
+    shard_of(id, W, wshift, owner, lr);
+    return owner == rank;
   }
 };
 
 __global__ void __launch_bounds__(256) shard_keys_kernel(const int64_t* __restrict__ gids,
-                                                         const int64_t* __restrict__ local_offs, uint32_t m,
+                                                         const int64_t* __restrict__ local_offs, uint32_t m, int W,
                                                          int wshift, const int32_t* __restrict__ own_gpos,
                                                          const int32_t* __restrict__ n_own, int32_t N_cap,
                                                          uint32_t sentinel, uint32_t* __restrict__ keys,
@@ -603,7 +607,10 @@ __global__ void __launch_bounds__(256) shard_keys_kernel(const int64_t* __restri
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N_cap; i += gridDim.x * blockDim.x) {
     if (i < n) {
       const int32_t gp = own_gpos[i];
-      keys[i] = (uint32_t)(local_offs[(uint32_t)gp % m] + (gids[gp] >> wshift));
+      int owner;
+      int64_t lr;
+      shard_of(gids[gp], W, wshift, owner, lr);
+      keys[i] = (uint32_t)(local_offs[(uint32_t)gp % m] + lr);
       pos[i] = gp;
     } else {
       keys[i] = sentinel;
@@ -655,7 +662,7 @@ static ShardPlanWs shard_plan_layout(int64_t Ntot, int64_t N_cap, void* base) {
   cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                   (const int32_t*)nullptr, (int32_t*)nullptr, (int)N_cap, 0, 32);
   thrust::counting_iterator<int32_t> counting(0);
-  OwnedBy own{nullptr, nullptr, 1, 0, 0};
+  OwnedBy own{nullptr, nullptr, 1, 1, 0, 0};
   cub::DeviceSelect::If(nullptr, sel1, counting, (int32_t*)nullptr, (int32_t*)nullptr, (int)Ntot, own);
   HeadOfLiveRun head{nullptr, nullptr, 0};
   cub::DeviceSelect::If(nullptr, sel2, counting, (int32_t*)nullptr, (int32_t*)nullptr, (int)N_cap, head);
@@ -831,7 +838,7 @@ int rm_shard_plan(const int64_t* gids, int64_t Ntot, int32_t m, int32_t W, int32
   RM_CHECK_ARG(gids && feat_sizes && local_offsets && workspace && sorted_gpos && seg_start && uniq_rows && n_unique &&
                    n_own, "null pointer");
   RM_CHECK_ARG(Ntot > 0 && m > 0 && N_cap > 0 && total_local > 0 && rank >= 0 && rank < W, "bad shape");
-  RM_UNSUPPORTED(W >= 1 && W <= RM_MAX_PEERS && (W & (W - 1)) == 0, "world size must be a power of two <= 8");
+  RM_UNSUPPORTED(W >= 1 && W <= RM_MAX_PEERS && true, "world size must be <= 8");
   RM_UNSUPPORTED(Ntot < ((int64_t)1 << 31) - 1 && N_cap <= Ntot, "W*B*m must be < 2^31 - 1 and N_cap <= W*B*m");
   RM_UNSUPPORTED(total_local < ((int64_t)1 << 31), "local rows must be < 2^31 (32-bit sort keys + sentinel)");
   cudaStream_t st = (cudaStream_t)stream;
@@ -840,17 +847,16 @@ int rm_shard_plan(const int64_t* gids, int64_t Ntot, int32_t m, int32_t W, int32
     set_error("rm_shard_plan: workspace %zu < required %zu", workspace_bytes, w.total);
     return RM_E_WORKSPACE;
   }
-  int wshift = 0;
-  while ((1 << wshift) < W) ++wshift;
+  const int wshift = world_shift(W);
   thrust::counting_iterator<int32_t> counting(0);
-  OwnedBy own{gids, feat_sizes, (uint32_t)m, (int64_t)(W - 1), (int64_t)rank};
+  OwnedBy own{gids, feat_sizes, (uint32_t)m, (int)W, wshift, (int)rank};
   size_t bytes = w.cub_bytes;
   RM_CUDA(cub::DeviceSelect::If(w.cub_temp, bytes, counting, w.own_gpos, n_own, (int)Ntot, own, st));
   count_launch();
   int end_bit = 1;
   while (end_bit < 31 && ((int64_t)1 << end_bit) < total_local) ++end_bit;
   const uint32_t sentinel = 1u << end_bit;
-  shard_keys_kernel<<<grid_for(N_cap, 256, 8), 256, 0, st>>>(gids, local_offsets, (uint32_t)m, wshift, w.own_gpos, n_own,
+  shard_keys_kernel<<<grid_for(N_cap, 256, 8), 256, 0, st>>>(gids, local_offsets, (uint32_t)m, (int)W, wshift, w.own_gpos, n_own,
                                                             (int32_t)N_cap, sentinel, w.keys_in, w.pos_in, status);
   RM_LAUNCH_CHECK();
   bytes = w.cub_bytes;

@@ -968,16 +968,20 @@ struct TowerOwned {
   const int32_t* gids;
   const int64_t* feat_sizes;
   uint32_t m;
-  int64_t wmask, rank;
+  int W, wshift, rank;
   __host__ __device__ __forceinline__ bool operator()(const int32_t& i) const {
     const int64_t id = gids[i];
-    return id >= 0 && id < feat_sizes[(uint32_t)i % m] && (id & wmask) == rank;
+    if (!(id >= 0 && id < feat_sizes[(uint32_t)i % m])) return false;
+    int owner;
+    int64_t lr;
+    shard_of(id, W, wshift, owner, lr);
+    return owner == rank;
   }
 };
 
 __global__ void __launch_bounds__(256) tower_shard_keys_kernel(const int32_t* __restrict__ gids,
                                                                const int64_t* __restrict__ local_offs, uint32_t m,
-                                                               int wshift, const int32_t* __restrict__ own_gpos,
+                                                               int W, int wshift, const int32_t* __restrict__ own_gpos,
                                                                const int32_t* __restrict__ n_own, int32_t N_cap,
                                                                uint32_t sentinel, uint32_t* __restrict__ keys,
                                                                int32_t* __restrict__ pos, int32_t* status) {
@@ -987,7 +991,10 @@ __global__ void __launch_bounds__(256) tower_shard_keys_kernel(const int32_t* __
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N_cap; i += gridDim.x * blockDim.x) {
     if (i < n) {
       const int32_t gp = own_gpos[i];
-      keys[i] = (uint32_t)(local_offs[(uint32_t)gp % m] + ((int64_t)gids[gp] >> wshift));
+      int owner;
+      int64_t lr;
+      shard_of((int64_t)gids[gp], W, wshift, owner, lr);
+      keys[i] = (uint32_t)(local_offs[(uint32_t)gp % m] + lr);
       pos[i] = gp;
     } else {
       keys[i] = sentinel;
@@ -1075,7 +1082,7 @@ size_t rm_tower_shard_plan_workspace_bytes(int64_t Ntot, int64_t N_cap) {
   cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                   (const int32_t*)nullptr, (int32_t*)nullptr, (int)N_cap, 0, 32);
   thrust::counting_iterator<int32_t> counting(0);
-  rm::TowerOwned own{nullptr, nullptr, 1, 0, 0};
+  rm::TowerOwned own{nullptr, nullptr, 1, 1, 0, 0};
   cub::DeviceSelect::If(nullptr, sel_bytes, counting, (int32_t*)nullptr, (int32_t*)nullptr, (int)Ntot, own);
   const size_t cubb = sort_bytes > sel_bytes ? sort_bytes : sel_bytes;
   return rm::align_up((size_t)Ntot * 4, 256) + 2 * rm::align_up((size_t)N_cap * 4, 256) + rm::align_up(cubb, 256) + 256;
@@ -1095,7 +1102,7 @@ int rm_tower_shard_plan(const int32_t* gids, int64_t Ntot, int32_t m, int32_t W,
                    unit_bounds && n_own, "null pointer");
   RM_CHECK_ARG(Ntot > 0 && m > 0 && N_cap > 0 && total_local > 0 && rank >= 0 && rank < W && unit >= BK_TILE && Bcap > 0,
                "bad shape");
-  RM_UNSUPPORTED(W >= 1 && W <= 8 && (W & (W - 1)) == 0, "world size must be a power of two <= 8");
+  RM_UNSUPPORTED(W >= 1 && W <= 8, "world size must be <= 8");
   RM_UNSUPPORTED(Ntot < ((int64_t)1 << 31) - 1 && N_cap <= Ntot, "W*B*m must be < 2^31 - 1 and N_cap <= W*B*m");
   RM_UNSUPPORTED(total_local < ((int64_t)1 << 31), "local rows must be < 2^31");
   const size_t need = rm_tower_shard_plan_workspace_bytes(Ntot, N_cap);
@@ -1110,17 +1117,16 @@ int rm_tower_shard_plan(const int32_t* gids, int64_t Ntot, int32_t m, int32_t W,
   int32_t* pos_in = (int32_t*)b; b += align_up((size_t)N_cap * 4, 256);
   void* cub_temp = (void*)b;
   size_t cub_bytes = (size_t)((char*)workspace + workspace_bytes - b);
-  int wshift = 0;
-  while ((1 << wshift) < W) ++wshift;
+  const int wshift = world_shift(W);
   thrust::counting_iterator<int32_t> counting(0);
-  TowerOwned own{gids, feat_sizes, (uint32_t)m, (int64_t)(W - 1), (int64_t)rank};
+  TowerOwned own{gids, feat_sizes, (uint32_t)m, (int)W, wshift, (int)rank};
   size_t bytes = cub_bytes;
   RM_CUDA(cub::DeviceSelect::If(cub_temp, bytes, counting, own_gpos, n_own, (int)Ntot, own, st));
   count_launch();
   int end_bit = 1;
   while (end_bit < 31 && ((int64_t)1 << end_bit) <= total_local) ++end_bit;
   const uint32_t sentinel = (uint32_t)total_local;  // sorts behind every owned row
-  tower_shard_keys_kernel<<<grid_for(N_cap, 256, 8), 256, 0, st>>>(gids, local_offsets_m1, (uint32_t)m, wshift, own_gpos,
+  tower_shard_keys_kernel<<<grid_for(N_cap, 256, 8), 256, 0, st>>>(gids, local_offsets_m1, (uint32_t)m, (int)W, wshift, own_gpos,
                                                                   n_own, (int32_t)N_cap, sentinel, keys_in, pos_in, status);
   RM_LAUNCH_CHECK();
   bytes = cub_bytes;

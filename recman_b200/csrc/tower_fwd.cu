@@ -142,7 +142,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tower_fwd_kernel(const TowerFwd
         if (id >= 0 && id < hi - lo) row = (uint32_t)(lo + id);
       } else if (id >= 0 && id < P.feat_sizes[f]) {
         // row-sharded tables: global row id lives on rank id mod W at local row id div W
-        row = ((uint32_t)(id & (P.W - 1)) << TF_ROW_BITS) | (uint32_t)(P.offs[f] + (id >> P.wshift));
+        int owner;
+        int64_t lr;
+        shard_of(id, P.W, P.wshift, owner, lr);
+        row = ((uint32_t)owner << TF_ROW_BITS) | (uint32_t)(P.offs[f] + lr);
       }
       if (row == TW_NONE && P.status) atomicOr(P.status, 1);
     }
@@ -397,7 +400,7 @@ static int tower_fwd_impl(const float* const* tables, const float* const* scals,
   RM_CHECK_ARG(n_dense == 0 || dense, "dense pointer missing");
   RM_CHECK_ARG(!x || ld >= (int64_t)m * k + n_dense, "ld smaller than m*k+n_dense");
   RM_UNSUPPORTED(rm_tower_supported(m, k, n_dense, N1), "tower kernels need k in {32, 64}, m <= 64, N1 <= 64");
-  RM_UNSUPPORTED(W >= 1 && W <= TF_MAX_PEERS && (W & (W - 1)) == 0, "world size must be a power of two <= 8");
+  RM_UNSUPPORTED(W >= 1 && W <= TF_MAX_PEERS && true, "world size must be <= 8");
   RM_CHECK_ARG(W == 1 || feat_sizes, "feat_sizes missing");
   RM_UNSUPPORTED((!x || (aligned16(x) && ld % 4 == 0)) && (!sum_out || aligned16(sum_out)) && aligned16(workspace),
                  "tower forward needs 16-byte aligned rows");
@@ -422,8 +425,7 @@ static int tower_fwd_impl(const float* const* tables, const float* const* scals,
                  "null / misaligned k=1 table");
   }
   P.W = W;
-  P.wshift = 0;
-  while ((1 << P.wshift) < W) ++P.wshift;
+  P.wshift = world_shift(W);
   P.feat_sizes = feat_sizes;
   P.offs = offs; P.ids = ids; P.dense = dense; P.lin_dense = lin_dense;
   P.lin_dense_stride = lin_dense_stride; P.wpack = wpack; P.W1 = W1; P.b1 = b1; P.x = x; P.ld = ld; P.y1 = y1;

@@ -14,7 +14,8 @@ lives on rank ``r mod W`` at local row ``r div W`` (cyclic: immune to id-range s
 The routing arithmetic (``ShardPlan``, ``build_exchange``) is pure torch and device agnostic so that it is
 tested on CPU with the gloo backend (tests/test_dist_gloo.py); the row movement is CUDA kernels + NCCL.
 
-Peer-memory mode (default when the world size is a power of two <= 8, i.e. one NVSwitch box; ``PeerMemory``,
+Peer-memory mode (default for any world size <= 8, i.e. one NVSwitch box; powers of two use mask / shift for the
+owner / local-row arithmetic, other sizes one integer division per id; ``PeerMemory``,
 ``P2PFrontEndFunction``): the tables and one gradient-row buffer per rank are cudaIpc-mapped into every rank, and
 
     forward   all-gather of the ids (13.6 MB per rank at C5; also the step's cross-rank barrier)
@@ -117,8 +118,8 @@ class ShardPlan:
 
     # ---- peer-memory mode -------------------------------------------------------------------------------
     def enable_peer_memory(self):
-        if self.world & (self.world - 1) or self.world > 8:
-            raise ValueError("peer-memory sharding needs a power-of-two world size <= 8 (one NVSwitch box)")
+        if self.world > 8:
+            raise ValueError("peer-memory sharding needs a world size <= 8 (one NVSwitch box)")
         self.peer = PeerMemory(self.world, self.rank, self.group)
         return self
 
@@ -508,13 +509,13 @@ def allreduce_dense(grads: List[torch.Tensor], group=None) -> None:
 def shard_model(model, world: int, rank: int, group=None, mode: str = "auto"):
     """Switch a recman.th model to row-sharded tables + DP dense layers (before its variables are created).
 
-    ``mode``: "p2p" (NVLink peer memory, power-of-two world <= 8), "a2a" (NCCL all-to-all exchange) or "auto"."""
+    ``mode``: "p2p" (NVLink peer memory, world <= 8), "a2a" (NCCL all-to-all exchange, any world) or "auto"."""
     if model.variables:
         raise RuntimeError("shard_model must be called before the first forward creates the variables")
     sizes = [f.feat_size for f in model.feat_dict.embedding_feats]
     model.shard = ShardPlan(sizes, world, rank, group)
     if mode == "auto":
-        mode = "p2p" if (world & (world - 1)) == 0 and world <= 8 and torch.cuda.is_available() else "a2a"
+        mode = "p2p" if world <= 8 and torch.cuda.is_available() else "a2a"
     if mode == "p2p":
         model.shard.enable_peer_memory()
     return model

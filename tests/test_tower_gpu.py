@@ -424,7 +424,7 @@ def _shard_tables(s, W):
     return sizes, loffs, total_local, tabs, scals
 
 
-@pytest.mark.parametrize("W", [2, 4, 8])
+@pytest.mark.parametrize("W", [2, 3, 4, 5, 8])
 def test_tower_forward_sharded_rows_from_their_owners(W):
     """rm_tower_fwd_p2p with the W shards living on one device: same outputs as the unsharded kernel, bit for bit
     (the rows are the same rows, wherever they live), including tables with fewer rows than ranks."""
@@ -445,7 +445,7 @@ def test_tower_forward_sharded_rows_from_their_owners(W):
     assert torch.equal(y1p, y1) and torch.equal(fmp, fm) and torch.equal(linp, lin) and torch.equal(Sp, S)
 
 
-@pytest.mark.parametrize("W", [2, 4])
+@pytest.mark.parametrize("W", [2, 3, 4])
 def test_tower_backward_sharded_owner_view(W):
     """Every owner runs rm_tower_shard_plan + rm_tower_bwd_update on its shard over the ids / per-sample operands of all
     W ranks (here: one device); together the shards receive the update the unsharded kernel applies to the full table,
