@@ -112,3 +112,75 @@ def test_cin_stack_against_golden(precision):
     for i in range(3):
         _close(variables[f"cin_filter_{i}"].grad, G[f"cin_dfilter_{i}"])
         _close(variables[f"cin_bias_{i}"].grad, G[f"cin_dbias_{i}"])
+
+
+# ----------------------------------------------------------------------------------------------- fused DeepFM tower
+GT = np.load(os.path.join(os.path.dirname(__file__), "golden", "tower_v1.npz"))
+
+
+def test_oracle_reproduces_golden_tower():
+    """tests/golden/tower_v1.npz is what the oracle computes today (any edit to oracle/ that moves a DeepFM logit,
+    gradient or update fails here)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(
+        "make_golden_tower", os.path.join(os.path.dirname(__file__), "golden", "make_golden_tower.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    d = mod.inputs()
+    for k_, v in d.items():
+        assert np.array_equal(GT[f"in_{k_}"], v.numpy()), k_
+    for k_, v in mod.expected(d).items():
+        np.testing.assert_allclose(v, GT[f"out_{k_}"], rtol=1e-12, atol=1e-14, err_msg=k_)
+
+
+@pytest.mark.gpu
+def test_tower_kernels_against_golden():
+    """rm_tower_fwd -> rm_deepfm_head -> rm_tower_plan -> rm_tower_bwd_update (GD step) through the C ABI against the
+    committed fp64 vectors: logits, loss and every gradient within 1e-5, updated tables within 1e-5."""
+    from recman_b200 import _C, ops
+
+    I = lambda n, dt=None: (torch.from_numpy(GT[f"in_{n}"]) if dt is None else torch.from_numpy(GT[f"in_{n}"]).to(dt)).cuda()
+    O = lambda n: torch.from_numpy(GT[f"out_{n}"])
+    K, B, ND, N1, N2 = (int(v) for v in GT["meta"])
+    sizes = GT["sizes"]
+    m = len(sizes)
+    total = int(sizes.sum())
+    offs = torch.from_numpy(np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)).cuda()
+    lr = float(GT["lr"][0])
+
+    def close(name, got, exp, scale=1e-5):
+        exp = exp.double()
+        torch.testing.assert_close(got.detach().cpu().double().reshape(exp.shape), exp, rtol=1e-5,
+                                   atol=scale * max(float(exp.abs().max()), 1e-30), msg=lambda m_: f"{name}: {m_}")
+
+    table, scal = I("table").clone(), I("scal").clone()
+    st = ops.new_status("cuda")
+    y1, fm, lin, S, _ = ops.tower_fwd(table, scal, offs, I("ids"), I("dense"), I("lin_dense"), I("W1"), I("b1"), status=st)
+    for n, got in (("y1", y1), ("fm", fm), ("lin", lin), ("S", S)):
+        close(n, got, O(n))
+    out = ops.deepfm_head(y1, fm, lin, I("w0"), I("W2"), I("b2"), I("w3").reshape(-1).contiguous(), I("b3"), I("y"),
+                          _C.ACT_KINDS["leaky_relu"], 0, dense=I("dense"))
+    close("logit", out["logit"], O("logit"))
+    close("loss", out["loss"], O("loss"))
+    for n, key in (("g1", "g1"), ("g", "g"), ("dW2", "dW2"), ("db2", "db2"), ("dw3", "dw3"), ("db3", "dscal"),
+                   ("dw0", "dscal"), ("db1", "db1"), ("dlin_dense", "dlin_dense")):
+        close(n, out[key], O(n))
+    close("dW1[dense rows]", out["dW1_dense"], O("dW1")[m * K :])
+    # backward over the sorted plan: gradients only, then the in-kernel GD update
+    plan = ops.tower_plan(I("ids"), offs, total, status=st)
+    keys = plan.sorted_keys.cpu().numpy().view(np.uint32).astype(np.int64)
+    closing = np.flatnonzero(np.append(keys[1:] != keys[:-1], True))
+    t0, s0 = table.clone(), scal.clone()
+    dW1, rows, sc = ops.tower_bwd_update(t0, s0, plan, out["g1"], S, out["g"], out["g"], I("W1"), _C.OPT_KINDS["gd"], lr,
+                                         update=False, debug=True, status=st)
+    close("dW1[embedding rows]", dW1, O("dW1")[: m * K])
+    close("summed gradient rows", rows.cpu()[closing], O("d_table")[keys[closing]])
+    close("k=1 gradients", sc.cpu()[closing], O("d_scal")[keys[closing]])
+    ops.tower_bwd_update(table, scal, plan, out["g1"], S, out["g"], out["g"], I("W1"), _C.OPT_KINDS["gd"], lr, status=st)
+    torch.cuda.synchronize()
+    assert int(st.item()) == 0
+    close("table after the GD step", table, O("table_gd"))
+    close("(bias, weight) after the GD step", scal, O("scal_gd"))
+    untouched = np.setdiff1d(np.arange(total), keys)
+    assert torch.equal(table.cpu()[untouched], torch.from_numpy(GT["in_table"])[untouched])
