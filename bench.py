@@ -205,6 +205,11 @@ def algorithmic_bytes(kind, B, m, k, n_dense, n_unique=None):
         # g_fm + g_lin 8; per unique row: table row written 4k, (bias, weight) read + written 16
         nu = n_unique if n_unique is not None else B * m
         return B * m * (8 + 4 * k) + B * (4 * 32 + 4 * k + 8) + nu * (4 * k + 16)
+    if kind == "rm_cross_fwd":
+        # the fused cross network reads the row and writes nothing but L dots + the logit: 2*4*d per sample
+        return B * 8 * (m * k + n_dense)
+    if kind == "rm_cross_bwd":
+        return B * 12 * (m * k + n_dense)  # x0 read, upstream gradient read, dx written: 3*4*d per sample
     # rm_sparse_opt_step is launched once per table kind (k = 64, 1, 1): its averaged time is not a single-kernel
     # figure, so it is listed without bytes
     return None
